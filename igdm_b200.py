@@ -1,0 +1,12 @@
+"""Import shim: registers the package directory ``imagegenerationdiffusionmodels.jl_b200/`` (whose
+name is not a valid Python identifier) as the importable package ``igdm_b200``."""
+import importlib.util
+import os
+import sys
+
+_PKG_DIR = os.path.join(os.path.dirname(os.path.abspath(__file__)), "imagegenerationdiffusionmodels.jl_b200")
+_spec = importlib.util.spec_from_file_location(
+    "igdm_b200", os.path.join(_PKG_DIR, "__init__.py"), submodule_search_locations=[_PKG_DIR])
+_mod = importlib.util.module_from_spec(_spec)
+sys.modules["igdm_b200"] = _mod
+_spec.loader.exec_module(_mod)

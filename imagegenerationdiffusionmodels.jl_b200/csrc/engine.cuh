@@ -1,0 +1,896 @@
+// Engine: owns all device state of one GPU (parameter arena, packed weights, activation
+// buffers, streams, CUDA graphs, NCCL communicator) and sequences the kernels of
+//   - the U-Net forward in train / inference mode  (/root/reference/src/train_brain.jl:159-179)
+//   - the backward pass + Adam                      (train_brain.jl:267-272)
+//   - the reverse-diffusion loop                    (/root/reference/src/generate_images.jl:174-245)
+#pragma once
+#include <vector>
+#include <map>
+#include <string>
+#include <cmath>
+#include <cstring>
+#include <dlfcn.h>
+#include <nccl.h>
+#include "common.cuh"
+#include "kernels.cuh"
+#include "igemm_simt.cuh"
+#include "conv_tc.cuh"
+
+namespace ddpm {
+
+constexpr int NUM_ARRAYS = 64;
+constexpr int NUM_CONV = 10;  // 3x3 convs followed by BatchNorm(relu)
+
+// ------------------------------------------------------------------------------------ model description
+struct ConvSpec {
+    int cin, cout, hw;   // hw = spatial size of the output (32 or 16)
+    int w, b;            // array indices of weight / bias
+    int bn;              // array index of BN beta (gamma = +1, mu = +2, var = +3)
+};
+// constructor order of SimpleUNet (train_brain.jl:109-145); index 0 unused so that L[1]..L[10]
+static const ConvSpec kConv[NUM_CONV + 1] = {
+    {0, 0, 0, 0, 0, 0},
+    {129, 64, 32, 0, 1, 2},     // down1.conv1
+    {64, 64, 32, 6, 7, 8},      // down1.conv2 -> h1
+    {64, 128, 16, 12, 13, 14},  // down2.conv1 (after MaxPool)
+    {128, 128, 16, 18, 19, 20}, // down2.conv2
+    {128, 128, 16, 24, 25, 26}, // mid.conv1
+    {128, 128, 16, 30, 31, 32}, // mid.conv2
+    {64, 64, 32, 38, 39, 40},   // up2.conv1 (after ConvTranspose, arrays 36,37)
+    {64, 64, 32, 44, 45, 46},   // up2.conv2
+    {128, 64, 32, 50, 51, 52},  // up1.conv1 on cat(up, h1)
+    {64, 64, 32, 56, 57, 58},   // up1.conv2
+};
+constexpr int kUpW = 36, kUpB = 37, kFinalW = 62, kFinalB = 63;
+
+inline void array_lengths(long long* lens) {
+    int k = 0;
+    auto conv = [&](int ci, int co, int kk) { lens[k++] = (long long)kk * kk * ci * co; lens[k++] = co; };
+    auto bn = [&](int c) { for (int i = 0; i < 4; ++i) lens[k++] = c; };
+    conv(129, 64, 3); bn(64); conv(64, 64, 3); bn(64);
+    conv(64, 128, 3); bn(128); conv(128, 128, 3); bn(128);
+    conv(128, 128, 3); bn(128); conv(128, 128, 3); bn(128);
+    conv(128, 64, 2); conv(64, 64, 3); bn(64); conv(64, 64, 3); bn(64);
+    conv(128, 64, 3); bn(64); conv(64, 64, 3); bn(64);
+    conv(64, 1, 1);
+}
+
+// ------------------------------------------------------------------------------------ NCCL (dlopen'd: no link-time dependency)
+struct NcclApi {
+    void* lib = nullptr;
+    ncclResult_t (*GetUniqueId)(ncclUniqueId*) = nullptr;
+    ncclResult_t (*CommInitRank)(ncclComm_t*, int, ncclUniqueId, int) = nullptr;
+    ncclResult_t (*AllReduce)(const void*, void*, size_t, ncclDataType_t, ncclRedOp_t, ncclComm_t, cudaStream_t) = nullptr;
+    ncclResult_t (*CommDestroy)(ncclComm_t) = nullptr;
+    const char* (*GetErrorString)(ncclResult_t) = nullptr;
+    void load() {
+        if (lib) return;
+        const char* names[] = {"libnccl.so.2", "libnccl.so"};
+        for (const char* n : names) {
+            lib = dlopen(n, RTLD_NOW | RTLD_GLOBAL);
+            if (lib) break;
+        }
+        DDPM_CHECK(lib != nullptr, "cannot dlopen libnccl.so.2");
+        GetUniqueId = (decltype(GetUniqueId))dlsym(lib, "ncclGetUniqueId");
+        CommInitRank = (decltype(CommInitRank))dlsym(lib, "ncclCommInitRank");
+        AllReduce = (decltype(AllReduce))dlsym(lib, "ncclAllReduce");
+        CommDestroy = (decltype(CommDestroy))dlsym(lib, "ncclCommDestroy");
+        GetErrorString = (decltype(GetErrorString))dlsym(lib, "ncclGetErrorString");
+        DDPM_CHECK(GetUniqueId && CommInitRank && AllReduce && CommDestroy, "libnccl is missing required symbols");
+    }
+    void check(ncclResult_t r, const char* what) {
+        if (r != ncclSuccess) {
+            std::string m = std::string(what) + " failed: " + (GetErrorString ? GetErrorString(r) : "nccl error");
+            throw Error(m);
+        }
+    }
+};
+inline NcclApi& nccl() {
+    static NcclApi api;
+    return api;
+}
+
+// ------------------------------------------------------------------------------------ padded tensor
+struct Tensor {
+    void* base = nullptr;
+    int C = 0;
+    Geo g{};
+    size_t esz = 0, bytes = 0;
+    template <typename T> T* pos0() const { return reinterpret_cast<T*>(base) + (size_t)g.guard * C; }
+    template <typename T> View<T> view(int c_off = 0) const { return View<T>{pos0<T>() + c_off, C}; }
+    template <typename T> View<const T> cview(int c_off = 0) const { return View<const T>{pos0<T>() + c_off, C}; }
+};
+
+struct DevBuf {  // grow-only raw device buffer
+    void* p = nullptr;
+    size_t cap = 0;
+    void ensure(size_t bytes) {
+        if (bytes <= cap) return;
+        if (p) DDPM_CUDA(cudaFree(p));
+        p = nullptr; cap = 0;
+        DDPM_CUDA(cudaMalloc(&p, bytes));
+        cap = bytes;
+    }
+    void release() { if (p) cudaFree(p); p = nullptr; cap = 0; }
+    template <typename T> T* as() const { return reinterpret_cast<T*>(p); }
+};
+
+struct GraphEntry {
+    cudaGraph_t graph = nullptr;
+    cudaGraphExec_t exec = nullptr;
+    long long launches = 0;
+};
+
+// Activation set for one batch size.  Training keeps every y (pre-BN) and a (post-ReLU);
+// inference aliases a small rotating set and never materialises y.
+struct ActSet {
+    int N = 0;
+    bool training = false;
+    Tensor y[NUM_CONV + 1], a[NUM_CONV + 1], p1, u;
+    // gradient scratch (training only)
+    Tensor g32a, g32b, gcat, g16a, g16b, gp1;
+    std::vector<void*> owned;
+    DevBuf x, eps_hat;  // boundary-layout Float32 [N][H*W]
+    DevBuf z;           // host-supplied sampler noise [steps][N][H*W]
+    // captured reverse loops, keyed by (t_start, zmode); they bake in this set's pointers
+    std::map<std::pair<int, int>, GraphEntry> graphs;
+    void drop_graphs() {
+        for (auto& kv : graphs) {
+            if (kv.second.exec) cudaGraphExecDestroy(kv.second.exec);
+            if (kv.second.graph) cudaGraphDestroy(kv.second.graph);
+        }
+        graphs.clear();
+    }
+};
+
+enum class Mode { Infer, Train };
+
+struct Engine {
+    int T, D, H, W, prec, dev;
+    int HW;
+    cudaStream_t stream = nullptr, comm_stream = nullptr;
+    cudaEvent_t ev_bucket[2] = {nullptr, nullptr}, ev_comm_done = nullptr;
+    cudaEvent_t ev_t0 = nullptr, ev_t1 = nullptr;
+    long long lens[NUM_ARRAYS], offs[NUM_ARRAYS + 1];
+    long long n_params = 0;
+
+    // tables
+    std::vector<float> h_beta, h_acum, h_pe, h_samp;  // host copies
+    float *d_sqrt_ac = nullptr, *d_sqrt_1mac = nullptr, *d_pe = nullptr;
+
+    // parameters
+    float *P = nullptr, *G = nullptr, *M1 = nullptr, *M2 = nullptr;
+    float eta = 1e-4f, b1 = 0.9f, b2 = 0.999f, aeps = 1e-8f, bt1 = 0.9f, bt2 = 0.999f;
+
+    // packed weights
+    void* Wf[NUM_CONV + 1] = {};   // [cout][9][cin]  (TA)  -- L1 unused
+    void* Wd[NUM_CONV + 1] = {};   // [cin][9][cout]  (TG)  -- L1 unused
+    void *Wt = nullptr, *Wtd = nullptr;  // convT fwd (TA) [256][128], dgrad (TG) [128][256]
+    float *Wimg = nullptr, *Wemb = nullptr;  // first conv, FP32
+    float *Ptab = nullptr, *Ecls = nullptr;  // [T][9][64] embedding contributions
+    bool ecls_valid = false, infer_affine_valid = false;
+
+    // per-BN-layer device vectors
+    float *inf_scale[NUM_CONV + 1] = {}, *inf_shift[NUM_CONV + 1] = {};
+    float *tr_mean[NUM_CONV + 1] = {}, *tr_istd[NUM_CONV + 1] = {}, *tr_scale[NUM_CONV + 1] = {}, *tr_shift[NUM_CONV + 1] = {};
+    float *bw_mg[NUM_CONV + 1] = {}, *bw_mgx[NUM_CONV + 1] = {};
+    double* sums = nullptr;       // [NUM_CONV+1][3*128] forward (sum, sumsq) / backward (g, g*xhat, dy)
+    double* sums_g = nullptr;     // all-reduced copies (SyncBN)
+    double* misc_sums = nullptr;  // [0]=loss, [8..72]=dwf, [72]=dbf, [128..192]=dbT
+
+    // activation sets: one for training, a small cache of inference sets keyed by batch size
+    ActSet train_set;
+    std::map<int, ActSet*> infer_sets;
+    DevBuf d_x0, d_eps, d_xt, d_deps, d_ts, d_idx, d_Tw, d_Ccls, d_S, d_z, d_dataset, d_sample_out;
+    long long dataset_n = 0;
+    unsigned long long* d_rng = nullptr;  // [seed, first_index]
+
+    // communicator
+    ncclComm_t comm = nullptr;
+    int rank = 0, world = 1, sync_bn = 0;
+
+    // options / counters
+    long long opt_sample_chunk = 256, opt_use_graph = 1, opt_conv_impl = 0 /*0 auto, 1 simt, 2 tc*/;
+    long long cnt_launches = 0;
+
+    Engine(int T_, int D_, int H_, int W_, int prec_, int dev_);
+    ~Engine();
+
+    // ---- helpers
+    size_t esz_a() const { return prec == 0 ? 4 : 2; }
+    size_t esz_g() const { return prec == 0 ? 4 : 2; }
+    float* arr(int k) const { return P + offs[k]; }
+    float* garr(int k) const { return G + offs[k]; }
+    double* lsum(int l) const { return sums + (size_t)l * 384; }
+    double* gsum(int l) const { return (sync_bn && comm ? sums_g : sums) + (size_t)l * 384; }
+    bool use_tc() const {
+        if (opt_conv_impl == 1) return false;
+        if (opt_conv_impl == 2) return true;
+        return prec != 0 && tc::available();
+    }
+
+    void set_default_tables();
+    void upload_tables();
+    void alloc_tensor(ActSet& s, Tensor& t, int N, int hw, int C, size_t esz);
+    void build_set(ActSet& s, int N, bool training);
+    void free_set(ActSet& s);
+    ActSet& get_set(int N, bool training);
+
+    template <typename TA, typename TG> void pack_weights_t();
+    void pack_weights();
+    void prepare_ecls();
+    void prepare_infer_affine();
+
+    template <typename TA, typename TG>
+    void conv3(const Tensor& s0, const Tensor* s1, int l, Tensor& out, const float* scale, const float* shift, int relu,
+               double* stats);
+    template <typename TA, typename TG>
+    void dgrad3(const Tensor& dy, int l, Tensor& out, int out_c_total);
+    template <typename TA, typename TG> void forward_t(ActSet& s, const float* x_dev, const int* ts_dev, int t_fixed, Mode mode, bool update_running);
+    void forward(ActSet& s, const float* x_dev, const int* ts_dev, int t_fixed, Mode mode, bool update_running);
+    template <typename TA, typename TG> void final_conv_t(ActSet& s, float* eps_hat_dev);
+    template <typename TA, typename TG> void backward_t(ActSet& s, const float* xt_dev, const int* ts_dev, const float* deps_dev, float inv_world);
+    void allreduce_sums(double* local, double* global, int n);
+
+    void train_core(int B, bool device_inputs, bool update, float* loss_out_host);
+    void sample_chunk(ActSet& s, bool host_z, unsigned long long seed, long long first_index, int t_start);
+    template <typename TA, typename TG> void sample_steps_t(ActSet& s, float* x_dev, const float* z_dev, int N, int t_start);
+};
+
+// ===================================================================================== implementation
+
+#define DDPM_DISPATCH(prec, ...)                                                         \
+    do {                                                                                 \
+        if ((prec) == 0) { using TA = float; using TG = float; __VA_ARGS__; }            \
+        else if ((prec) == 1) { using TA = __half; using TG = __nv_bfloat16; __VA_ARGS__; } \
+        else { using TA = __nv_bfloat16; using TG = __nv_bfloat16; __VA_ARGS__; }        \
+    } while (0)
+
+inline Engine::Engine(int T_, int D_, int H_, int W_, int prec_, int dev_)
+    : T(T_), D(D_), H(H_), W(W_), prec(prec_), dev(dev_), HW(H_ * W_) {
+    DDPM_CHECK(T >= 2 && T <= 100000, "T out of range");
+    DDPM_CHECK(D == 128, "only D=128 (the reference's embedding width) is supported");
+    DDPM_CHECK(H == 32 && W == 32, "only 32x32 images (the reference's data) are supported");
+    DDPM_CHECK(prec >= 0 && prec <= 2, "precision must be 0 (fp32), 1 (fp16) or 2 (bf16)");
+    int ndev = 0;
+    cudaError_t e = cudaGetDeviceCount(&ndev);
+    if (e != cudaSuccess || ndev == 0) throw Error("no CUDA device: libddpm has no CPU fallback");
+    DDPM_CHECK(dev >= 0 && dev < ndev, "device index out of range");
+    DDPM_CUDA(cudaSetDevice(dev));
+    cudaDeviceProp prop;
+    DDPM_CUDA(cudaGetDeviceProperties(&prop, dev));
+    if (prop.major != 10) throw Error("libddpm is built for sm_100a (B200) only");
+    DDPM_CUDA(cudaStreamCreateWithFlags(&stream, cudaStreamNonBlocking));
+    DDPM_CUDA(cudaStreamCreateWithFlags(&comm_stream, cudaStreamNonBlocking));
+    for (auto& ev : ev_bucket) DDPM_CUDA(cudaEventCreateWithFlags(&ev, cudaEventDisableTiming));
+    DDPM_CUDA(cudaEventCreateWithFlags(&ev_comm_done, cudaEventDisableTiming));
+    DDPM_CUDA(cudaEventCreate(&ev_t0));
+    DDPM_CUDA(cudaEventCreate(&ev_t1));
+
+    array_lengths(lens);
+    offs[0] = 0;
+    for (int k = 0; k < NUM_ARRAYS; ++k) {
+        // keep every array 16-byte aligned inside the arena
+        offs[k + 1] = offs[k] + ((lens[k] + 3) / 4) * 4;
+    }
+    n_params = offs[NUM_ARRAYS];
+    auto zalloc = [&](float** p, size_t n) {
+        DDPM_CUDA(cudaMalloc(p, n * sizeof(float)));
+        DDPM_CUDA(cudaMemset(*p, 0, n * sizeof(float)));
+    };
+    zalloc(&P, n_params); zalloc(&G, n_params); zalloc(&M1, n_params); zalloc(&M2, n_params);
+    zalloc(&d_sqrt_ac, T); zalloc(&d_sqrt_1mac, T); zalloc(&d_pe, (size_t)T * D);
+    zalloc(&Wimg, 9 * 64); zalloc(&Wemb, (size_t)9 * 64 * D);
+    zalloc(&Ptab, (size_t)T * 576); zalloc(&Ecls, (size_t)T * 576);
+    for (int l = 1; l <= NUM_CONV; ++l) {
+        int C = kConv[l].cout;
+        zalloc(&inf_scale[l], C); zalloc(&inf_shift[l], C);
+        zalloc(&tr_mean[l], C); zalloc(&tr_istd[l], C); zalloc(&tr_scale[l], C); zalloc(&tr_shift[l], C);
+        zalloc(&bw_mg[l], C); zalloc(&bw_mgx[l], C);
+        if (l >= 2) {
+            size_t n = (size_t)9 * kConv[l].cin * kConv[l].cout;
+            DDPM_CUDA(cudaMalloc(&Wf[l], n * esz_a()));
+            DDPM_CUDA(cudaMalloc(&Wd[l], n * esz_g()));
+        }
+    }
+    DDPM_CUDA(cudaMalloc(&Wt, (size_t)4 * 128 * 64 * esz_a()));
+    DDPM_CUDA(cudaMalloc(&Wtd, (size_t)4 * 128 * 64 * esz_g()));
+    DDPM_CUDA(cudaMalloc(&sums, sizeof(double) * 384 * (NUM_CONV + 1)));
+    DDPM_CUDA(cudaMalloc(&sums_g, sizeof(double) * 384 * (NUM_CONV + 1)));
+    DDPM_CUDA(cudaMalloc(&misc_sums, sizeof(double) * 256));
+    DDPM_CUDA(cudaMalloc(&d_rng, 2 * sizeof(unsigned long long)));
+    tc::init();
+    set_default_tables();
+    // Flux default initialisation of the BatchNorm state so an un-loaded handle is well defined:
+    // gamma = 1, var = 1; conv weights stay zero until ddpm_set_weights.
+    for (int l = 1; l <= NUM_CONV; ++l) {
+        int C = kConv[l].cout;
+        std::vector<float> ones(C, 1.f);
+        DDPM_CUDA(cudaMemcpy(arr(kConv[l].bn + 1), ones.data(), C * 4, cudaMemcpyHostToDevice));
+        DDPM_CUDA(cudaMemcpy(arr(kConv[l].bn + 3), ones.data(), C * 4, cudaMemcpyHostToDevice));
+    }
+    pack_weights();
+}
+
+inline Engine::~Engine() {
+    cudaSetDevice(dev);
+    cudaDeviceSynchronize();
+    if (comm) nccl().CommDestroy(comm);
+    free_set(train_set);
+    for (auto& kv : infer_sets) { free_set(*kv.second); delete kv.second; }
+    infer_sets.clear();
+    float* fl[] = {P, G, M1, M2, d_sqrt_ac, d_sqrt_1mac, d_pe, Wimg, Wemb, Ptab, Ecls};
+    for (float* p : fl) cudaFree(p);
+    for (int l = 1; l <= NUM_CONV; ++l) {
+        float* v[] = {inf_scale[l], inf_shift[l], tr_mean[l], tr_istd[l], tr_scale[l], tr_shift[l], bw_mg[l], bw_mgx[l]};
+        for (float* p : v) cudaFree(p);
+        cudaFree(Wf[l]); cudaFree(Wd[l]);
+    }
+    cudaFree(Wt); cudaFree(Wtd); cudaFree(sums); cudaFree(sums_g); cudaFree(misc_sums); cudaFree(d_rng);
+    DevBuf* bufs[] = {&d_x0, &d_eps, &d_xt, &d_deps, &d_ts, &d_idx, &d_Tw, &d_Ccls, &d_S, &d_z, &d_dataset, &d_sample_out};
+    for (DevBuf* b : bufs) b->release();
+    for (auto& ev : ev_bucket) cudaEventDestroy(ev);
+    cudaEventDestroy(ev_comm_done);
+    cudaEventDestroy(ev_t0); cudaEventDestroy(ev_t1);
+    cudaStreamDestroy(stream);
+    cudaStreamDestroy(comm_stream);
+}
+
+// The library's own restatement of the script constants (train_brain.jl:20-24,54-62); the host
+// normally overrides it with ddpm_set_tables so the tables are bit-exact with the host language.
+inline void Engine::set_default_tables() {
+    h_beta.resize(T); h_acum.resize(T); h_pe.resize((size_t)T * D);
+    const double b0 = (double)1e-4f, b1d = (double)0.02f;
+    float prod = 1.f;
+    for (int i = 0; i < T; ++i) {
+        h_beta[i] = (float)(b0 + i * (b1d - b0) / (T - 1));
+        float alpha = 1.f - h_beta[i];
+        prod = (i == 0) ? alpha : prod * alpha;
+        h_acum[i] = prod;
+    }
+    const double neg_log = -(double)logf(1e4f);
+    for (int t = 1; t <= T; ++t)
+        for (int i = 1; i <= D / 2; ++i) {
+            double div = exp(neg_log * (2.0 * (i - 1) / (D - 1)));
+            h_pe[(size_t)(t - 1) * D + 2 * i - 2] = (float)sin(t * div);
+            h_pe[(size_t)(t - 1) * D + 2 * i - 1] = (float)cos(t * div);
+        }
+    upload_tables();
+}
+
+inline void Engine::upload_tables() {
+    // per-step scalars exactly in the order generate_images.jl:186-208 writes them (Float32)
+    std::vector<float> sa(T), sb(T);
+    h_samp.assign((size_t)T * 4, 0.f);
+    for (int t = 1; t <= T; ++t) {
+        volatile float a_t = h_acum[t - 1];
+        volatile float a_prev = t > 1 ? h_acum[t - 2] : 1.f;
+        volatile float beta_t = 1.f - a_t;
+        volatile float beta_prev = 1.f - a_prev;
+        volatile float one_m = 1.f - a_t;
+        volatile float num = beta_prev * one_m;
+        volatile float pv = num / one_m;
+        h_samp[(t - 1) * 4 + 0] = sqrtf(beta_t);
+        h_samp[(t - 1) * 4 + 1] = sqrtf(a_t);
+        h_samp[(t - 1) * 4 + 2] = sqrtf(a_prev);
+        h_samp[(t - 1) * 4 + 3] = sqrtf(pv);
+        sa[t - 1] = sqrtf(a_t);
+        volatile float om = 1.f - a_t;
+        sb[t - 1] = sqrtf(om);
+    }
+    DDPM_CUDA(cudaMemcpy(d_sqrt_ac, sa.data(), T * 4, cudaMemcpyHostToDevice));
+    DDPM_CUDA(cudaMemcpy(d_sqrt_1mac, sb.data(), T * 4, cudaMemcpyHostToDevice));
+    DDPM_CUDA(cudaMemcpy(d_pe, h_pe.data(), (size_t)T * D * 4, cudaMemcpyHostToDevice));
+    ecls_valid = false;
+    for (auto& kv : infer_sets) kv.second->drop_graphs();  // scalars are baked into captured graphs
+}
+
+// ------------------------------------------------------------------------------------ buffers
+inline void Engine::alloc_tensor(ActSet& s, Tensor& t, int N, int hw, int C, size_t esz) {
+    t.C = C; t.g = Geo::make(N, hw, hw); t.esz = esz;
+    t.bytes = (size_t)t.g.alloc_positions() * C * esz;
+    DDPM_CUDA(cudaMalloc(&t.base, t.bytes));
+    DDPM_CUDA(cudaMemsetAsync(t.base, 0, t.bytes, stream));
+    s.owned.push_back(t.base);
+}
+
+inline void Engine::free_set(ActSet& s) {
+    s.drop_graphs();
+    for (void* p : s.owned) cudaFree(p);
+    s.owned.clear();
+    s.x.release(); s.eps_hat.release(); s.z.release();
+    s = ActSet();
+}
+
+inline void Engine::build_set(ActSet& s, int N, bool training) {
+    free_set(s);
+    s.N = N; s.training = training;
+    const size_t ea = esz_a(), eg = esz_g();
+    if (training) {
+        for (int l = 1; l <= NUM_CONV; ++l) {
+            alloc_tensor(s, s.y[l], N, kConv[l].hw, kConv[l].cout, ea);
+            alloc_tensor(s, s.a[l], N, kConv[l].hw, kConv[l].cout, ea);
+        }
+        alloc_tensor(s, s.p1, N, 16, 64, ea);
+        alloc_tensor(s, s.u, N, 32, 64, ea);
+        alloc_tensor(s, s.g32a, N, 32, 64, eg);
+        alloc_tensor(s, s.g32b, N, 32, 64, eg);
+        alloc_tensor(s, s.gcat, N, 32, 128, eg);
+        alloc_tensor(s, s.g16a, N, 16, 128, eg);
+        alloc_tensor(s, s.g16b, N, 16, 128, eg);
+        alloc_tensor(s, s.gp1, N, 16, 64, eg);
+    } else {
+        Tensor i32[4], i16[2];
+        for (auto& t : i32) alloc_tensor(s, t, N, 32, 64, ea);
+        for (auto& t : i16) alloc_tensor(s, t, N, 16, 128, ea);
+        alloc_tensor(s, s.p1, N, 16, 64, ea);
+        s.a[1] = i32[0]; s.a[2] = i32[1];
+        s.a[3] = i16[0]; s.a[4] = i16[1]; s.a[5] = i16[0]; s.a[6] = i16[1];
+        s.u = i32[0]; s.a[7] = i32[2]; s.a[8] = i32[0]; s.a[9] = i32[2]; s.a[10] = i32[3];
+    }
+    s.x.ensure((size_t)N * HW * 4);
+    s.eps_hat.ensure((size_t)N * HW * 4);
+}
+
+inline ActSet& Engine::get_set(int N, bool training) {
+    if (training) {
+        if (train_set.N != N) {
+            DDPM_CUDA(cudaStreamSynchronize(stream));
+            build_set(train_set, N, true);
+        }
+        return train_set;
+    }
+    auto it = infer_sets.find(N);
+    if (it != infer_sets.end()) return *it->second;
+    DDPM_CUDA(cudaStreamSynchronize(stream));
+    if (infer_sets.size() >= 4) {  // bounded cache: drop the smallest-batch set
+        auto victim = infer_sets.begin();
+        free_set(*victim->second);
+        delete victim->second;
+        infer_sets.erase(victim);
+    }
+    ActSet* s = new ActSet();
+    build_set(*s, N, false);
+    infer_sets[N] = s;
+    return *s;
+}
+
+// ------------------------------------------------------------------------------------ derived weights
+template <typename TA, typename TG>
+void Engine::pack_weights_t() {
+    for (int l = 2; l <= NUM_CONV; ++l) {
+        const ConvSpec& c = kConv[l];
+        long long n = 9LL * c.cin * c.cout;
+        pack_conv3_kernel<TA><<<cdiv(n, 256), 256, 0, stream>>>(arr(c.w), c.cin, 0, c.cin, c.cout, 0, (TA*)Wf[l]);
+        pack_conv3_kernel<TG><<<cdiv(n, 256), 256, 0, stream>>>(arr(c.w), c.cin, 0, c.cin, c.cout, 1, (TG*)Wd[l]);
+    }
+    long long nt = 4LL * 128 * 64;
+    pack_up2_kernel<TA><<<cdiv(nt, 256), 256, 0, stream>>>(arr(kUpW), 128, 64, 0, (TA*)Wt);
+    pack_up2_kernel<TG><<<cdiv(nt, 256), 256, 0, stream>>>(arr(kUpW), 128, 64, 1, (TG*)Wtd);
+    long long n1 = 9LL * 64 * (D + 1);
+    pack_l1_kernel<<<cdiv(n1, 256), 256, 0, stream>>>(arr(0), D, 64, Wimg, Wemb);
+    DDPM_LAUNCH_CHECK();
+    cnt_launches += 2 * (NUM_CONV - 1) + 3;
+}
+
+inline void Engine::pack_weights() {
+    DDPM_DISPATCH(prec, (pack_weights_t<TA, TG>()));
+    ecls_valid = false;
+    infer_affine_valid = false;
+}
+
+// Ptab[t][tap][co] = sum_c pe[t][c] * Wemb[tap][co][c]  (500 x 128 x 576 GEMM), then border-class sums
+inline void Engine::prepare_ecls() {
+    if (ecls_valid) return;
+    View<const float> pe{d_pe, D}, none{nullptr, 0};
+    EpiPlain<float> epi{Ptab, 576, (long long)T, nullptr};
+    launch_igemm_simt<float, float>(stream, pe, D, none, 0, Wemb, 576, 1, (long long)T, MapId{(long long)T}, epi);
+    emb_class_sums_kernel<<<cdiv((long long)T * 576, 256), 256, 0, stream>>>(Ptab, Ecls, T, 64);
+    DDPM_LAUNCH_CHECK();
+    cnt_launches += 2;
+    ecls_valid = true;
+}
+
+inline void Engine::prepare_infer_affine() {
+    if (infer_affine_valid) return;
+    for (int l = 1; l <= NUM_CONV; ++l) {
+        const ConvSpec& c = kConv[l];
+        bn_inference_affine_kernel<<<1, 128, 0, stream>>>(arr(c.bn + 1), arr(c.bn), arr(c.bn + 2), arr(c.bn + 3), arr(c.b),
+                                                          inf_scale[l], inf_shift[l], c.cout, 1e-5f);
+    }
+    DDPM_LAUNCH_CHECK();
+    cnt_launches += NUM_CONV;
+    infer_affine_valid = true;
+}
+
+// ------------------------------------------------------------------------------------ convolutions
+// Conv((3,3), cin=>cout, pad=1) of layer l on s0 (and s1 concatenated along channels)
+template <typename TA, typename TG>
+void Engine::conv3(const Tensor& s0, const Tensor* s1, int l, Tensor& out, const float* scale, const float* shift,
+                   int relu, double* stats) {
+    const ConvSpec& c = kConv[l];
+    const Geo& g = out.g;
+    int C0 = s0.C, C1 = s1 ? s1->C : 0;
+    DDPM_CHECK(C0 + C1 == c.cin && out.C == c.cout, "conv3: channel mismatch");
+    if (use_tc()) {
+        if (tc::conv3x3<TA, TA>(stream, s0.pos0<TA>(), C0, s1 ? s1->pos0<TA>() : nullptr, C1, (const TA*)Wf[l], c.cout,
+                                out.pos0<TA>(), g, scale, shift, relu, stats)) {
+            cnt_launches += 1;
+            return;
+        }
+    }
+    MapConv3 map{g.Wp, -(long long)g.guard, g.npos + g.guard};
+    EpiConv<TA> epi{out.view<TA>(), g, scale, shift, relu, stats};
+    View<const TA> v1 = s1 ? s1->cview<TA>() : View<const TA>{nullptr, 0};
+    launch_igemm_simt<TA, TA>(stream, s0.cview<TA>(), C0, v1, C1, (const TA*)Wf[l], c.cout, 9, g.npos, map, epi);
+    cnt_launches += 1;
+}
+
+// data gradient of layer l: out[p][ci] = sum_tap sum_co dy[p - shift(tap)][co] * W[co][tap][ci]
+template <typename TA, typename TG>
+void Engine::dgrad3(const Tensor& dy, int l, Tensor& out, int out_c_total) {
+    const ConvSpec& c = kConv[l];
+    const Geo& g = out.g;
+    DDPM_CHECK(dy.C == c.cout && out.C == out_c_total && out_c_total == c.cin, "dgrad3: channel mismatch");
+    if (use_tc()) {
+        if (tc::conv3x3<TG, TG>(stream, dy.pos0<TG>(), c.cout, nullptr, 0, (const TG*)Wd[l], c.cin, out.pos0<TG>(), g,
+                                nullptr, nullptr, 0, nullptr)) {
+            cnt_launches += 1;
+            return;
+        }
+    }
+    MapConv3 map{g.Wp, -(long long)g.guard, g.npos + g.guard};
+    EpiConv<TG> epi{out.view<TG>(), g, nullptr, nullptr, 0, nullptr};
+    launch_igemm_simt<TG, TG>(stream, dy.cview<TG>(), c.cout, View<const TG>{nullptr, 0}, 0, (const TG*)Wd[l], c.cin, 9,
+                              g.npos, map, epi);
+    cnt_launches += 1;
+}
+
+// ------------------------------------------------------------------------------------ forward
+template <typename TA, typename TG>
+void Engine::forward_t(ActSet& s, const float* x_dev, const int* ts_dev, int t_fixed, Mode mode, bool update_running) {
+    const int N = s.N;
+    const bool train = mode == Mode::Train;
+    prepare_ecls();
+    if (!train) prepare_infer_affine();
+    if (train) {
+        DDPM_CHECK(s.training, "train-mode forward needs a training activation set");
+        DDPM_CUDA(cudaMemsetAsync(sums, 0, sizeof(double) * 384 * (NUM_CONV + 1), stream));
+    }
+    const double count_local = (double)N;
+    auto bn = [&](int l, bool pool) {
+        // finalise batch statistics of layer l and apply BatchNorm+ReLU (train mode only)
+        const ConvSpec& c = kConv[l];
+        double m = count_local * c.hw * c.hw;
+        if (sync_bn && comm) {
+            allreduce_sums(lsum(l), gsum(l), 2 * c.cout);
+            m *= world;
+        }
+        bn_finalize_kernel<<<1, 128, 0, stream>>>(gsum(l), m, arr(c.bn + 1), arr(c.bn), arr(c.bn + 2), arr(c.bn + 3),
+                                                  tr_mean[l], tr_istd[l], tr_scale[l], tr_shift[l], c.cout, 1e-5f, 0.1f,
+                                                  update_running ? 1 : 0);
+        long long work;
+        if (pool) {
+            work = (long long)N * 16 * 16 * (c.cout / 8);
+            bn_apply_pool_kernel<TA><<<cdiv(work, 256), 256, 0, stream>>>(s.y[l].cview<TA>(), s.a[l].view<TA>(), s.p1.view<TA>(),
+                                                                          s.y[l].g, s.p1.g, c.cout, tr_scale[l], tr_shift[l]);
+        } else {
+            work = (long long)N * c.hw * c.hw * (c.cout / 8);
+            bn_apply_kernel<TA><<<cdiv(work, 256), 256, 0, stream>>>(s.y[l].cview<TA>(), s.a[l].view<TA>(), s.y[l].g, c.cout,
+                                                                     tr_scale[l], tr_shift[l]);
+        }
+        DDPM_LAUNCH_CHECK();
+        cnt_launches += 2;
+    };
+    auto layer = [&](int l, const Tensor& in0, const Tensor* in1) {
+        const ConvSpec& c = kConv[l];
+        if (train) {
+            conv3<TA, TG>(in0, in1, l, s.y[l], nullptr, arr(c.b), 0, lsum(l));
+            bn(l, l == 2);
+        } else {
+            conv3<TA, TG>(in0, in1, l, s.a[l], inf_scale[l], inf_shift[l], 1, nullptr);
+        }
+    };
+
+    // ---- down1.conv1 (+ folded embedding)
+    {
+        const ConvSpec& c = kConv[1];
+        long long work = (long long)N * HW * 8;
+        Tensor& o = train ? s.y[1] : s.a[1];
+        conv1_kernel<TA><<<cdiv(work, 256), 256, 0, stream>>>(x_dev, ts_dev, t_fixed, Wimg, Ecls,
+                                                              train ? nullptr : inf_scale[1], train ? arr(c.b) : inf_shift[1],
+                                                              train ? 0 : 1, o.view<TA>(), o.g, train ? lsum(1) : nullptr);
+        DDPM_LAUNCH_CHECK();
+        cnt_launches += 1;
+        if (train) bn(1, false);
+    }
+    layer(2, s.a[1], nullptr);
+    if (!train) {  // MaxPool((2,2)) of h1 (train mode: fused into the BatchNorm apply of layer 2)
+        long long work = (long long)N * 16 * 16 * 8;
+        bn_apply_pool_kernel<TA><<<cdiv(work, 256), 256, 0, stream>>>(s.a[2].cview<TA>(), s.a[2].view<TA>(), s.p1.view<TA>(),
+                                                                      s.a[2].g, s.p1.g, 64, nullptr, nullptr);
+        DDPM_LAUNCH_CHECK();
+        cnt_launches += 1;
+    }
+    layer(3, s.p1, nullptr);
+    layer(4, s.a[3], nullptr);
+    layer(5, s.a[4], nullptr);
+    layer(6, s.a[5], nullptr);
+    // ---- ConvTranspose((2,2), 128=>64, stride=2): GEMM [pos16][128] x [128][4*64] + pixel shuffle
+    {
+        const Geo& gi = s.a[6].g;
+        const Geo& go = s.u.g;
+        bool done = false;
+        if (use_tc())
+            done = tc::up2<TA>(stream, s.a[6].pos0<TA>(), (const TA*)Wt, s.u.pos0<TA>(), gi, go, arr(kUpB));
+        if (!done) {
+            EpiUp2<TA> epi{s.u.view<TA>(), gi, go, arr(kUpB), 64, nullptr};
+            launch_igemm_simt<TA, TA>(stream, s.a[6].cview<TA>(), 128, View<const TA>{nullptr, 0}, 0, (const TA*)Wt, 256, 1,
+                                      gi.npos, MapId{gi.npos}, epi);
+        }
+        cnt_launches += 1;
+    }
+    layer(7, s.u, nullptr);
+    layer(8, s.a[7], nullptr);
+    layer(9, s.a[8], &s.a[2]);  // cat(up_h3, h1; dims=3): upsampled first, skip second (train_brain.jl:175)
+    layer(10, s.a[9], nullptr);
+}
+
+inline void Engine::forward(ActSet& s, const float* x_dev, const int* ts_dev, int t_fixed, Mode mode, bool update_running) {
+    DDPM_DISPATCH(prec, (forward_t<TA, TG>(s, x_dev, ts_dev, t_fixed, mode, update_running)));
+}
+
+template <typename TA, typename TG>
+void Engine::final_conv_t(ActSet& s, float* eps_hat_dev) {
+    long long work = (long long)s.N * HW * 8;
+    final_conv_kernel<TA><<<cdiv(work, 256), 256, 0, stream>>>(s.a[10].cview<TA>(), s.a[10].g, arr(kFinalW), arr(kFinalB),
+                                                               eps_hat_dev, 0, nullptr, nullptr, make_float4(0, 0, 0, 0), 0ull,
+                                                               nullptr, 0u, 0);
+    DDPM_LAUNCH_CHECK();
+    cnt_launches += 1;
+}
+
+inline void Engine::allreduce_sums(double* local, double* global, int n) {
+    nccl().check(nccl().AllReduce(local, global, n, ncclFloat64, ncclSum, comm, stream), "ncclAllReduce(bn sums)");
+}
+
+// ------------------------------------------------------------------------------------ backward
+template <typename TA, typename TG>
+void Engine::backward_t(ActSet& s, const float* xt_dev, const int* ts_dev, const float* deps_dev, float alpha) {
+    const int N = s.N;
+    DDPM_CUDA(cudaMemsetAsync(G, 0, n_params * sizeof(float), stream));
+    DDPM_CUDA(cudaMemsetAsync(misc_sums + 8, 0, sizeof(double) * 248, stream));
+    const double count_local = (double)N;
+
+    // BatchNorm(relu) backward of layer l: da (view) -> dy tensor
+    auto bn_bwd = [&](int l, View<const TG> da, Tensor& dy) {
+        const ConvSpec& c = kConv[l];
+        const Geo& g = s.y[l].g;
+        long long pixels = (long long)N * c.hw * c.hw;
+        int blocks = cdiv(pixels, BNB_PIX_PER_BLOCK);
+        double m = count_local * c.hw * c.hw;
+        bn_bwd_kernel<TA, TG, 1><<<blocks, 256, 0, stream>>>(s.y[l].cview<TA>(), da, dy.view<TG>(), g, c.cout, tr_scale[l],
+                                                             tr_shift[l], tr_mean[l], tr_istd[l], nullptr, nullptr, lsum(l));
+        if (sync_bn && comm) {
+            allreduce_sums(lsum(l), gsum(l), 2 * c.cout);
+            m *= world;
+        }
+        bn_bwd_means_kernel<<<1, 128, 0, stream>>>(lsum(l), gsum(l), m, c.cout, bw_mg[l], bw_mgx[l], garr(c.bn), garr(c.bn + 1));
+        bn_bwd_kernel<TA, TG, 2><<<blocks, 256, 0, stream>>>(s.y[l].cview<TA>(), da, dy.view<TG>(), g, c.cout, tr_scale[l],
+                                                             tr_shift[l], tr_mean[l], tr_istd[l], bw_mg[l], bw_mgx[l], lsum(l));
+        f64_to_f32_kernel<<<1, 128, 0, stream>>>(lsum(l) + 2 * c.cout, garr(c.b), c.cout, 1.0);
+        DDPM_LAUNCH_CHECK();
+        cnt_launches += 4;
+    };
+    // weight gradient of a 3x3 conv: dW[co][tap][ci] = sum_p dy[p][co] * x[p + shift(tap)][ci]
+    auto wgrad = [&](int l, const Tensor& dy, const Tensor& x, int ci_off) {
+        const ConvSpec& c = kConv[l];
+        const Geo& g = dy.g;
+        bool done = false;
+        if (use_tc())
+            done = tc::wgrad3x3<TG, TA>(stream, dy.pos0<TG>(), c.cout, x.pos0<TA>(), x.C, g, garr(c.w), c.cin, ci_off);
+        if (!done) {
+            MapConv3 mapB{g.Wp, -(long long)g.guard, g.npos + g.guard};
+            launch_wgrad_simt<TG, TA>(stream, dy.cview<TG>(), x.cview<TA>(), g.npos, 9, c.cout, x.C, MapId{g.npos}, mapB,
+                                      IdxConv3{c.cin, ci_off}, 1.f, garr(c.w));
+        }
+        cnt_launches += 1;
+    };
+
+    // memset the sums used by the backward (forward sums are no longer needed)
+    DDPM_CUDA(cudaMemsetAsync(sums, 0, sizeof(double) * 384 * (NUM_CONV + 1), stream));
+
+    // ---- final 1x1 conv
+    {
+        long long work = (long long)N * HW * 8;
+        final_bwd_kernel<TA, TG><<<cdiv(work, 256), 256, 0, stream>>>(s.a[10].cview<TA>(), s.g32a.view<TG>(), s.a[10].g,
+                                                                      arr(kFinalW), deps_dev, misc_sums + 8);
+        f64_to_f32_kernel<<<1, 128, 0, stream>>>(misc_sums + 8, garr(kFinalW), 64, 1.0);
+        f64_to_f32_kernel<<<1, 32, 0, stream>>>(misc_sums + 72, garr(kFinalB), 1, 1.0);
+        DDPM_LAUNCH_CHECK();
+        cnt_launches += 3;
+    }
+    // ---- up1
+    bn_bwd(10, s.g32a.cview<TG>(), s.g32b);
+    wgrad(10, s.g32b, s.a[9], 0);
+    dgrad3<TA, TG>(s.g32b, 10, s.g32a, 64);
+    bn_bwd(9, s.g32a.cview<TG>(), s.g32b);
+    wgrad(9, s.g32b, s.a[8], 0);
+    wgrad(9, s.g32b, s.a[2], 64);
+    dgrad3<TA, TG>(s.g32b, 9, s.gcat, 128);
+    // ---- up2
+    bn_bwd(8, s.gcat.cview<TG>(0), s.g32b);
+    wgrad(8, s.g32b, s.a[7], 0);
+    dgrad3<TA, TG>(s.g32b, 8, s.g32a, 64);
+    bn_bwd(7, s.g32a.cview<TG>(), s.g32b);
+    wgrad(7, s.g32b, s.u, 0);
+    dgrad3<TA, TG>(s.g32b, 7, s.g32a, 64);  // g32a = d(u)
+    {   // ConvTranspose backward
+        const Geo& gi = s.a[6].g;
+        const Geo& go = s.u.g;
+        long long pixels = (long long)N * HW;
+        channel_sum_kernel<TG><<<cdiv(pixels, BNB_PIX_PER_BLOCK), 256, 0, stream>>>(s.g32a.cview<TG>(), go, 64, misc_sums + 128);
+        f64_to_f32_kernel<<<1, 128, 0, stream>>>(misc_sums + 128, garr(kUpB), 64, 1.0);
+        // dW[a,b,co,ci] = sum_in du[outpos(in,q)][co] * a6[in][ci]
+        launch_wgrad_simt<TG, TA>(stream, s.g32a.cview<TG>(), s.a[6].cview<TA>(), gi.npos, 4, 64, 128, MapUp2{gi, go},
+                                  MapValid{gi}, IdxUp2{64}, 1.f, garr(kUpW));
+        // da6[in][ci] = sum_{q,co} du[outpos(in,q)][co] * Wtd[ci][q*64+co]
+        EpiConv<TG> epi{s.g16a.view<TG>(), gi, nullptr, nullptr, 0, nullptr};
+        launch_igemm_simt<TG, TG>(stream, s.g32a.cview<TG>(), 64, View<const TG>{nullptr, 0}, 0, (const TG*)Wtd, 128, 4,
+                                  gi.npos, MapUp2{gi, go}, epi);
+        DDPM_LAUNCH_CHECK();
+        cnt_launches += 4;
+    }
+    // first gradient bucket complete: arrays [kUpW, 64) -- start its all-reduce while the rest runs
+    if (comm) {
+        DDPM_CUDA(cudaEventRecord(ev_bucket[0], stream));
+        DDPM_CUDA(cudaStreamWaitEvent(comm_stream, ev_bucket[0], 0));
+        nccl().check(nccl().AllReduce(G + offs[kUpW], G + offs[kUpW], (size_t)(n_params - offs[kUpW]), ncclFloat32, ncclSum,
+                                      comm, comm_stream), "ncclAllReduce(grad bucket 0)");
+    }
+    // ---- mid, down2
+    bn_bwd(6, s.g16a.cview<TG>(), s.g16b);
+    wgrad(6, s.g16b, s.a[5], 0);
+    dgrad3<TA, TG>(s.g16b, 6, s.g16a, 128);
+    bn_bwd(5, s.g16a.cview<TG>(), s.g16b);
+    wgrad(5, s.g16b, s.a[4], 0);
+    dgrad3<TA, TG>(s.g16b, 5, s.g16a, 128);
+    bn_bwd(4, s.g16a.cview<TG>(), s.g16b);
+    wgrad(4, s.g16b, s.a[3], 0);
+    dgrad3<TA, TG>(s.g16b, 4, s.g16a, 128);
+    bn_bwd(3, s.g16a.cview<TG>(), s.g16b);
+    wgrad(3, s.g16b, s.p1, 0);
+    dgrad3<TA, TG>(s.g16b, 3, s.gp1, 64);
+    // ---- down1: h1 receives the skip half of d(cat) plus the MaxPool-routed gradient
+    {
+        long long work = (long long)N * 16 * 16 * 8;
+        pool_bwd_merge_kernel<TA, TG><<<cdiv(work, 256), 256, 0, stream>>>(s.a[2].cview<TA>(), s.gcat.cview<TG>(64),
+                                                                           s.gp1.cview<TG>(), s.g32a.view<TG>(), s.a[2].g,
+                                                                           s.p1.g, 64);
+        DDPM_LAUNCH_CHECK();
+        cnt_launches += 1;
+    }
+    bn_bwd(2, s.g32a.cview<TG>(), s.g32b);
+    wgrad(2, s.g32b, s.a[1], 0);
+    dgrad3<TA, TG>(s.g32b, 2, s.g32a, 64);
+    bn_bwd(1, s.g32a.cview<TG>(), s.g32b);
+    {   // first conv: image channel + folded embedding channels
+        d_Tw.ensure((size_t)N * 576 * 4); d_Ccls.ensure((size_t)N * 576 * 4); d_S.ensure((size_t)N * 576 * 4);
+        l1_bwd_kernel<TG><<<N, 256, 0, stream>>>(s.g32b.cview<TG>(), s.g32b.g, xt_dev, d_Tw.as<float>(), d_Ccls.as<float>());
+        l1_tap_sums_kernel<<<cdiv((long long)N * 576, 256), 256, 0, stream>>>(d_Ccls.as<float>(), d_S.as<float>(), N);
+        l1_wimg_grad_kernel<<<576, 256, 0, stream>>>(d_Tw.as<float>(), N, 1.f, 129, garr(0));
+        View<const float> Sv{d_S.as<float>(), 576}, pev{d_pe, D};
+        launch_wgrad_simt<float, float>(stream, Sv, pev, (long long)N, 1, 576, D, MapId{(long long)N}, MapTs{ts_dev, (long long)N},
+                                        IdxEmb{129, 64}, 1.f, garr(0));
+        DDPM_LAUNCH_CHECK();
+        cnt_launches += 4;
+    }
+    if (comm) {
+        DDPM_CUDA(cudaEventRecord(ev_bucket[1], stream));
+        DDPM_CUDA(cudaStreamWaitEvent(comm_stream, ev_bucket[1], 0));
+        nccl().check(nccl().AllReduce(G, G, (size_t)offs[kUpW], ncclFloat32, ncclSum, comm, comm_stream),
+                     "ncclAllReduce(grad bucket 1)");
+        DDPM_CUDA(cudaEventRecord(ev_comm_done, comm_stream));
+        DDPM_CUDA(cudaStreamWaitEvent(stream, ev_comm_done, 0));
+    }
+    (void)alpha;
+}
+
+// ------------------------------------------------------------------------------------ one training iteration
+// inputs already on the device: d_x0 (or dataset gather via d_idx), d_ts, d_eps
+inline void Engine::train_core(int B, bool gather, bool update, float* loss_out_host) {
+    ActSet& s = get_set(B, true);
+    d_xt.ensure((size_t)B * HW * 4);
+    d_deps.ensure((size_t)B * HW * 4);
+    const float* x0 = gather ? d_dataset.as<float>() : d_x0.as<float>();
+    const int* idx = gather ? d_idx.as<int>() : nullptr;
+    long long n4 = (long long)B * HW / 4;
+    qsample_kernel<<<cdiv(n4, 256), 256, 0, stream>>>(x0, idx, d_eps.as<float>(), d_ts.as<int>(), d_sqrt_ac, d_sqrt_1mac,
+                                                      d_xt.as<float>(), B, HW);
+    DDPM_LAUNCH_CHECK();
+    cnt_launches += 1;
+    forward(s, d_xt.as<float>(), d_ts.as<int>(), 0, Mode::Train, update);
+    DDPM_DISPATCH(prec, (final_conv_t<TA, TG>(s, s.eps_hat.as<float>())));
+    DDPM_CUDA(cudaMemsetAsync(misc_sums, 0, sizeof(double), stream));
+    // loss = mean over the GLOBAL batch; every rank contributes its local sum / (B*world*HW)
+    float inv_count = 1.f / ((float)B * (float)world * (float)HW);
+    mse_kernel<<<cdiv(n4, 256), 256, 0, stream>>>(s.eps_hat.as<float>(), d_eps.as<float>(), n4, inv_count, misc_sums,
+                                                  d_deps.as<float>());
+    DDPM_LAUNCH_CHECK();
+    cnt_launches += 1;
+    DDPM_DISPATCH(prec, (backward_t<TA, TG>(s, d_xt.as<float>(), d_ts.as<int>(), d_deps.as<float>(), 1.f)));
+    if (update) {
+        adam_kernel<<<cdiv(n_params, 256), 256, 0, stream>>>(P, G, M1, M2, n_params, eta, b1, b2, aeps, bt1, bt2);
+        DDPM_LAUNCH_CHECK();
+        cnt_launches += 1;
+        bt1 *= b1; bt2 *= b2;
+        pack_weights();
+    }
+    if (loss_out_host) {
+        double ls = 0;
+        if (comm) {
+            // global loss = sum of local sums / global count
+            nccl().check(nccl().AllReduce(misc_sums, misc_sums, 1, ncclFloat64, ncclSum, comm, stream), "ncclAllReduce(loss)");
+        }
+        DDPM_CUDA(cudaMemcpyAsync(&ls, misc_sums, sizeof(double), cudaMemcpyDeviceToHost, stream));
+        DDPM_CUDA(cudaStreamSynchronize(stream));
+        *loss_out_host = (float)(ls * (double)inv_count);
+    }
+}
+
+// ------------------------------------------------------------------------------------ sampling
+template <typename TA, typename TG>
+void Engine::sample_steps_t(ActSet& s, float* x_dev, const float* z_dev, int N, int t_start) {
+    for (int t = t_start, k = 0; t >= 2; --t, ++k) {
+        forward_t<TA, TG>(s, x_dev, nullptr, t, Mode::Infer, false);
+        const float* sc = &h_samp[(size_t)(t - 1) * 4];
+        long long work = (long long)N * HW * 8;
+        final_conv_kernel<TA><<<cdiv(work, 256), 256, 0, stream>>>(
+            s.a[10].cview<TA>(), s.a[10].g, arr(kFinalW), arr(kFinalB), nullptr, 1, x_dev,
+            z_dev ? z_dev + (size_t)k * N * HW : nullptr, make_float4(sc[0], sc[1], sc[2], sc[3]), 0ull,
+            reinterpret_cast<const long long*>(d_rng), (uint32_t)t, t == 2 ? 1 : 0);
+        cnt_launches += 1;
+    }
+    DDPM_LAUNCH_CHECK();
+}
+
+// reverse loop for the N images resident in s.x (in place); z from s.z (host-supplied) or Philox
+inline void Engine::sample_chunk(ActSet& s, bool host_z, unsigned long long seed, long long first_index, int t_start) {
+    prepare_ecls();
+    prepare_infer_affine();
+    unsigned long long rng[2] = {seed, (unsigned long long)first_index};
+    DDPM_CUDA(cudaMemcpyAsync(d_rng, rng, sizeof rng, cudaMemcpyHostToDevice, stream));
+    if (t_start < 2) return;
+    float* x_dev = s.x.as<float>();
+    const float* z_dev = host_z ? s.z.as<float>() : nullptr;
+    const int N = s.N;
+    if (!opt_use_graph) {
+        DDPM_DISPATCH(prec, (sample_steps_t<TA, TG>(s, x_dev, z_dev, N, t_start)));
+        return;
+    }
+    auto key = std::make_pair(t_start, host_z ? 1 : 0);
+    auto it = s.graphs.find(key);
+    if (it == s.graphs.end()) {
+        DDPM_CUDA(cudaStreamSynchronize(stream));
+        GraphEntry ge;
+        long long before = cnt_launches;
+        DDPM_CUDA(cudaStreamBeginCapture(stream, cudaStreamCaptureModeThreadLocal));
+        try {
+            DDPM_DISPATCH(prec, (sample_steps_t<TA, TG>(s, x_dev, z_dev, N, t_start)));
+        } catch (...) {
+            cudaGraph_t g = nullptr;
+            cudaStreamEndCapture(stream, &g);
+            if (g) cudaGraphDestroy(g);
+            throw;
+        }
+        DDPM_CUDA(cudaStreamEndCapture(stream, &ge.graph));
+        DDPM_CUDA(cudaGraphInstantiate(&ge.exec, ge.graph, 0));
+        ge.launches = cnt_launches - before;
+        cnt_launches = before;
+        it = s.graphs.emplace(key, ge).first;
+    }
+    DDPM_CUDA(cudaGraphLaunch(it->second.exec, stream));
+    cnt_launches += it->second.launches;
+}
+
+}  // namespace ddpm

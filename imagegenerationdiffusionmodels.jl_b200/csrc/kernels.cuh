@@ -1,0 +1,742 @@
+// HBM-bound kernels of the DDPM path: forward noising, the first (1+128 channel) convolution
+// with the folded timestep embedding, BatchNorm statistics / apply / backward, pooling, the final
+// 1x1 convolution fused with the reverse-diffusion update, MSE, Adam, weight packing, Philox.
+// All multi-channel tensors use the padded [position][channel] layout of common.cuh and are
+// accessed 8 channels (16 B in 16-bit modes) per thread, channel-fastest => fully coalesced.
+#pragma once
+#include "common.cuh"
+
+namespace ddpm {
+
+// ------------------------------------------------------------------------------------ 8-wide access
+template <typename T> struct V8;
+template <> struct V8<float> {
+    static __device__ __forceinline__ void ld(const float* p, float o[8]) {
+        float4 a = *reinterpret_cast<const float4*>(p), b = *reinterpret_cast<const float4*>(p + 4);
+        o[0] = a.x; o[1] = a.y; o[2] = a.z; o[3] = a.w; o[4] = b.x; o[5] = b.y; o[6] = b.z; o[7] = b.w;
+    }
+    static __device__ __forceinline__ void st(float* p, const float o[8]) {
+        *reinterpret_cast<float4*>(p) = make_float4(o[0], o[1], o[2], o[3]);
+        *reinterpret_cast<float4*>(p + 4) = make_float4(o[4], o[5], o[6], o[7]);
+    }
+};
+template <> struct V8<__half> {
+    static __device__ __forceinline__ void ld(const __half* p, float o[8]) {
+        uint4 v = *reinterpret_cast<const uint4*>(p);
+        const __half2* h = reinterpret_cast<const __half2*>(&v);
+#pragma unroll
+        for (int i = 0; i < 4; ++i) { float2 f = __half22float2(h[i]); o[2 * i] = f.x; o[2 * i + 1] = f.y; }
+    }
+    static __device__ __forceinline__ void st(__half* p, const float o[8]) {
+        uint4 v;
+        __half2* h = reinterpret_cast<__half2*>(&v);
+#pragma unroll
+        for (int i = 0; i < 4; ++i) h[i] = __floats2half2_rn(o[2 * i], o[2 * i + 1]);
+        *reinterpret_cast<uint4*>(p) = v;
+    }
+};
+template <> struct V8<__nv_bfloat16> {
+    static __device__ __forceinline__ void ld(const __nv_bfloat16* p, float o[8]) {
+        uint4 v = *reinterpret_cast<const uint4*>(p);
+        const __nv_bfloat162* h = reinterpret_cast<const __nv_bfloat162*>(&v);
+#pragma unroll
+        for (int i = 0; i < 4; ++i) { float2 f = __bfloat1622float2(h[i]); o[2 * i] = f.x; o[2 * i + 1] = f.y; }
+    }
+    static __device__ __forceinline__ void st(__nv_bfloat16* p, const float o[8]) {
+        uint4 v;
+        __nv_bfloat162* h = reinterpret_cast<__nv_bfloat162*>(&v);
+#pragma unroll
+        for (int i = 0; i < 4; ++i) h[i] = __floats2bfloat162_rn(o[2 * i], o[2 * i + 1]);
+        *reinterpret_cast<uint4*>(p) = v;
+    }
+};
+
+// ------------------------------------------------------------------------------------ Philox-4x32-10
+struct Philox {
+    static __device__ __forceinline__ uint4 gen(uint4 c, uint2 k) {
+#pragma unroll
+        for (int r = 0; r < 10; ++r) {
+            uint32_t hi0 = __umulhi(0xD2511F53u, c.x), lo0 = 0xD2511F53u * c.x;
+            uint32_t hi1 = __umulhi(0xCD9E8D57u, c.z), lo1 = 0xCD9E8D57u * c.z;
+            c = make_uint4(hi1 ^ c.y ^ k.x, lo1, hi0 ^ c.w ^ k.y, lo0);
+            k.x += 0x9E3779B9u;
+            k.y += 0xBB67AE85u;
+        }
+        return c;
+    }
+    // four N(0,1) draws for pixel quad `quad` of global image `img` at `step` (oracle: device_normal)
+    static __device__ __forceinline__ float4 normal4(unsigned long long seed, unsigned long long img,
+                                                     uint32_t step, uint32_t quad) {
+        uint4 r = gen(make_uint4(quad, (uint32_t)img, (uint32_t)(img >> 32), step),
+                      make_uint2((uint32_t)seed, (uint32_t)(seed >> 32)));
+        const float s = 2.3283064365386963e-10f;  // 2^-32
+        float u0 = ((float)r.x + 0.5f) * s, u1 = ((float)r.y + 0.5f) * s;
+        float u2 = ((float)r.z + 0.5f) * s, u3 = ((float)r.w + 0.5f) * s;
+        // (float)r + 0.5f can round up to 2^32 -> u == 1 -> log(1) = 0: harmless; u > 0 always.
+        float ra = sqrtf(-2.f * logf(u0)), rb = sqrtf(-2.f * logf(u2));
+        float s0, c0, s1, c1;
+        sincospif(2.f * u1, &s0, &c0);
+        sincospif(2.f * u3, &s1, &c1);
+        return make_float4(ra * c0, ra * s0, rb * c1, rb * s1);
+    }
+};
+
+// x[n][p] = N(0,1), keyed by (seed, first_index + n, step)
+__global__ void randn_kernel(float* __restrict__ x, long long n_img, int hw, unsigned long long seed,
+                             long long first_index, uint32_t step) {
+    long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;  // quad index
+    int qpi = hw / 4;
+    if (i >= n_img * qpi) return;
+    long long n = i / qpi;
+    int q = (int)(i - n * qpi);
+    float4 z = Philox::normal4(seed, (unsigned long long)(first_index + n), step, (uint32_t)q);
+    *reinterpret_cast<float4*>(x + n * hw + 4 * q) = z;
+}
+
+// ts[n] ~ U{1..T}: mulhi of a Philox word (step-keyed, component by image index)
+__global__ void randint_ts_kernel(int* __restrict__ ts, int B, int T, unsigned long long seed,
+                                  long long first_index, uint32_t step) {
+    int n = blockIdx.x * blockDim.x + threadIdx.x;
+    if (n >= B) return;
+    unsigned long long img = (unsigned long long)(first_index + n);
+    uint4 r = Philox::gen(make_uint4(0xFFFFFFFFu, (uint32_t)img, (uint32_t)(img >> 32), step),
+                          make_uint2((uint32_t)seed, (uint32_t)(seed >> 32)));
+    ts[n] = 1 + (int)__umulhi(r.x, (uint32_t)T);
+}
+
+// ------------------------------------------------------------------------------------ K1: q_sample
+// x_t = a_n*x0 + b_n*eps with a = sqrt(acum[t]), b = sqrt(1-acum[t]) from host-built Float32 tables.
+// Separately rounded multiplies and add (no FMA contraction) => bit-exact with the reference's
+// broadcast `a .* x0 .+ b .* ϵ` (/root/reference/src/train_brain.jl:230-233).
+// idx != nullptr gathers x0 rows from a resident dataset.
+__global__ void qsample_kernel(const float* __restrict__ x0, const int* __restrict__ idx, const float* __restrict__ eps,
+                               const int* __restrict__ ts, const float* __restrict__ sqrt_ac,
+                               const float* __restrict__ sqrt_1mac, float* __restrict__ xt, long long B, int hw) {
+    long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;  // float4 index
+    int v = hw / 4;
+    if (i >= B * v) return;
+    long long n = i / v;
+    int q = (int)(i - n * v);
+    int t = ts[n] - 1;
+    float a = sqrt_ac[t], b = sqrt_1mac[t];
+    long long src = idx ? (long long)idx[n] : n;
+    float4 x = *reinterpret_cast<const float4*>(x0 + src * hw + 4 * q);
+    float4 e = *reinterpret_cast<const float4*>(eps + n * hw + 4 * q);
+    float4 o;
+    o.x = __fadd_rn(__fmul_rn(a, x.x), __fmul_rn(b, e.x));
+    o.y = __fadd_rn(__fmul_rn(a, x.y), __fmul_rn(b, e.y));
+    o.z = __fadd_rn(__fmul_rn(a, x.z), __fmul_rn(b, e.z));
+    o.w = __fadd_rn(__fmul_rn(a, x.w), __fmul_rn(b, e.w));
+    *reinterpret_cast<float4*>(xt + n * hw + 4 * q) = o;
+}
+
+// final `clamp.(x_t, -1f0, 1f0)` of generate_image (/root/reference/src/generate_images.jl:242)
+__global__ void clamp_kernel(float* __restrict__ x, long long n) {
+    long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i < n) x[i] = fminf(fmaxf(x[i], -1.f), 1.f);
+}
+
+// apply_noise (/root/reference/src/ImageGenerationDiffusionModels.jl:60-73): Float64 recurrence
+__global__ void apply_noise_f64_kernel(const double* __restrict__ img, const double* __restrict__ eps, long long n,
+                                       const double* __restrict__ sa, const double* __restrict__ sb, int nb,
+                                       double* __restrict__ out) {
+    long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    double x = img[i], e = eps[i];
+    for (int k = 0; k < nb; ++k) x = __dadd_rn(__dmul_rn(sa[k], x), __dmul_rn(sb[k], e));
+    out[i] = x;
+}
+
+// ------------------------------------------------------------------------------------ first convolution
+// down1.conv1 = Conv((3,3), 1+128 => 64, pad=1) on cat(x, tile(t_emb)) (train_brain.jl:111,164-168).
+// The 128 tiled embedding channels are constant over the image, so their contribution is a
+// per-(timestep, border-class, cout) constant Ecls (border class = which taps fall inside the
+// image); only the image channel is convolved (K = 9), in FP32 on CUDA cores.
+//   y = (sum_tap x[h+dy,w+dx]*Wimg[tap][co] + Ecls[t][cls][co]) * scale[co] + shift[co]
+// x is the unpadded boundary layout [N][H][W].
+template <typename TA>
+__global__ void __launch_bounds__(256)
+conv1_kernel(const float* __restrict__ x, const int* __restrict__ ts, int t_fixed, const float* __restrict__ Wimg,
+             const float* __restrict__ Ecls, const float* __restrict__ scale, const float* __restrict__ shift, int relu,
+             View<TA> out, Geo g, double* __restrict__ stats) {
+    __shared__ float w_s[9 * 64];
+    __shared__ float sc_s[64], sh_s[64];
+    __shared__ float red[2][64];
+    const int t = threadIdx.x;
+    for (int i = t; i < 576; i += 256) w_s[i] = Wimg[i];
+    if (t < 64) {
+        sc_s[t] = scale ? scale[t] : 1.f;
+        sh_s[t] = shift ? shift[t] : 0.f;
+        red[0][t] = 0.f; red[1][t] = 0.f;
+    }
+    __syncthreads();
+    const int H = g.H, W = g.W;
+    long long idx = (long long)blockIdx.x * 256 + t;
+    long long pix = idx >> 3;
+    const int cg = (int)(idx & 7) * 8;
+    float s1[8], s2[8];
+#pragma unroll
+    for (int j = 0; j < 8; ++j) { s1[j] = 0.f; s2[j] = 0.f; }
+    if (pix < (long long)g.N * H * W) {
+        int n = (int)(pix / (H * W));
+        int rem = (int)(pix - (long long)n * H * W);
+        int h = rem / W, w = rem - h * W;
+        const float* xi = x + (long long)n * H * W;
+        float xv[9];
+#pragma unroll
+        for (int tap = 0; tap < 9; ++tap) {
+            int hh = h + tap / 3 - 1, ww = w + tap % 3 - 1;
+            xv[tap] = (hh >= 0 && hh < H && ww >= 0 && ww < W) ? xi[hh * W + ww] : 0.f;
+        }
+        int cls = (h == 0 ? 0 : (h == H - 1 ? 2 : 1)) * 3 + (w == 0 ? 0 : (w == W - 1 ? 2 : 1));
+        int trow = ts ? (ts[n] - 1) : (t_fixed - 1);
+        const float* e = Ecls + ((long long)trow * 9 + cls) * 64 + cg;
+        float o[8];
+#pragma unroll
+        for (int j = 0; j < 8; ++j) {
+            float acc = 0.f;
+#pragma unroll
+            for (int tap = 0; tap < 9; ++tap) acc = fmaf(xv[tap], w_s[tap * 64 + cg + j], acc);
+            float v = (acc + e[j]) * sc_s[cg + j] + sh_s[cg + j];
+            s1[j] = v; s2[j] = v * v;
+            o[j] = relu ? fmaxf(v, 0.f) : v;
+        }
+        V8<TA>::st(out.p + g.pos(n, h, w) * out.cs + cg, o);
+    }
+    if (stats) {
+#pragma unroll
+        for (int j = 0; j < 8; ++j) { atomicAdd(&red[0][cg + j], s1[j]); atomicAdd(&red[1][cg + j], s2[j]); }
+        __syncthreads();
+        if (t < 64) { atomicAdd(&stats[t], (double)red[0][t]); atomicAdd(&stats[64 + t], (double)red[1][t]); }
+    }
+}
+
+// Ecls[t][cls][co] = sum over the taps that are inside the image for border class cls of P[t][tap][co]
+__global__ void emb_class_sums_kernel(const float* __restrict__ P, float* __restrict__ Ecls, int T, int Cout) {
+    int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= T * 9 * Cout) return;
+    int co = i % Cout, cls = (i / Cout) % 9, t = i / (9 * Cout);
+    int rc = cls / 3, cc = cls % 3;  // 0 = first row/col, 1 = interior, 2 = last
+    float s = 0.f;
+    for (int tap = 0; tap < 9; ++tap) {
+        int dy = tap / 3 - 1, dx = tap % 3 - 1;
+        bool ok = !(rc == 0 && dy < 0) && !(rc == 2 && dy > 0) && !(cc == 0 && dx < 0) && !(cc == 2 && dx > 0);
+        if (ok) s += P[((long long)t * 9 + tap) * Cout + co];
+    }
+    Ecls[i] = s;
+}
+
+// ------------------------------------------------------------------------------------ BatchNorm forward
+// Flux BatchNorm(c, relu), eps=1e-5, momentum=0.1.
+// sums = [sum y | sum y^2] (Float64, accumulated from the FP32 conv accumulators).
+__global__ void bn_finalize_kernel(const double* __restrict__ sums, double count, const float* __restrict__ gamma,
+                                   const float* __restrict__ beta, float* __restrict__ run_mu, float* __restrict__ run_var,
+                                   float* __restrict__ mean_o, float* __restrict__ istd_o, float* __restrict__ scale_o,
+                                   float* __restrict__ shift_o, int C, float eps, float momentum, int update_running) {
+    int c = blockIdx.x * blockDim.x + threadIdx.x;
+    if (c >= C) return;
+    double mean = sums[c] / count;
+    double var = sums[C + c] / count - mean * mean;
+    if (var < 0) var = 0;
+    float meanf = (float)mean, varf = (float)var;
+    float istd = 1.f / sqrtf(varf + eps);
+    float sc = gamma[c] * istd;
+    mean_o[c] = meanf; istd_o[c] = istd; scale_o[c] = sc; shift_o[c] = beta[c] - sc * meanf;
+    if (update_running) {
+        float corr = (float)(count / (count - 1.0));
+        run_mu[c] = (1.f - momentum) * run_mu[c] + momentum * meanf;
+        run_var[c] = (1.f - momentum) * run_var[c] + momentum * (corr * varf);
+    }
+}
+
+// inference: BN folded into an affine epilogue: scale = gamma/sqrt(var_run+eps), shift = (b-mu_run)*scale + beta
+__global__ void bn_inference_affine_kernel(const float* __restrict__ gamma, const float* __restrict__ beta,
+                                           const float* __restrict__ mu, const float* __restrict__ var,
+                                           const float* __restrict__ bias, float* __restrict__ scale_o,
+                                           float* __restrict__ shift_o, int C, float eps) {
+    int c = blockIdx.x * blockDim.x + threadIdx.x;
+    if (c >= C) return;
+    float sc = gamma[c] / sqrtf(var[c] + eps);
+    scale_o[c] = sc;
+    shift_o[c] = (bias[c] - mu[c]) * sc + beta[c];
+}
+
+// a = relu(y*scale + shift) over valid pixels
+template <typename TA>
+__global__ void __launch_bounds__(256)
+bn_apply_kernel(View<const TA> y, View<TA> a, Geo g, int C, const float* __restrict__ scale, const float* __restrict__ shift) {
+    const int groups = C / 8;
+    long long idx = (long long)blockIdx.x * 256 + threadIdx.x;
+    long long pix = idx / groups;
+    int c0 = (int)(idx - pix * groups) * 8;
+    if (pix >= (long long)g.N * g.H * g.W) return;
+    int n = (int)(pix / (g.H * g.W));
+    int rem = (int)(pix - (long long)n * g.H * g.W);
+    long long p = g.pos(n, rem / g.W, rem % g.W);
+    float v[8];
+    V8<TA>::ld(y.p + p * y.cs + c0, v);
+#pragma unroll
+    for (int j = 0; j < 8; ++j) v[j] = fmaxf(fmaf(v[j], scale[c0 + j], shift[c0 + j]), 0.f);
+    V8<TA>::st(a.p + p * a.cs + c0, v);
+}
+
+// a = relu(y*scale+shift) at the four pixels of a 2x2 window and pooled = max of them
+// (BatchNorm(relu) followed by MaxPool((2,2)), train_brain.jl:114,117).  y == nullptr-scale variant:
+// if scale == nullptr the input is already activated (inference: plain max-pool of h1).
+template <typename TA>
+__global__ void __launch_bounds__(256)
+bn_apply_pool_kernel(View<const TA> y, View<TA> a, View<TA> pooled, Geo gf, Geo gc, int C,
+                     const float* __restrict__ scale, const float* __restrict__ shift) {
+    const int groups = C / 8;
+    long long idx = (long long)blockIdx.x * 256 + threadIdx.x;
+    long long pix = idx / groups;
+    int c0 = (int)(idx - pix * groups) * 8;
+    if (pix >= (long long)gc.N * gc.H * gc.W) return;
+    int n = (int)(pix / (gc.H * gc.W));
+    int rem = (int)(pix - (long long)n * gc.H * gc.W);
+    int i = rem / gc.W, j = rem % gc.W;
+    float m[8];
+#pragma unroll
+    for (int k = 0; k < 8; ++k) m[k] = -INFINITY;
+#pragma unroll
+    for (int q = 0; q < 4; ++q) {
+        long long p = gf.pos(n, 2 * i + (q >> 1), 2 * j + (q & 1));
+        float v[8];
+        V8<TA>::ld(y.p + p * y.cs + c0, v);
+        if (scale) {
+#pragma unroll
+            for (int k = 0; k < 8; ++k) v[k] = fmaxf(fmaf(v[k], scale[c0 + k], shift[c0 + k]), 0.f);
+            V8<TA>::st(a.p + p * a.cs + c0, v);
+            // pooled value must equal the max of the STORED (rounded) activations
+#pragma unroll
+            for (int k = 0; k < 8; ++k) v[k] = to_f<TA>(from_f<TA>(v[k]));
+        }
+#pragma unroll
+        for (int k = 0; k < 8; ++k) m[k] = fmaxf(m[k], v[k]);
+    }
+    V8<TA>::st(pooled.p + gc.pos(n, i, j) * pooled.cs + c0, m);
+}
+
+// ------------------------------------------------------------------------------------ final conv (+ reverse update)
+// final = Conv((1,1), 64 => 1) (train_brain.jl:142): eps_hat[n,p] = sum_c a[p][c]*wf[c] + bf.
+// 8 lanes per pixel, 8 channels each, 3-step shuffle reduction.
+// mode 0: write eps_hat.  mode 1: fused reverse-diffusion update (generate_images.jl:196-208)
+//   x <- sqrt(a_prev)*clamp((x - sigma_t*eps_hat)/sqrt(a_t), -1, 1) + sqrt(post_var)*z   (in place)
+// with z read from zbuf (host-supplied noise) or drawn from Philox(seed, image, step).
+template <typename TA>
+__global__ void __launch_bounds__(256)
+final_conv_kernel(View<const TA> a, Geo g, const float* __restrict__ wf, const float* __restrict__ bf,
+                  float* __restrict__ eps_hat, int mode, float* __restrict__ x, const float* __restrict__ zbuf,
+                  float4 scal /*sigma_t, sqrt_at, sqrt_aprev, sqrt_pv*/, unsigned long long seed,
+                  const long long* __restrict__ first_index_dev, uint32_t step, int final_clamp) {
+    long long idx = (long long)blockIdx.x * 256 + threadIdx.x;
+    long long pix = idx >> 3;
+    int c0 = (int)(idx & 7) * 8;
+    const int HW = g.H * g.W;
+    bool live = pix < (long long)g.N * HW;
+    float part = 0.f;
+    int n = 0, rem = 0;
+    if (live) {
+        n = (int)(pix / HW);
+        rem = (int)(pix - (long long)n * HW);
+        long long p = g.pos(n, rem / g.W, rem % g.W);
+        float v[8];
+        V8<TA>::ld(a.p + p * a.cs + c0, v);
+#pragma unroll
+        for (int j = 0; j < 8; ++j) part = fmaf(v[j], wf[c0 + j], part);
+    }
+    part += __shfl_xor_sync(0xffffffffu, part, 1);
+    part += __shfl_xor_sync(0xffffffffu, part, 2);
+    part += __shfl_xor_sync(0xffffffffu, part, 4);
+    if (!live || c0 != 0) return;
+    float e = part + bf[0];
+    if (mode == 0) {
+        eps_hat[pix] = e;
+        return;
+    }
+    float z;
+    if (zbuf) {
+        z = zbuf[pix];
+    } else {
+        long long fi = first_index_dev ? *first_index_dev : 0;
+        float4 zz = Philox::normal4(seed, (unsigned long long)(fi + n), step, (uint32_t)(rem >> 2));
+        int k = rem & 3;
+        z = k == 0 ? zz.x : (k == 1 ? zz.y : (k == 2 ? zz.z : zz.w));
+    }
+    float xv = x[pix];
+    float x0 = __fdiv_rn(__fsub_rn(xv, __fmul_rn(scal.x, e)), scal.y);
+    x0 = fminf(fmaxf(x0, -1.f), 1.f);
+    float xn = __fadd_rn(__fmul_rn(scal.z, x0), __fmul_rn(scal.w, z));
+    if (final_clamp) xn = fminf(fmaxf(xn, -1.f), 1.f);
+    x[pix] = xn;
+}
+
+// ------------------------------------------------------------------------------------ MSE
+// Flux.Losses.mse = mean(abs2.(pred .- target)) (train_brain.jl:240).  Warp-shuffle + block
+// reduction, one Float64 atomic per block; also emits d(loss)/d(pred) = 2(pred-target)*inv_count.
+__global__ void __launch_bounds__(256)
+mse_kernel(const float* __restrict__ pred, const float* __restrict__ target, long long n4, float inv_count,
+           double* __restrict__ loss_sum, float* __restrict__ dpred) {
+    __shared__ float wsum[8];
+    long long i = (long long)blockIdx.x * 256 + threadIdx.x;
+    float s = 0.f;
+    if (i < n4) {
+        float4 p = *reinterpret_cast<const float4*>(pred + 4 * i);
+        float4 t = *reinterpret_cast<const float4*>(target + 4 * i);
+        float4 d = make_float4(p.x - t.x, p.y - t.y, p.z - t.z, p.w - t.w);
+        s = d.x * d.x + d.y * d.y + d.z * d.z + d.w * d.w;
+        if (dpred) {
+            float k = 2.f * inv_count;
+            *reinterpret_cast<float4*>(dpred + 4 * i) = make_float4(k * d.x, k * d.y, k * d.z, k * d.w);
+        }
+    }
+    s = warp_sum(s);
+    if ((threadIdx.x & 31) == 0) wsum[threadIdx.x >> 5] = s;
+    __syncthreads();
+    if (threadIdx.x < 32) {
+        float v = threadIdx.x < 8 ? wsum[threadIdx.x] : 0.f;
+        v = warp_sum(v);
+        if (threadIdx.x == 0) atomicAdd(loss_sum, (double)v);
+    }
+}
+
+// ------------------------------------------------------------------------------------ backward: final conv
+// da[p][c] = deps[p]*wf[c];  dwf[c] = sum_p deps[p]*a[p][c];  dbf = sum_p deps[p]   (sums -> Float64)
+template <typename TA, typename TG>
+__global__ void __launch_bounds__(256)
+final_bwd_kernel(View<const TA> a, View<TG> da, Geo g, const float* __restrict__ wf, const float* __restrict__ deps,
+                 double* __restrict__ sums /*[64 dwf | 1 dbf]*/) {
+    __shared__ float red[65];
+    const int t = threadIdx.x;
+    if (t < 65) red[t] = 0.f;
+    __syncthreads();
+    long long idx = (long long)blockIdx.x * 256 + t;
+    long long pix = idx >> 3;
+    int c0 = (int)(idx & 7) * 8;
+    const int HW = g.H * g.W;
+    if (pix < (long long)g.N * HW) {
+        int n = (int)(pix / HW);
+        int rem = (int)(pix - (long long)n * HW);
+        long long p = g.pos(n, rem / g.W, rem % g.W);
+        float d = deps[pix];
+        float v[8], o[8];
+        V8<TA>::ld(a.p + p * a.cs + c0, v);
+#pragma unroll
+        for (int j = 0; j < 8; ++j) {
+            o[j] = d * wf[c0 + j];
+            atomicAdd(&red[c0 + j], d * v[j]);
+        }
+        V8<TG>::st(da.p + p * da.cs + c0, o);
+        if (c0 == 0) atomicAdd(&red[64], d);
+    }
+    __syncthreads();
+    if (t < 65) atomicAdd(&sums[t], (double)red[t]);
+}
+
+// ------------------------------------------------------------------------------------ BatchNorm backward
+// z = y*scale+shift; g = da * [z > 0]; xhat = (y-mean)*istd
+// pass 1: sums[0:C] += sum g, sums[C:2C] += sum g*xhat
+// pass 2: dy = scale*(g - mg - xhat*mgx), sums[2C:3C] += sum dy   (conv-bias gradient)
+// Each thread owns 8 channels and walks PIX_PER_THREAD pixels, so the block-level reduction is
+// one shared-memory atomic per channel per thread.
+constexpr int BNB_PIX_PER_BLOCK = 512;
+
+template <typename TA, typename TG, int PASS>
+__global__ void __launch_bounds__(256)
+bn_bwd_kernel(View<const TA> y, View<const TG> da, View<TG> dy, Geo g, int C, const float* __restrict__ scale,
+              const float* __restrict__ shift, const float* __restrict__ mean, const float* __restrict__ istd,
+              const float* __restrict__ mg, const float* __restrict__ mgx, double* __restrict__ sums) {
+    __shared__ float red[2][128];
+    const int t = threadIdx.x;
+    if (t < 128) { red[0][t] = 0.f; red[1][t] = 0.f; }
+    __syncthreads();
+    const int groups = C / 8;
+    const int lanes = 256 / groups;
+    const int c0 = (t % groups) * 8, pl = t / groups;
+    const long long total = (long long)g.N * g.H * g.W;
+    const long long pbeg = (long long)blockIdx.x * BNB_PIX_PER_BLOCK;
+    long long pend = pbeg + BNB_PIX_PER_BLOCK;
+    if (pend > total) pend = total;
+    float sc[8], sh[8], mu[8], is[8], a0[8], a1[8], r0[8], r1[8];
+#pragma unroll
+    for (int j = 0; j < 8; ++j) {
+        sc[j] = scale[c0 + j]; sh[j] = shift[c0 + j]; mu[j] = mean[c0 + j]; is[j] = istd[c0 + j];
+        r0[j] = 0.f; r1[j] = 0.f;
+        if (PASS == 2) { a0[j] = mg[c0 + j]; a1[j] = mgx[c0 + j]; }
+    }
+    const int HW = g.H * g.W;
+    for (long long pix = pbeg + pl; pix < pend; pix += lanes) {
+        int n = (int)(pix / HW);
+        int rem = (int)(pix - (long long)n * HW);
+        long long p = g.pos(n, rem / g.W, rem % g.W);
+        float yv[8], gv[8];
+        V8<TA>::ld(y.p + p * y.cs + c0, yv);
+        V8<TG>::ld(da.p + p * da.cs + c0, gv);
+        float o[8];
+#pragma unroll
+        for (int j = 0; j < 8; ++j) {
+            float z = fmaf(yv[j], sc[j], sh[j]);
+            float gg = z > 0.f ? gv[j] : 0.f;
+            float xh = (yv[j] - mu[j]) * is[j];
+            if (PASS == 1) {
+                r0[j] += gg; r1[j] += gg * xh;
+            } else {
+                float d = sc[j] * (gg - a0[j] - xh * a1[j]);
+                o[j] = d; r0[j] += d;
+            }
+        }
+        if (PASS == 2) V8<TG>::st(dy.p + p * dy.cs + c0, o);
+    }
+#pragma unroll
+    for (int j = 0; j < 8; ++j) {
+        atomicAdd(&red[0][c0 + j], r0[j]);
+        if (PASS == 1) atomicAdd(&red[1][c0 + j], r1[j]);
+    }
+    __syncthreads();
+    if (t < C) {
+        if (PASS == 1) {
+            atomicAdd(&sums[t], (double)red[0][t]);
+            atomicAdd(&sums[C + t], (double)red[1][t]);
+        } else {
+            atomicAdd(&sums[2 * C + t], (double)red[0][t]);
+        }
+    }
+}
+
+// after pass 1: local sums -> gradient arena (d beta, d gamma); global sums -> means for pass 2
+__global__ void bn_bwd_means_kernel(const double* __restrict__ local_sums, const double* __restrict__ global_sums,
+                                    double count, int C, float* __restrict__ mg, float* __restrict__ mgx,
+                                    float* __restrict__ dbeta, float* __restrict__ dgamma) {
+    int c = blockIdx.x * blockDim.x + threadIdx.x;
+    if (c >= C) return;
+    dbeta[c] = (float)local_sums[c];
+    dgamma[c] = (float)local_sums[C + c];
+    mg[c] = (float)(global_sums[c] / count);
+    mgx[c] = (float)(global_sums[C + c] / count);
+}
+
+// generic: out[i] = (float)(alpha * in[i])
+__global__ void f64_to_f32_kernel(const double* __restrict__ in, float* __restrict__ out, int n, double alpha) {
+    int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i < n) out[i] = (float)(alpha * in[i]);
+}
+
+// ------------------------------------------------------------------------------------ MaxPool backward + skip merge
+// dh1[p] = dskip[p] + (p is the first arg-max of its 2x2 window ? dpool[window] : 0)
+// (NNlib maxpool backward routes the gradient to the first maximal element)
+template <typename TA, typename TG>
+__global__ void __launch_bounds__(256)
+pool_bwd_merge_kernel(View<const TA> a, View<const TG> dskip, View<const TG> dpool, View<TG> out, Geo gf, Geo gc, int C) {
+    const int groups = C / 8;
+    long long idx = (long long)blockIdx.x * 256 + threadIdx.x;
+    long long pix = idx / groups;
+    int c0 = (int)(idx - pix * groups) * 8;
+    if (pix >= (long long)gc.N * gc.H * gc.W) return;
+    int n = (int)(pix / (gc.H * gc.W));
+    int rem = (int)(pix - (long long)n * gc.H * gc.W);
+    int i = rem / gc.W, j = rem % gc.W;
+    float av[4][8], dp[8];
+    long long p[4];
+#pragma unroll
+    for (int q = 0; q < 4; ++q) {
+        p[q] = gf.pos(n, 2 * i + (q >> 1), 2 * j + (q & 1));
+        V8<TA>::ld(a.p + p[q] * a.cs + c0, av[q]);
+    }
+    V8<TG>::ld(dpool.p + gc.pos(n, i, j) * dpool.cs + c0, dp);
+    int arg[8];
+#pragma unroll
+    for (int k = 0; k < 8; ++k) {
+        int best = 0;
+        float bv = av[0][k];
+#pragma unroll
+        for (int q = 1; q < 4; ++q)
+            if (av[q][k] > bv) { bv = av[q][k]; best = q; }
+        arg[k] = best;
+    }
+#pragma unroll
+    for (int q = 0; q < 4; ++q) {
+        float s[8];
+        V8<TG>::ld(dskip.p + p[q] * dskip.cs + c0, s);
+#pragma unroll
+        for (int k = 0; k < 8; ++k) s[k] += (arg[k] == q) ? dp[k] : 0.f;
+        V8<TG>::st(out.p + p[q] * out.cs + c0, s);
+    }
+}
+
+// ------------------------------------------------------------------------------------ backward of the first conv
+// One block per image.  For the image channel:  Tw[n][tap][co] = sum_p dy[p][co]*x[p+shift(tap)]
+// For the folded embedding channels: class sums Ccls[n][cls][co] = sum_{p in border class} dy[p][co]
+template <typename TG>
+__global__ void __launch_bounds__(256)
+l1_bwd_kernel(View<const TG> dy, Geo g, const float* __restrict__ x, float* __restrict__ Tw, float* __restrict__ Ccls) {
+    __shared__ float tw_s[9 * 64], cl_s[9 * 64];
+    const int t = threadIdx.x, n = blockIdx.x;
+    for (int i = t; i < 576; i += 256) { tw_s[i] = 0.f; cl_s[i] = 0.f; }
+    __syncthreads();
+    const int H = g.H, W = g.W;
+    const int c0 = (t & 7) * 8, pl = t >> 3;
+    const float* xi = x + (long long)n * H * W;
+    float tw[9][8];
+#pragma unroll
+    for (int a = 0; a < 9; ++a)
+#pragma unroll
+        for (int j = 0; j < 8; ++j) tw[a][j] = 0.f;
+    for (int pix = pl; pix < H * W; pix += 32) {
+        int h = pix / W, w = pix - h * W;
+        float d[8];
+        V8<TG>::ld(dy.p + g.pos(n, h, w) * dy.cs + c0, d);
+        int cls = (h == 0 ? 0 : (h == H - 1 ? 2 : 1)) * 3 + (w == 0 ? 0 : (w == W - 1 ? 2 : 1));
+#pragma unroll
+        for (int j = 0; j < 8; ++j) atomicAdd(&cl_s[cls * 64 + c0 + j], d[j]);
+#pragma unroll
+        for (int tap = 0; tap < 9; ++tap) {
+            int hh = h + tap / 3 - 1, ww = w + tap % 3 - 1;
+            float xv = (hh >= 0 && hh < H && ww >= 0 && ww < W) ? xi[hh * W + ww] : 0.f;
+#pragma unroll
+            for (int j = 0; j < 8; ++j) tw[tap][j] = fmaf(d[j], xv, tw[tap][j]);
+        }
+    }
+#pragma unroll
+    for (int tap = 0; tap < 9; ++tap)
+#pragma unroll
+        for (int j = 0; j < 8; ++j) atomicAdd(&tw_s[tap * 64 + c0 + j], tw[tap][j]);
+    __syncthreads();
+    for (int i = t; i < 576; i += 256) {
+        Tw[(long long)n * 576 + i] = tw_s[i];
+        Ccls[(long long)n * 576 + i] = cl_s[i];
+    }
+}
+
+// S[n][tap][co] = sum of the class sums of the border classes for which tap stays inside the image
+__global__ void l1_tap_sums_kernel(const float* __restrict__ Ccls, float* __restrict__ S, long long B) {
+    long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= B * 576) return;
+    int co = (int)(i % 64), tap = (int)((i / 64) % 9);
+    long long n = i / 576;
+    int dy = tap / 3 - 1, dx = tap % 3 - 1;
+    float s = 0.f;
+    for (int rc = 0; rc < 3; ++rc) {
+        if ((rc == 0 && dy < 0) || (rc == 2 && dy > 0)) continue;
+        for (int cc = 0; cc < 3; ++cc) {
+            if ((cc == 0 && dx < 0) || (cc == 2 && dx > 0)) continue;
+            s += Ccls[n * 576 + (rc * 3 + cc) * 64 + co];
+        }
+    }
+    S[i] = s;
+}
+
+// dWimg: arena[idx(tap,co)] = alpha * sum_n Tw[n][tap][co]   (Flux index of input channel 0)
+__global__ void l1_wimg_grad_kernel(const float* __restrict__ Tw, long long B, float alpha, int Cin_total,
+                                    float* __restrict__ dW) {
+    int i = blockIdx.x;  // tap*64 + co
+    int tap = i / 64, co = i % 64;
+    double s = 0;
+    for (long long n = threadIdx.x; n < B; n += blockDim.x) s += Tw[n * 576 + i];
+    __shared__ double ws[8];
+    s = warp_sum_d(s);
+    if ((threadIdx.x & 31) == 0) ws[threadIdx.x >> 5] = s;
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        double tot = 0;
+        for (int k = 0; k < (int)(blockDim.x >> 5); ++k) tot += ws[k];
+        int dy = tap / 3 - 1, dx = tap % 3 - 1;
+        dW[(1 - dx) + 3 * (1 - dy) + 9LL * Cin_total * co] = (float)(alpha * tot);
+    }
+}
+
+// per-channel sum over valid pixels of a tensor -> Float64 (ConvTranspose bias gradient)
+template <typename TG>
+__global__ void __launch_bounds__(256)
+channel_sum_kernel(View<const TG> d, Geo g, int C, double* __restrict__ sums) {
+    __shared__ float red[128];
+    const int t = threadIdx.x;
+    if (t < 128) red[t] = 0.f;
+    __syncthreads();
+    const int groups = C / 8, lanes = 256 / groups;
+    const int c0 = (t % groups) * 8, pl = t / groups;
+    const long long total = (long long)g.N * g.H * g.W;
+    const long long pbeg = (long long)blockIdx.x * BNB_PIX_PER_BLOCK;
+    long long pend = pbeg + BNB_PIX_PER_BLOCK;
+    if (pend > total) pend = total;
+    float r[8];
+#pragma unroll
+    for (int j = 0; j < 8; ++j) r[j] = 0.f;
+    const int HW = g.H * g.W;
+    for (long long pix = pbeg + pl; pix < pend; pix += lanes) {
+        int n = (int)(pix / HW);
+        int rem = (int)(pix - (long long)n * HW);
+        float v[8];
+        V8<TG>::ld(d.p + g.pos(n, rem / g.W, rem % g.W) * d.cs + c0, v);
+#pragma unroll
+        for (int j = 0; j < 8; ++j) r[j] += v[j];
+    }
+#pragma unroll
+    for (int j = 0; j < 8; ++j) atomicAdd(&red[c0 + j], r[j]);
+    __syncthreads();
+    if (t < C) atomicAdd(&sums[t], (double)red[t]);
+}
+
+// ------------------------------------------------------------------------------------ Adam (Optimisers.jl 0.4.6)
+// m = b1*m + (1-b1)*g ; v = b2*v + (1-b2)*g^2 ; p -= m/(1-bt1) / (sqrt(v/(1-bt2)) + eps) * eta
+// over the whole flat parameter arena (running statistics have g = m = v = 0 => unchanged).
+__global__ void __launch_bounds__(256)
+adam_kernel(float* __restrict__ p, const float* __restrict__ g, float* __restrict__ m, float* __restrict__ v,
+            long long n, float eta, float b1, float b2, float eps, float bt1, float bt2) {
+    long long i = (long long)blockIdx.x * 256 + threadIdx.x;
+    if (i >= n) return;
+    float gi = g[i];
+    float mi = __fadd_rn(__fmul_rn(b1, m[i]), __fmul_rn(1.f - b1, gi));
+    float vi = __fadd_rn(__fmul_rn(b2, v[i]), __fmul_rn(1.f - b2, __fmul_rn(gi, gi)));
+    m[i] = mi; v[i] = vi;
+    float num = __fdiv_rn(mi, 1.f - bt1);
+    float den = __fadd_rn(__fsqrt_rn(__fdiv_rn(vi, 1.f - bt2)), eps);
+    p[i] = __fsub_rn(p[i], __fmul_rn(__fdiv_rn(num, den), eta));
+}
+
+// ------------------------------------------------------------------------------------ weight packing
+// Flux Conv weight w[a,b,ci,co] (column-major; true convolution) -> cross-correlation, K-major:
+//   fwd  : Wf[co][tap][ci]  = w[1-dx, 1-dy, ci+ci_off, co]              tap = (dy+1)*3 + (dx+1)
+//   dgrad: Wd[ci][tap][co]  = w[1+dx, 1+dy, ci, co]                     (transposed, un-flipped)
+template <typename TW>
+__global__ void pack_conv3_kernel(const float* __restrict__ w, int Cin_total, int ci_off, int Cin, int Cout,
+                                  int dgrad, TW* __restrict__ out) {
+    long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    long long total = 9LL * Cin * Cout;
+    if (i >= total) return;
+    if (!dgrad) {
+        int ci = (int)(i % Cin), tap = (int)((i / Cin) % 9), co = (int)(i / (9LL * Cin));
+        int dy = tap / 3 - 1, dx = tap % 3 - 1;
+        out[i] = from_f<TW>(w[(1 - dx) + 3 * (1 - dy) + 9LL * (ci + ci_off) + 9LL * Cin_total * co]);
+    } else {
+        int co = (int)(i % Cout), tap = (int)((i / Cout) % 9), ci = (int)(i / (9LL * Cout));
+        int dy = tap / 3 - 1, dx = tap % 3 - 1;
+        out[i] = from_f<TW>(w[(1 + dx) + 3 * (1 + dy) + 9LL * (ci + ci_off) + 9LL * Cin_total * co]);
+    }
+}
+// ConvTranspose weight w[a,b,co,ci]:  Wt[q*Cout+co][ci] (fwd, K = ci)  /  Wtd[ci][q*Cout+co] (dgrad, K = q,co)
+template <typename TW>
+__global__ void pack_up2_kernel(const float* __restrict__ w, int Cin, int Cout, int dgrad, TW* __restrict__ out) {
+    long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    long long total = 4LL * Cin * Cout;
+    if (i >= total) return;
+    int q, co, ci;
+    if (!dgrad) { ci = (int)(i % Cin); co = (int)((i / Cin) % Cout); q = (int)(i / ((long long)Cin * Cout)); }
+    else { co = (int)(i % Cout); q = (int)((i / Cout) % 4); ci = (int)(i / (4LL * Cout)); }
+    int py = q >> 1, px = q & 1;
+    out[i] = from_f<TW>(w[(1 - px) + 2 * (1 - py) + 4LL * co + 4LL * Cout * ci]);
+}
+// down1.conv1: Wimg[tap][co] (input channel 0) and Wemb[tap*Cout+co][c] (input channels 1..128), FP32
+__global__ void pack_l1_kernel(const float* __restrict__ w, int D, int Cout, float* __restrict__ Wimg,
+                               float* __restrict__ Wemb) {
+    long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    long long total = 9LL * Cout * (D + 1);
+    if (i >= total) return;
+    int c = (int)(i % (D + 1));
+    int co = (int)((i / (D + 1)) % Cout), tap = (int)(i / ((long long)(D + 1) * Cout));
+    int dy = tap / 3 - 1, dx = tap % 3 - 1;
+    float v = w[(1 - dx) + 3 * (1 - dy) + 9LL * c + 9LL * (D + 1) * co];
+    if (c == 0) Wimg[tap * Cout + co] = v;
+    else Wemb[((long long)tap * Cout + co) * D + (c - 1)] = v;
+}
+
+}  // namespace ddpm

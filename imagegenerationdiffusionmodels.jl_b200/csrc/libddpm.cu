@@ -1,0 +1,551 @@
+// libddpm.so -- C ABI (include/libddpm.h) over the Engine.  Every entry point converts C++
+// exceptions into a nonzero return code + thread-local message; nothing throws across the ABI.
+#include "../../include/libddpm.h"
+#include "engine.cuh"
+
+#include <algorithm>
+
+using namespace ddpm;
+
+struct ddpm_handle {
+    Engine* eng;
+};
+
+static thread_local std::string g_last_error;
+
+#define API_BEGIN try {
+#define API_END                                   \
+    }                                             \
+    catch (const std::exception& e) {             \
+        g_last_error = e.what();                  \
+        cudaGetLastError();                       \
+        return 1;                                 \
+    }                                             \
+    catch (...) {                                 \
+        g_last_error = "unknown error";           \
+        return 1;                                 \
+    }                                             \
+    return 0;
+
+static Engine& E(ddpm_handle* h) {
+    if (!h || !h->eng) throw Error("null handle");
+    DDPM_CUDA(cudaSetDevice(h->eng->dev));
+    return *h->eng;
+}
+
+extern "C" {
+
+const char* ddpm_last_error(void) { return g_last_error.c_str(); }
+int ddpm_version(void) { return 100; }
+
+int ddpm_device_count(void) {
+    int n = 0;
+    if (cudaGetDeviceCount(&n) != cudaSuccess) { cudaGetLastError(); return 0; }
+    return n;
+}
+
+int ddpm_array_lengths(int64_t* lens) {
+    API_BEGIN
+    long long l[NUM_ARRAYS];
+    array_lengths(l);
+    for (int i = 0; i < NUM_ARRAYS; ++i) lens[i] = l[i];
+    API_END
+}
+
+int ddpm_create(ddpm_handle** out, int T, int D, int H, int W, int precision, int device) {
+    API_BEGIN
+    DDPM_CHECK(out != nullptr, "out is null");
+    *out = nullptr;
+    Engine* e = new Engine(T, D, H, W, precision, device);
+    *out = new ddpm_handle{e};
+    API_END
+}
+
+int ddpm_destroy(ddpm_handle* h) {
+    API_BEGIN
+    if (h) { delete h->eng; delete h; }
+    API_END
+}
+
+int ddpm_set_tables(ddpm_handle* h, const float* beta, const float* alpha_cum, const float* pe) {
+    API_BEGIN
+    Engine& e = E(h);
+    DDPM_CHECK(beta && alpha_cum && pe, "null table");
+    DDPM_CUDA(cudaStreamSynchronize(e.stream));
+    std::copy(beta, beta + e.T, e.h_beta.begin());
+    std::copy(alpha_cum, alpha_cum + e.T, e.h_acum.begin());
+    std::copy(pe, pe + (size_t)e.T * e.D, e.h_pe.begin());
+    e.upload_tables();
+    API_END
+}
+
+int ddpm_get_tables(ddpm_handle* h, float* beta, float* alpha_cum, float* pe, float* samp) {
+    API_BEGIN
+    Engine& e = E(h);
+    if (beta) std::copy(e.h_beta.begin(), e.h_beta.end(), beta);
+    if (alpha_cum) std::copy(e.h_acum.begin(), e.h_acum.end(), alpha_cum);
+    if (pe) std::copy(e.h_pe.begin(), e.h_pe.end(), pe);
+    if (samp) std::copy(e.h_samp.begin(), e.h_samp.end(), samp);
+    API_END
+}
+
+static void check_lens(Engine& e, const int64_t* lens, int n) {
+    DDPM_CHECK(n == NUM_ARRAYS, "expected 64 arrays (SimpleUNet in BSON order)");
+    for (int k = 0; k < n; ++k) DDPM_CHECK(lens[k] == e.lens[k], "array length mismatch");
+}
+
+int ddpm_set_weights(ddpm_handle* h, const float* const* arrays, const int64_t* lens, int n) {
+    API_BEGIN
+    Engine& e = E(h);
+    check_lens(e, lens, n);
+    std::vector<float> host((size_t)e.n_params, 0.f);
+    for (int k = 0; k < n; ++k) std::memcpy(host.data() + e.offs[k], arrays[k], (size_t)lens[k] * 4);
+    DDPM_CUDA(cudaStreamSynchronize(e.stream));
+    DDPM_CUDA(cudaMemcpy(e.P, host.data(), (size_t)e.n_params * 4, cudaMemcpyHostToDevice));
+    e.pack_weights();
+    DDPM_CUDA(cudaStreamSynchronize(e.stream));
+    API_END
+}
+
+static void fetch_arena(Engine& e, const float* dev, float* const* arrays, const int64_t* lens, int n) {
+    check_lens(e, lens, n);
+    std::vector<float> host((size_t)e.n_params);
+    DDPM_CUDA(cudaStreamSynchronize(e.stream));
+    DDPM_CUDA(cudaMemcpy(host.data(), dev, (size_t)e.n_params * 4, cudaMemcpyDeviceToHost));
+    for (int k = 0; k < n; ++k) std::memcpy(arrays[k], host.data() + e.offs[k], (size_t)lens[k] * 4);
+}
+
+int ddpm_get_weights(ddpm_handle* h, float* const* arrays, const int64_t* lens, int n) {
+    API_BEGIN
+    Engine& e = E(h);
+    fetch_arena(e, e.P, arrays, lens, n);
+    API_END
+}
+
+int ddpm_set_adam(ddpm_handle* h, float eta, float beta1, float beta2, float eps) {
+    API_BEGIN
+    Engine& e = E(h);
+    e.eta = eta; e.b1 = beta1; e.b2 = beta2; e.aeps = eps; e.bt1 = beta1; e.bt2 = beta2;
+    DDPM_CUDA(cudaMemsetAsync(e.M1, 0, (size_t)e.n_params * 4, e.stream));
+    DDPM_CUDA(cudaMemsetAsync(e.M2, 0, (size_t)e.n_params * 4, e.stream));
+    API_END
+}
+
+static void check_ts(Engine& e, const int32_t* ts, int B) {
+    for (int i = 0; i < B; ++i) DDPM_CHECK(ts[i] >= 1 && ts[i] <= e.T, "timestep out of range 1..T");
+}
+
+static void upload_batch(Engine& e, const float* x0, const int32_t* ts, const float* eps, int B) {
+    size_t nb = (size_t)B * e.HW * 4;
+    if (x0) { e.d_x0.ensure(nb); DDPM_CUDA(cudaMemcpyAsync(e.d_x0.p, x0, nb, cudaMemcpyHostToDevice, e.stream)); }
+    if (eps) { e.d_eps.ensure(nb); DDPM_CUDA(cudaMemcpyAsync(e.d_eps.p, eps, nb, cudaMemcpyHostToDevice, e.stream)); }
+    if (ts) {
+        check_ts(e, ts, B);
+        e.d_ts.ensure((size_t)B * 4);
+        DDPM_CUDA(cudaMemcpyAsync(e.d_ts.p, ts, (size_t)B * 4, cudaMemcpyHostToDevice, e.stream));
+    }
+}
+
+int ddpm_q_sample(ddpm_handle* h, const float* x0, const int32_t* ts, const float* eps, int B, float* x_t) {
+    API_BEGIN
+    Engine& e = E(h);
+    DDPM_CHECK(B > 0 && x0 && ts && eps && x_t, "bad arguments");
+    upload_batch(e, x0, ts, eps, B);
+    e.d_xt.ensure((size_t)B * e.HW * 4);
+    long long n4 = (long long)B * e.HW / 4;
+    qsample_kernel<<<cdiv(n4, 256), 256, 0, e.stream>>>(e.d_x0.as<float>(), nullptr, e.d_eps.as<float>(), e.d_ts.as<int>(),
+                                                        e.d_sqrt_ac, e.d_sqrt_1mac, e.d_xt.as<float>(), B, e.HW);
+    DDPM_LAUNCH_CHECK();
+    e.cnt_launches += 1;
+    DDPM_CUDA(cudaMemcpyAsync(x_t, e.d_xt.p, (size_t)B * e.HW * 4, cudaMemcpyDeviceToHost, e.stream));
+    DDPM_CUDA(cudaStreamSynchronize(e.stream));
+    API_END
+}
+
+int ddpm_predict_eps(ddpm_handle* h, const float* x_t, const int32_t* ts, int B, int train_mode, float* eps_hat) {
+    API_BEGIN
+    Engine& e = E(h);
+    DDPM_CHECK(B > 0 && x_t && ts && eps_hat, "bad arguments");
+    ActSet& s = e.get_set(B, train_mode != 0);
+    upload_batch(e, nullptr, ts, nullptr, B);
+    DDPM_CUDA(cudaMemcpyAsync(s.x.p, x_t, (size_t)B * e.HW * 4, cudaMemcpyHostToDevice, e.stream));
+    e.forward(s, s.x.as<float>(), e.d_ts.as<int>(), 0, train_mode ? Mode::Train : Mode::Infer, false);
+    DDPM_DISPATCH(e.prec, (e.final_conv_t<TA, TG>(s, s.eps_hat.as<float>())));
+    DDPM_CUDA(cudaMemcpyAsync(eps_hat, s.eps_hat.p, (size_t)B * e.HW * 4, cudaMemcpyDeviceToHost, e.stream));
+    DDPM_CUDA(cudaStreamSynchronize(e.stream));
+    API_END
+}
+
+int ddpm_train_step(ddpm_handle* h, const float* x0, const int32_t* ts, const float* eps, int B, float* loss) {
+    API_BEGIN
+    Engine& e = E(h);
+    DDPM_CHECK(B > 1 && x0 && ts && eps, "bad arguments (B must be > 1 for batch statistics)");
+    upload_batch(e, x0, ts, eps, B);
+    float l = 0.f;
+    e.train_core(B, false, true, &l);
+    if (loss) *loss = l;
+    API_END
+}
+
+int ddpm_loss_and_grad(ddpm_handle* h, const float* x0, const int32_t* ts, const float* eps, int B, float* loss,
+                       float* const* grads, const int64_t* lens, int n) {
+    API_BEGIN
+    Engine& e = E(h);
+    DDPM_CHECK(B > 1 && x0 && ts && eps, "bad arguments");
+    upload_batch(e, x0, ts, eps, B);
+    float l = 0.f;
+    e.train_core(B, false, false, &l);
+    if (loss) *loss = l;
+    if (grads) fetch_arena(e, e.G, grads, lens, n);
+    API_END
+}
+
+int ddpm_upload_dataset(ddpm_handle* h, const float* imgs, int64_t n_imgs) {
+    API_BEGIN
+    Engine& e = E(h);
+    DDPM_CHECK(imgs && n_imgs > 0, "bad arguments");
+    DDPM_CUDA(cudaStreamSynchronize(e.stream));
+    e.d_dataset.ensure((size_t)n_imgs * e.HW * 4);
+    DDPM_CUDA(cudaMemcpy(e.d_dataset.p, imgs, (size_t)n_imgs * e.HW * 4, cudaMemcpyHostToDevice));
+    e.dataset_n = n_imgs;
+    API_END
+}
+
+int ddpm_train_step_device(ddpm_handle* h, const int32_t* idx, int B, uint64_t seed, int64_t step, float* loss) {
+    API_BEGIN
+    Engine& e = E(h);
+    DDPM_CHECK(B > 1 && e.dataset_n > 0, "upload a dataset first");
+    std::vector<int> host_idx(B);
+    for (int i = 0; i < B; ++i) {
+        host_idx[i] = idx ? idx[i] : (int)(i % e.dataset_n);
+        DDPM_CHECK(host_idx[i] >= 0 && host_idx[i] < e.dataset_n, "dataset index out of range");
+    }
+    e.d_idx.ensure((size_t)B * 4);
+    DDPM_CUDA(cudaMemcpyAsync(e.d_idx.p, host_idx.data(), (size_t)B * 4, cudaMemcpyHostToDevice, e.stream));
+    e.d_ts.ensure((size_t)B * 4);
+    e.d_eps.ensure((size_t)B * e.HW * 4);
+    long long first = (long long)e.rank * B;
+    randint_ts_kernel<<<cdiv(B, 256), 256, 0, e.stream>>>(e.d_ts.as<int>(), B, e.T, seed, first, (uint32_t)step);
+    long long quads = (long long)B * e.HW / 4;
+    randn_kernel<<<cdiv(quads, 256), 256, 0, e.stream>>>(e.d_eps.as<float>(), B, e.HW, seed ^ 0x9E3779B97F4A7C15ull, first,
+                                                         (uint32_t)step);
+    DDPM_LAUNCH_CHECK();
+    e.cnt_launches += 2;
+    float l = 0.f;
+    e.train_core(B, true, true, loss ? &l : nullptr);
+    if (loss) *loss = l;
+    else DDPM_CUDA(cudaStreamSynchronize(e.stream));  // host_idx must outlive the async copy
+    API_END
+}
+
+// ------------------------------------------------------------------------------------ sampling
+static void sample_impl(Engine& e, const float* x_T, const float* z, uint64_t seed, int64_t N, int64_t first_index,
+                        int t_start, float* out, bool keep_on_device) {
+    DDPM_CHECK(N > 0, "N must be positive");
+    DDPM_CHECK(t_start >= 1 && t_start <= e.T, "t_start out of range 1..T");
+    const int HW = e.HW;
+    const int steps = t_start - 1;
+    long long chunk = std::max<long long>(1, std::min<long long>(e.opt_sample_chunk, N));
+    if (keep_on_device) e.d_sample_out.ensure((size_t)N * HW * 4);
+    for (long long c0 = 0; c0 < N; c0 += chunk) {
+        int nb = (int)std::min<long long>(chunk, N - c0);
+        ActSet& s = e.get_set(nb, false);
+        float* xd = s.x.as<float>();
+        if (x_T) {
+            DDPM_CUDA(cudaMemcpyAsync(xd, x_T + c0 * HW, (size_t)nb * HW * 4, cudaMemcpyHostToDevice, e.stream));
+        } else {
+            long long quads = (long long)nb * HW / 4;
+            randn_kernel<<<cdiv(quads, 256), 256, 0, e.stream>>>(xd, nb, HW, seed, first_index + c0, 0u);
+            DDPM_LAUNCH_CHECK();
+            e.cnt_launches += 1;
+        }
+        if (z && steps > 0) {
+            if (s.z.cap < (size_t)steps * nb * HW * 4) s.drop_graphs();  // graphs captured the old z pointer
+            s.z.ensure((size_t)steps * nb * HW * 4);
+            // z[k] is an [N][HW] slab; take columns c0..c0+nb of every slab
+            DDPM_CUDA(cudaMemcpy2DAsync(s.z.p, (size_t)nb * HW * 4, z + c0 * HW, (size_t)N * HW * 4, (size_t)nb * HW * 4,
+                                        steps, cudaMemcpyHostToDevice, e.stream));
+            // a re-grown z buffer invalidates graphs that captured the old pointer
+        }
+        e.sample_chunk(s, z != nullptr, seed, first_index + c0, t_start);
+        if (steps == 0) {
+            // t_start == 1: the loop body never runs (generate_images.jl:236), only the final clamp applies
+            clamp_kernel<<<cdiv((long long)nb * HW, 256), 256, 0, e.stream>>>(xd, (long long)nb * HW);
+            DDPM_LAUNCH_CHECK();
+        }
+        if (out)
+            DDPM_CUDA(cudaMemcpyAsync(out + c0 * HW, xd, (size_t)nb * HW * 4, cudaMemcpyDeviceToHost, e.stream));
+        if (keep_on_device)
+            DDPM_CUDA(cudaMemcpyAsync(e.d_sample_out.as<float>() + c0 * HW, xd, (size_t)nb * HW * 4, cudaMemcpyDeviceToDevice,
+                                      e.stream));
+    }
+    DDPM_CUDA(cudaStreamSynchronize(e.stream));
+}
+
+int ddpm_sample(ddpm_handle* h, const float* x_T, const float* z, uint64_t seed, int64_t N, int64_t first_index,
+                int t_start, float* out) {
+    API_BEGIN
+    Engine& e = E(h);
+    DDPM_CHECK(out != nullptr, "out is null");
+    sample_impl(e, x_T, z, seed, N, first_index, t_start, out, false);
+    API_END
+}
+
+int ddpm_sample_device(ddpm_handle* h, uint64_t seed, int64_t N, int64_t first_index, int t_start) {
+    API_BEGIN
+    Engine& e = E(h);
+    sample_impl(e, nullptr, nullptr, seed, N, first_index, t_start, nullptr, true);
+    API_END
+}
+
+int ddpm_sample_fetch(ddpm_handle* h, int64_t N, float* out) {
+    API_BEGIN
+    Engine& e = E(h);
+    DDPM_CHECK(out && (size_t)N * e.HW * 4 <= e.d_sample_out.cap, "nothing to fetch");
+    DDPM_CUDA(cudaMemcpy(out, e.d_sample_out.p, (size_t)N * e.HW * 4, cudaMemcpyDeviceToHost));
+    API_END
+}
+
+int ddpm_apply_noise_f64(const double* img, const double* eps, int64_t n, const double* betas, int n_betas, double* out) {
+    API_BEGIN
+    DDPM_CHECK(img && eps && betas && out && n > 0 && n_betas > 0, "bad arguments");
+    int ndev = 0;
+    if (cudaGetDeviceCount(&ndev) != cudaSuccess || ndev == 0) throw Error("no CUDA device: libddpm has no CPU fallback");
+    std::vector<double> sa(n_betas), sb(n_betas);
+    for (int k = 0; k < n_betas; ++k) { sa[k] = sqrt(1.0 - betas[k]); sb[k] = sqrt(betas[k]); }
+    double *d_img = nullptr, *d_eps = nullptr, *d_out = nullptr, *d_sa = nullptr, *d_sb = nullptr;
+    auto cleanup = [&]() { cudaFree(d_img); cudaFree(d_eps); cudaFree(d_out); cudaFree(d_sa); cudaFree(d_sb); };
+    try {
+        DDPM_CUDA(cudaMalloc(&d_img, n * 8)); DDPM_CUDA(cudaMalloc(&d_eps, n * 8)); DDPM_CUDA(cudaMalloc(&d_out, n * 8));
+        DDPM_CUDA(cudaMalloc(&d_sa, n_betas * 8)); DDPM_CUDA(cudaMalloc(&d_sb, n_betas * 8));
+        DDPM_CUDA(cudaMemcpy(d_img, img, n * 8, cudaMemcpyHostToDevice));
+        DDPM_CUDA(cudaMemcpy(d_eps, eps, n * 8, cudaMemcpyHostToDevice));
+        DDPM_CUDA(cudaMemcpy(d_sa, sa.data(), n_betas * 8, cudaMemcpyHostToDevice));
+        DDPM_CUDA(cudaMemcpy(d_sb, sb.data(), n_betas * 8, cudaMemcpyHostToDevice));
+        apply_noise_f64_kernel<<<cdiv(n, 256), 256>>>(d_img, d_eps, n, d_sa, d_sb, n_betas, d_out);
+        DDPM_LAUNCH_CHECK();
+        DDPM_CUDA(cudaMemcpy(out, d_out, n * 8, cudaMemcpyDeviceToHost));
+    } catch (...) {
+        cleanup();
+        throw;
+    }
+    cleanup();
+    API_END
+}
+
+// ------------------------------------------------------------------------------------ communicator
+int ddpm_comm_unique_id(void* id_out) {
+    API_BEGIN
+    DDPM_CHECK(id_out != nullptr, "null id buffer");
+    nccl().load();
+    ncclUniqueId id;
+    nccl().check(nccl().GetUniqueId(&id), "ncclGetUniqueId");
+    static_assert(sizeof(ncclUniqueId) == DDPM_NCCL_ID_BYTES, "ncclUniqueId size");
+    std::memcpy(id_out, &id, sizeof id);
+    API_END
+}
+
+int ddpm_comm_init(ddpm_handle* h, const void* id, int rank, int world, int sync_bn) {
+    API_BEGIN
+    Engine& e = E(h);
+    DDPM_CHECK(id && world >= 1 && rank >= 0 && rank < world, "bad communicator arguments");
+    nccl().load();
+    ncclUniqueId uid;
+    std::memcpy(&uid, id, sizeof uid);
+    nccl().check(nccl().CommInitRank(&e.comm, world, uid, rank), "ncclCommInitRank");
+    e.rank = rank; e.world = world; e.sync_bn = sync_bn;
+    API_END
+}
+
+// ------------------------------------------------------------------------------------ instrumentation
+int ddpm_set_option(ddpm_handle* h, const char* key, int64_t value) {
+    API_BEGIN
+    Engine& e = E(h);
+    std::string k = key ? key : "";
+    if (k == "sample_chunk") { DDPM_CHECK(value >= 1, "sample_chunk must be >= 1"); e.opt_sample_chunk = value; }
+    else if (k == "use_graph") e.opt_use_graph = value;
+    else if (k == "conv_impl") { e.opt_conv_impl = value; for (auto& kv : e.infer_sets) kv.second->drop_graphs(); }
+    else if (k == "sync_bn") e.sync_bn = (int)value;
+    else throw Error("unknown option: " + k);
+    API_END
+}
+
+int64_t ddpm_get_counter(ddpm_handle* h, const char* key) {
+    if (!h || !h->eng) return -1;
+    std::string k = key ? key : "";
+    if (k == "launches") return h->eng->cnt_launches;
+    if (k == "n_params") return h->eng->n_params;
+    if (k == "tc_available") return tc::available() ? 1 : 0;
+    if (k == "uses_tc") return h->eng->use_tc() ? 1 : 0;
+    return -1;
+}
+
+int ddpm_timer_start(ddpm_handle* h) {
+    API_BEGIN
+    Engine& e = E(h);
+    DDPM_CUDA(cudaEventRecord(e.ev_t0, e.stream));
+    API_END
+}
+
+int ddpm_timer_stop(ddpm_handle* h, float* ms) {
+    API_BEGIN
+    Engine& e = E(h);
+    DDPM_CHECK(ms != nullptr, "ms is null");
+    DDPM_CUDA(cudaEventRecord(e.ev_t1, e.stream));
+    DDPM_CUDA(cudaEventSynchronize(e.ev_t1));
+    DDPM_CUDA(cudaEventElapsedTime(ms, e.ev_t0, e.ev_t1));
+    API_END
+}
+
+int ddpm_time_kernel(ddpm_handle* h, const char* name, int64_t n_images, int iters, float* ms, double* bytes, double* flops) {
+    API_BEGIN
+    Engine& e = E(h);
+    std::string k = name ? name : "";
+    DDPM_CHECK(n_images > 0 && iters > 0 && ms, "bad arguments");
+    const int N = (int)n_images, HW = e.HW;
+    double by = 0, fl = 0;
+    cudaEvent_t e0, e1;
+    DDPM_CUDA(cudaEventCreate(&e0)); DDPM_CUDA(cudaEventCreate(&e1));
+    auto time_it = [&](auto&& fn) {
+        for (int i = 0; i < 3; ++i) fn();
+        DDPM_CUDA(cudaStreamSynchronize(e.stream));
+        DDPM_CUDA(cudaEventRecord(e0, e.stream));
+        for (int i = 0; i < iters; ++i) fn();
+        DDPM_CUDA(cudaEventRecord(e1, e.stream));
+        DDPM_CUDA(cudaEventSynchronize(e1));
+        float t = 0;
+        DDPM_CUDA(cudaEventElapsedTime(&t, e0, e1));
+        *ms = t / iters;
+    };
+    long long n4 = (long long)N * HW / 4;
+    if (k == "qsample" || k == "mse") {
+        e.d_x0.ensure((size_t)N * HW * 4); e.d_eps.ensure((size_t)N * HW * 4); e.d_xt.ensure((size_t)N * HW * 4);
+        e.d_ts.ensure((size_t)N * 4); e.d_deps.ensure((size_t)N * HW * 4);
+        randn_kernel<<<cdiv(n4, 256), 256, 0, e.stream>>>(e.d_x0.as<float>(), N, HW, 1, 0, 0);
+        randn_kernel<<<cdiv(n4, 256), 256, 0, e.stream>>>(e.d_eps.as<float>(), N, HW, 2, 0, 0);
+        randint_ts_kernel<<<cdiv(N, 256), 256, 0, e.stream>>>(e.d_ts.as<int>(), N, e.T, 3, 0, 0);
+        if (k == "qsample") {
+            time_it([&] {
+                qsample_kernel<<<cdiv(n4, 256), 256, 0, e.stream>>>(e.d_x0.as<float>(), nullptr, e.d_eps.as<float>(),
+                                                                    e.d_ts.as<int>(), e.d_sqrt_ac, e.d_sqrt_1mac,
+                                                                    e.d_xt.as<float>(), N, HW);
+            });
+            by = 12.0 * N * HW;
+        } else {
+            time_it([&] {
+                mse_kernel<<<cdiv(n4, 256), 256, 0, e.stream>>>(e.d_x0.as<float>(), e.d_eps.as<float>(), n4, 1.f, e.misc_sums,
+                                                                nullptr);
+            });
+            by = 8.0 * N * HW;
+        }
+    } else if (k == "adam") {
+        // scratch copies so the timing run does not disturb the optimiser state
+        DevBuf sp, sm, sv;
+        sp.ensure((size_t)e.n_params * 4); sm.ensure((size_t)e.n_params * 4); sv.ensure((size_t)e.n_params * 4);
+        DDPM_CUDA(cudaMemcpyAsync(sp.p, e.P, (size_t)e.n_params * 4, cudaMemcpyDeviceToDevice, e.stream));
+        DDPM_CUDA(cudaMemsetAsync(sm.p, 0, (size_t)e.n_params * 4, e.stream));
+        DDPM_CUDA(cudaMemsetAsync(sv.p, 0, (size_t)e.n_params * 4, e.stream));
+        time_it([&] {
+            adam_kernel<<<cdiv(e.n_params, 256), 256, 0, e.stream>>>(sp.as<float>(), e.G, sm.as<float>(), sv.as<float>(),
+                                                                     e.n_params, e.eta, e.b1, e.b2, e.aeps, e.bt1, e.bt2);
+        });
+        DDPM_CUDA(cudaStreamSynchronize(e.stream));
+        sp.release(); sm.release(); sv.release();
+        by = 28.0 * e.n_params;
+    } else {
+        // network kernels: populate an inference set with a real forward on random input first
+        ActSet& s = e.get_set(N, false);
+        randn_kernel<<<cdiv(n4, 256), 256, 0, e.stream>>>(s.x.as<float>(), N, HW, 1, 0, 0);
+        e.forward(s, s.x.as<float>(), nullptr, e.T / 2, Mode::Infer, false);
+        if (k == "forward_infer") {
+            time_it([&] { e.forward(s, s.x.as<float>(), nullptr, e.T / 2, Mode::Infer, false); });
+            fl = 735.31e6 * N;
+        } else if (k == "reverse_update") {
+            const float* sc = &e.h_samp[(size_t)(e.T / 2) * 4];
+            unsigned long long rng[2] = {7ull, 0ull};
+            DDPM_CUDA(cudaMemcpyAsync(e.d_rng, rng, sizeof rng, cudaMemcpyHostToDevice, e.stream));
+            DDPM_DISPATCH(e.prec, time_it([&] {
+                long long work = (long long)N * HW * 8;
+                final_conv_kernel<TA><<<cdiv(work, 256), 256, 0, e.stream>>>(
+                    s.a[10].cview<TA>(), s.a[10].g, e.arr(kFinalW), e.arr(kFinalB), nullptr, 1, s.x.as<float>(), nullptr,
+                    make_float4(sc[0], sc[1], sc[2], sc[3]), 0ull, reinterpret_cast<const long long*>(e.d_rng), 5u, 0);
+            }));
+            // reads a10 (64 ch) + x, writes x; z is generated in registers
+            by = (double)N * HW * (64.0 * e.esz_a() + 8.0);
+        } else if (k.rfind("conv_l", 0) == 0) {
+            int l = std::atoi(k.c_str() + 6);
+            DDPM_CHECK(l >= 2 && l <= NUM_CONV, "conv layer index must be 2..10");
+            const ConvSpec& c = kConv[l];
+            const Tensor* in0 = nullptr; const Tensor* in1 = nullptr;
+            switch (l) {
+                case 2: in0 = &s.a[1]; break;
+                case 3: in0 = &s.p1; break;
+                case 7: in0 = &s.u; break;
+                case 9: in0 = &s.a[8]; in1 = &s.a[2]; break;
+                default: in0 = &s.a[l - 1];
+            }
+            // inference aliasing: a[l] may alias an input two layers back, never in0/in1
+            DDPM_DISPATCH(e.prec, time_it([&] {
+                e.conv3<TA, TG>(*in0, in1, l, s.a[l], e.inf_scale[l], e.inf_shift[l], 1, nullptr);
+            }));
+            double px = (double)N * c.hw * c.hw;
+            fl = 2.0 * px * c.cout * 9.0 * c.cin;
+            by = px * (c.cin + c.cout) * e.esz_a() + 9.0 * c.cin * c.cout * e.esz_a();
+        } else {
+            throw Error("unknown kernel name: " + k);
+        }
+    }
+    DDPM_LAUNCH_CHECK();
+    DDPM_CUDA(cudaStreamSynchronize(e.stream));
+    cudaEventDestroy(e0); cudaEventDestroy(e1);
+    if (bytes) *bytes = by;
+    if (flops) *flops = fl;
+    API_END
+}
+
+int ddpm_debug_fetch(ddpm_handle* h, const char* name, float* out, int64_t capacity, int64_t* written) {
+    API_BEGIN
+    Engine& e = E(h);
+    std::string k = name ? name : "";
+    DDPM_CUDA(cudaStreamSynchronize(e.stream));
+    ActSet* sp = &e.train_set;
+    if (k.rfind("infer:", 0) == 0) {
+        DDPM_CHECK(!e.infer_sets.empty(), "no inference activations");
+        sp = e.infer_sets.rbegin()->second;
+        k = k.substr(6);
+    }
+    ActSet& s = *sp;
+    DDPM_CHECK(s.N > 0, "no activations recorded yet");
+    const Tensor* t = nullptr;
+    bool grad_type = false;
+    if (k == "p1") t = &s.p1;
+    else if (k == "u") t = &s.u;
+    else if (k == "g32a") { t = &s.g32a; grad_type = true; }
+    else if (k == "g32b") { t = &s.g32b; grad_type = true; }
+    else if (k[0] == 'y') t = &s.y[std::atoi(k.c_str() + 1)];
+    else if (k[0] == 'a') t = &s.a[std::atoi(k.c_str() + 1)];
+    DDPM_CHECK(t && t->base, "unknown or unallocated tensor name");
+    const Geo& g = t->g;
+    long long n_out = (long long)g.N * t->C * g.H * g.W;
+    if (written) *written = n_out;
+    DDPM_CHECK(out && capacity >= n_out, "output buffer too small");
+    std::vector<unsigned char> host(t->bytes);
+    DDPM_CUDA(cudaMemcpy(host.data(), t->base, t->bytes, cudaMemcpyDeviceToHost));
+    const size_t esz = t->esz;
+    for (int n = 0; n < g.N; ++n)
+        for (int hh = 0; hh < g.H; ++hh)
+            for (int ww = 0; ww < g.W; ++ww) {
+                size_t p = (size_t)(g.pos(n, hh, ww) + g.guard) * t->C;
+                for (int c = 0; c < t->C; ++c) {
+                    const unsigned char* src = host.data() + (p + c) * esz;
+                    float v;
+                    if (esz == 4) v = *reinterpret_cast<const float*>(src);
+                    else if (grad_type || e.prec == 2) v = __bfloat162float(*reinterpret_cast<const __nv_bfloat16*>(src));
+                    else v = __half2float(*reinterpret_cast<const __half*>(src));
+                    out[(((size_t)n * t->C + c) * g.H + hh) * g.W + ww] = v;
+                }
+            }
+    API_END
+}
+
+}  // extern "C"

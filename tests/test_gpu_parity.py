@@ -1,0 +1,305 @@
+"""Parity of the CUDA path (through the C ABI) against the CPU oracle.  Needs a B200."""
+import json
+import os
+
+import numpy as np
+import pytest
+import torch
+
+from conftest import ROOT, config2_batch, rel_l2
+
+pytestmark = pytest.mark.gpu
+
+OUT = os.path.join(ROOT, "gpurun_out")
+
+
+def _dump(name, obj):
+    os.makedirs(OUT, exist_ok=True)
+    with open(os.path.join(OUT, name), "w") as fh:
+        json.dump(obj, fh, indent=1, default=float)
+
+
+# ------------------------------------------------------------------------------ bit-exact pieces
+def test_tables_bit_exact(gpu_handles, oracle, tabs):
+    from igdm_b200 import capi
+    h = gpu_handles["fp32"]
+    beta, acum, pe, samp = h.get_tables()
+    assert np.array_equal(beta.view(np.uint32), tabs["beta"].view(np.uint32))
+    assert np.array_equal(samp.view(np.uint32), oracle.sampler_table(tabs["acum"]).view(np.uint32))
+    # the library's built-in default tables (no ddpm_set_tables) equal the host's
+    with capi.Handle(T=500, precision=capi.PREC_FP32) as h2:
+        b2, a2, p2, s2 = h2.get_tables()
+    assert np.array_equal(b2.view(np.uint32), tabs["beta"].view(np.uint32))
+    assert np.array_equal(a2.view(np.uint32), tabs["acum"].view(np.uint32))
+    assert np.array_equal(p2.view(np.uint32), tabs["pe"].view(np.uint32))
+
+
+@pytest.mark.parametrize("B", [1, 52, 64, 257])
+def test_q_sample_bit_exact(gpu_handles, oracle, dataset, tabs, B):
+    h = gpu_handles["fp16"]
+    rng = np.random.default_rng(B)
+    x0 = dataset[rng.integers(0, 500, B)]
+    ts = rng.integers(1, 501, B)
+    ts[0], ts[-1] = 1, 500
+    eps = rng.standard_normal(x0.shape).astype(np.float32)
+    got = h.q_sample(x0, ts, eps)
+    want = oracle.q_sample(x0, ts, eps, tabs["acum"])
+    assert np.array_equal(got.view(np.uint32), want.view(np.uint32))
+
+
+def test_q_sample_properties_full_size(gpu_handles, tabs):
+    """Size-independent properties at the data-parallel batch of config 5 (B=4096)."""
+    h = gpu_handles["fp16"]
+    rng = np.random.default_rng(0)
+    B = 4096
+    x0 = rng.uniform(-1, 1, (B, 1, 32, 32)).astype(np.float32)
+    eps = rng.standard_normal(x0.shape).astype(np.float32)
+    ts = rng.integers(1, 501, B)
+    z = np.zeros_like(x0)
+    a = h.q_sample(x0, ts, z)      # a*x0
+    b = h.q_sample(z, ts, eps)     # b*eps
+    full = h.q_sample(x0, ts, eps)
+    assert np.array_equal(full, a + b)          # fl(a*x0) + fl(b*eps), one rounding of the sum
+    sa = np.sqrt(tabs["acum"][ts - 1]).reshape(-1, 1, 1, 1)
+    assert np.array_equal(a, sa * x0)
+
+
+def test_apply_noise_bit_exact(oracle):
+    from igdm_b200 import capi, tables
+    img = np.full((64, 64), 0.7)          # the reference's own test input (test/runtests.jl:17)
+    eps = np.random.default_rng(7).standard_normal((64, 64))
+    got = capi.apply_noise_f64(img, eps, tables.apply_noise_betas())
+    want = oracle.apply_noise_f64(img, eps)
+    assert np.array_equal(got, want)
+    assert not np.all(got == img)
+    g = np.load(os.path.join(ROOT, "tests", "golden", "oracle_golden.npz"))
+    assert np.array_equal(got, g["apply_noise_64"])
+    # ragged sizes and another schedule
+    img = np.random.default_rng(1).random((5, 13))
+    eps = np.random.default_rng(2).standard_normal((5, 13))
+    got = capi.apply_noise_f64(img, eps, tables.apply_noise_betas(10, 1e-3, 0.05))
+    assert np.array_equal(got, oracle.apply_noise_f64(img, eps, 10, 1e-3, 0.05))
+
+
+# ------------------------------------------------------------------------------ forward parity
+TOL_EPS = {"fp32": 2e-4, "fp16": 1e-2, "bf16": 3e-2}   # north_star: rel-L2 <= 1e-2 (bf16 is a reported mode)
+
+
+@pytest.mark.parametrize("mode", ["fp32", "fp16", "bf16"])
+@pytest.mark.parametrize("train", [False, True])
+def test_predict_eps_parity(gpu_handles, oracle, model_arrays, dataset, tabs, mode, train):
+    h = gpu_handles[mode]
+    h.set_weights(model_arrays)
+    x0, ts, eps = config2_batch(dataset)
+    xt = oracle.q_sample(x0, ts, eps, tabs["acum"])
+    net = oracle.Net(model_arrays)
+    with torch.no_grad():
+        want = oracle.unet_forward(net, torch.tensor(xt), torch.tensor(tabs["pe"][ts - 1]), train=train).numpy()
+    got = h.predict_eps(xt, ts, train_mode=train)
+    r = rel_l2(got, want)
+    _dump(f"eps_parity_{mode}_{'train' if train else 'test'}.json", {"rel_l2": r})
+    assert r <= TOL_EPS[mode], r
+
+
+def test_per_layer_activations_fp32(gpu_handles, oracle, model_arrays, dataset, tabs):
+    """Every intermediate of the train-mode forward against the oracle's taps (FP32 mode)."""
+    h = gpu_handles["fp32"]
+    h.set_weights(model_arrays)
+    B = 8
+    x0, ts, eps = config2_batch(dataset, B)
+    xt = oracle.q_sample(x0, ts, eps, tabs["acum"])
+    taps = {}
+    net = oracle.Net(model_arrays)
+    with torch.no_grad():
+        oracle.unet_forward(net, torch.tensor(xt), torch.tensor(tabs["pe"][ts - 1]), train=True, taps=taps)
+    h.predict_eps(xt, ts, train_mode=True)
+    report = {}
+    names = ["y1", "a1", "y2", "a2", "p1", "y3", "a3", "y4", "a4", "y5", "a5", "y6", "a6", "u", "y7", "a7", "y8", "a8",
+             "y9", "a9", "y10", "a10"]
+    for nm in names:
+        want = taps["h1" if nm == "a2" else nm].numpy()
+        got = h.debug_fetch(nm).reshape(want.shape)
+        report[nm] = rel_l2(got, want)
+    _dump("per_layer_fp32.json", report)
+    bad = {k: v for k, v in report.items() if v > 2e-4}
+    assert not bad, bad
+
+
+def test_known_answer_through_abi(gpu_handles, model_arrays, tabs):
+    """SURVEY.md Appendix F network known answers (B=1, test mode), FP32 mode."""
+    h = gpu_handles["fp32"]
+    h.set_weights(model_arrays)
+    i = np.arange(1, 33, dtype=np.float64)
+    x = (np.sin(0.1 * i)[None, :] * np.cos(0.07 * i)[:, None] + 0.01 * i[None, :]).astype(np.float32)
+    want = {2: (1.610716, 1.288811, 0.588145, 0.287682, 0.381552), 500: (0.644030, 0.699858, 0.081792, 0.104264, 0.507330)}
+    for t, w in want.items():
+        e = h.predict_eps(x.reshape(1, 1, 32, 32), np.array([t]))[0, 0]
+        J = lambda a, b: e[b - 1, a - 1]
+        got = (J(1, 1), J(32, 1), J(1, 32), J(5, 20), J(20, 5))
+        assert np.allclose(got, w, atol=5e-5), (t, got, w)
+
+
+# ------------------------------------------------------------------------------ backward parity
+GRAD_TOL = {"fp32": 2e-3, "fp16": 6e-2, "bf16": 1.5e-1}
+
+
+@pytest.mark.parametrize("mode", ["fp32", "fp16", "bf16"])
+def test_loss_and_grad_parity(gpu_handles, oracle, model_arrays, dataset, tabs, mode):
+    h = gpu_handles[mode]
+    h.set_weights(model_arrays)
+    B = 64
+    x0, ts, eps = config2_batch(dataset, B)
+    net = oracle.Net(model_arrays)
+    loss_t, _, _ = oracle.train_step_loss(net, x0, ts, eps, tabs["acum"], tabs["pe"], update_stats=False)
+    loss_t.backward()
+    want_loss = float(loss_t.detach())
+    loss, grads = h.loss_and_grad(x0, ts, eps)
+    mask = oracle.trainable_mask()
+    report = {"loss": loss, "loss_oracle": want_loss}
+    worst = 0.0
+    for k in range(64):
+        if not mask[k]:
+            assert not grads[k].any()          # running statistics carry no gradient
+            continue
+        want = net.flat[k].grad.numpy().ravel()
+        wn = float(np.linalg.norm(want))
+        if wn < 1e-5:
+            # conv bias in front of a train-mode BatchNorm: exactly zero in exact arithmetic
+            report[f"g{k}"] = {"norm": float(np.linalg.norm(grads[k])), "oracle_norm": wn, "zero": True}
+            assert np.linalg.norm(grads[k]) < 1e-2 * max(1.0, np.sqrt(B))
+            continue
+        r = rel_l2(grads[k], want)
+        report[f"g{k}"] = {"rel": r, "norm": wn}
+        worst = max(worst, r)
+    _dump(f"grad_parity_{mode}.json", report)
+    assert abs(loss - want_loss) <= 1e-3 * want_loss, (loss, want_loss)
+    assert worst <= GRAD_TOL[mode], report
+
+
+@pytest.mark.parametrize("mode", ["fp32", "fp16"])
+def test_training_epoch_loss_parity(gpu_handles, oracle, model_arrays, dataset, tabs, mode):
+    """one epoch = 7x64 + 52 images, Adam eta=1e-4, host-supplied
+    permutation / ts / eps; per-step loss within 1e-3 relative of the CPU oracle."""
+    h = gpu_handles[mode]
+    h.set_weights(model_arrays)
+    h.set_adam(1e-4, 0.9, 0.999, 1e-8)
+    perm = np.random.default_rng(3).permutation(500)
+    net = oracle.Net(model_arrays)
+    opt = oracle.Adam(net.trainable(), eta=1e-4)
+    rows = []
+    for bi, i0 in enumerate(range(0, 500, 64)):
+        sel = perm[i0:i0 + 64]
+        x0 = dataset[sel]
+        ts = np.random.default_rng(1000 + bi).integers(1, 501, len(sel))
+        eps = np.random.default_rng(2000 + bi).standard_normal(x0.shape).astype(np.float32)
+        want, _ = oracle.train_step(net, opt, x0, ts, eps, tabs["acum"], tabs["pe"])
+        got = h.train_step(x0, ts, eps)
+        rows.append({"B": len(sel), "loss": got, "oracle": want, "rel": abs(got - want) / want})
+    # weights and running statistics after the epoch
+    w_gpu = h.get_weights()
+    w_cpu = net.arrays()
+    stats = {}
+    for k in (6, 10, 11, 36, 60, 61, 62):
+        stats[f"w{k}"] = rel_l2(w_gpu[k], w_cpu[k])
+    _dump(f"train_epoch_{mode}.json", {"steps": rows, "weights": stats})
+    assert len(rows) == 8 and rows[-1]["B"] == 52
+    assert max(r["rel"] for r in rows) <= 1e-3, rows
+    h.set_weights(model_arrays)
+
+
+# ------------------------------------------------------------------------------ sampler
+def test_sampler_host_noise_parity_fp32(gpu_handles, oracle, model_arrays, tabs):
+    h = gpu_handles["fp32"]
+    h.set_weights(model_arrays)
+    g = np.load(os.path.join(ROOT, "tests", "golden", "oracle_golden.npz"))
+    xT = np.random.default_rng(5).standard_normal((2, 1, 32, 32)).astype(np.float32)
+    z = np.random.default_rng(6).standard_normal((5, 2, 1, 32, 32)).astype(np.float32)
+    got = h.sample(2, x_T=xT, z=z, t_start=6)
+    assert np.abs(got - g["samp_t6"]).max() < 2e-4
+    assert np.abs(got).max() <= 1.0
+
+
+@pytest.mark.parametrize("mode,tol", [("fp32", 5e-3), ("fp16", 5e-2)])
+def test_sampler_full_500_steps(gpu_handles, oracle, model_arrays, tabs, mode, tol):
+    """BASELINE config 1: generate_image(num_images=1) -- all 499 evaluations on identical host noise."""
+    h = gpu_handles[mode]
+    h.set_weights(model_arrays)
+    N, T = 2, 500
+    xT = np.random.default_rng(0).standard_normal((N, 1, 32, 32)).astype(np.float32)
+    z = np.random.default_rng(1).standard_normal((T - 1, N, 1, 32, 32)).astype(np.float32)
+    want = oracle.generate_image(oracle.Net(model_arrays), xT, z, tabs["acum"], tabs["pe"])
+    got = h.sample(N, x_T=xT, z=z, t_start=T)
+    err = float(np.abs(got - want).mean())
+    _dump(f"sample500_{mode}.json", {"mean_abs_err": err, "max_abs_err": float(np.abs(got - want).max())})
+    assert err < tol, err
+    assert np.abs(got).max() <= 1.0
+    # graph replay == eager launch sequence
+    h.set_option("use_graph", 0)
+    eager = h.sample(N, x_T=xT, z=z, t_start=20)
+    h.set_option("use_graph", 1)
+    graph = h.sample(N, x_T=xT, z=z, t_start=20)
+    assert np.array_equal(eager, graph)
+
+
+def test_device_rng_matches_oracle_stream(gpu_handles, oracle):
+    """t_start=1 runs zero reverse steps (generate_images.jl:236) => output = clamp(x_T); x_T comes
+    from the device Philox stream keyed by (seed, global image index, step 0)."""
+    h = gpu_handles["fp16"]
+    got = h.sample(5, seed=1234, first_index=7, t_start=1).reshape(5, -1)
+    want = np.clip(oracle.device_normal(1234, np.arange(7, 12), 0), -1, 1)
+    assert np.abs(got - want).max() < 1e-5
+    raw = oracle.device_normal(99, np.arange(256), 3)
+    assert abs(raw.mean()) < 0.01 and abs(raw.std() - 1) < 0.01
+
+
+def test_sampling_is_shard_and_chunk_invariant(gpu_handles):
+    """Outputs depend only on (seed, global image index): splitting N across calls / GPUs / chunks
+    does not change a bit (sampling shards with no collective)."""
+    h = gpu_handles["fp16"]
+    t0 = 12
+    whole = h.sample(6, seed=5, first_index=100, t_start=t0)
+    a = h.sample(4, seed=5, first_index=100, t_start=t0)
+    b = h.sample(2, seed=5, first_index=104, t_start=t0)
+    assert np.array_equal(whole, np.concatenate([a, b]))
+    h.set_option("sample_chunk", 4)
+    chunked = h.sample(6, seed=5, first_index=100, t_start=t0)
+    h.set_option("sample_chunk", 256)
+    assert np.array_equal(whole, chunked)
+    other = h.sample(6, seed=6, first_index=100, t_start=t0)
+    assert not np.array_equal(whole, other)
+    h.sample_device(6, seed=5, first_index=100, t_start=t0)
+    assert np.array_equal(h.sample_fetch(6), whole)
+
+
+def test_error_behaviour(gpu_handles, model_arrays):
+    from igdm_b200 import capi
+    h = gpu_handles["fp32"]
+    x = np.zeros((2, 1, 32, 32), np.float32)
+    with pytest.raises(capi.DDPMError, match="timestep"):
+        h.predict_eps(x, np.array([0, 3]))
+    with pytest.raises(capi.DDPMError, match="timestep"):
+        h.q_sample(x, np.array([1, 501]), x)
+    with pytest.raises(ValueError):
+        h.set_weights(model_arrays[:10])
+    with pytest.raises(capi.DDPMError):
+        h.sample(1, t_start=0)
+    assert h.counter("launches") > 0
+
+
+def test_public_api_smoke(tmp_path, model_arrays):
+    """The reference's own smoke tests (test/runtests.jl) restated on the host mirror."""
+    from igdm_b200 import api
+    os.chdir(tmp_path)
+    img = np.full((64, 64), 0.7)
+    noisy = api.apply_noise(img)
+    assert not np.all(noisy == img) and os.path.isfile("noisy_img.png")
+    den = api.denoise_image(np.clip(api.apply_noise(np.full((32, 32), 0.5), out_path=None), 0, 1), t_start=30)
+    assert den.shape == (32, 32) and os.path.isfile("denoised_img.png") and den.min() >= 0 and den.max() <= 1
+    gen = api.generate_image(num_images=2, T=500, seed=1)
+    assert gen.shape == (2, 1, 32, 32) and np.abs(gen).max() <= 1
+    res = api.train(epochs=1, save_dir=str(tmp_path), log=None, rng=np.random.default_rng(0),
+                    model=api.SimpleUNet.load())
+    assert len(res.losses) == 1 and len(res.step_losses) == 8 and os.path.isfile("trained_model.bson")
+    assert 0.05 < res.losses[0] < 0.2
+    back = api.SimpleUNet.load(str(tmp_path / "trained_model.bson"))
+    assert np.array_equal(back.arrays[0], res.model.arrays[0])
