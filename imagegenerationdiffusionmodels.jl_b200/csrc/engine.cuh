@@ -644,8 +644,8 @@ template <typename TA, typename TG>
 void Engine::final_conv_t(ActSet& s, float* eps_hat_dev) {
     long long work = (long long)s.N * HW * 8;
     final_conv_kernel<TA><<<cdiv(work, 256), 256, 0, stream>>>(s.a[10].cview<TA>(), s.a[10].g, arr(kFinalW), arr(kFinalB),
-                                                               eps_hat_dev, 0, nullptr, nullptr, make_float4(0, 0, 0, 0), 0ull,
-                                                               nullptr, 0u, 0);
+                                                               eps_hat_dev, 0, nullptr, nullptr, make_float4(0, 0, 0, 0), nullptr,
+                                                               0u, 0);
     DDPM_LAUNCH_CHECK();
     cnt_launches += 1;
 }
@@ -847,8 +847,8 @@ void Engine::sample_steps_t(ActSet& s, float* x_dev, const float* z_dev, int N, 
         long long work = (long long)N * HW * 8;
         final_conv_kernel<TA><<<cdiv(work, 256), 256, 0, stream>>>(
             s.a[10].cview<TA>(), s.a[10].g, arr(kFinalW), arr(kFinalB), nullptr, 1, x_dev,
-            z_dev ? z_dev + (size_t)k * N * HW : nullptr, make_float4(sc[0], sc[1], sc[2], sc[3]), 0ull,
-            reinterpret_cast<const long long*>(d_rng), (uint32_t)t, t == 2 ? 1 : 0);
+            z_dev ? z_dev + (size_t)k * N * HW : nullptr, make_float4(sc[0], sc[1], sc[2], sc[3]), d_rng, (uint32_t)t,
+            t == 2 ? 1 : 0);
         cnt_launches += 1;
     }
     DDPM_LAUNCH_CHECK();

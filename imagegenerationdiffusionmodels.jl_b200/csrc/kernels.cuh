@@ -327,8 +327,8 @@ template <typename TA>
 __global__ void __launch_bounds__(256)
 final_conv_kernel(View<const TA> a, Geo g, const float* __restrict__ wf, const float* __restrict__ bf,
                   float* __restrict__ eps_hat, int mode, float* __restrict__ x, const float* __restrict__ zbuf,
-                  float4 scal /*sigma_t, sqrt_at, sqrt_aprev, sqrt_pv*/, unsigned long long seed,
-                  const long long* __restrict__ first_index_dev, uint32_t step, int final_clamp) {
+                  float4 scal /*sigma_t, sqrt_at, sqrt_aprev, sqrt_pv*/,
+                  const unsigned long long* __restrict__ rng_dev /*[seed, first_index]*/, uint32_t step, int final_clamp) {
     long long idx = (long long)blockIdx.x * 256 + threadIdx.x;
     long long pix = idx >> 3;
     int c0 = (int)(idx & 7) * 8;
@@ -358,8 +358,8 @@ final_conv_kernel(View<const TA> a, Geo g, const float* __restrict__ wf, const f
     if (zbuf) {
         z = zbuf[pix];
     } else {
-        long long fi = first_index_dev ? *first_index_dev : 0;
-        float4 zz = Philox::normal4(seed, (unsigned long long)(fi + n), step, (uint32_t)(rem >> 2));
+        // seed and first image index live in device memory so one captured graph serves every chunk
+        float4 zz = Philox::normal4(rng_dev[0], rng_dev[1] + (unsigned long long)n, step, (uint32_t)(rem >> 2));
         int k = rem & 3;
         z = k == 0 ? zz.x : (k == 1 ? zz.y : (k == 2 ? zz.z : zz.w));
     }

@@ -468,7 +468,7 @@ int ddpm_time_kernel(ddpm_handle* h, const char* name, int64_t n_images, int ite
                 long long work = (long long)N * HW * 8;
                 final_conv_kernel<TA><<<cdiv(work, 256), 256, 0, e.stream>>>(
                     s.a[10].cview<TA>(), s.a[10].g, e.arr(kFinalW), e.arr(kFinalB), nullptr, 1, s.x.as<float>(), nullptr,
-                    make_float4(sc[0], sc[1], sc[2], sc[3]), 0ull, reinterpret_cast<const long long*>(e.d_rng), 5u, 0);
+                    make_float4(sc[0], sc[1], sc[2], sc[3]), e.d_rng, 5u, 0);
             }));
             // reads a10 (64 ch) + x, writes x; z is generated in registers
             by = (double)N * HW * (64.0 * e.esz_a() + 8.0);
