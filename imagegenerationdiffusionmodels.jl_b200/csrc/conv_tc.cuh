@@ -1,23 +1,485 @@
-// tcgen05 (5th-gen tensor core) implicit-GEMM kernels.  Entry points return false when they do
-// not handle a case; the engine then runs the CUDA-core kernel of igemm_simt.cuh instead.
+// tcgen05 (5th-generation tensor core) implicit-GEMM convolution for sm_100a.
+//
+// Formulation ("shifted-window implicit GEMM on the padded position matrix"):
+// activations are a 2-D matrix [position][channel] over the zero-padded, image-stacked position
+// space of common.cuh, so the 3x3 tap (dy,dx) is the constant row shift dy*(W+2)+dx.  For one
+// M-tile of 128 consecutive positions a CTA
+//   1. TMA-loads ONE halo'ed slab of rows [m0-(Wp+1), m0+128+(Wp+1)) x 64 channels into shared memory
+//      (128B-swizzled, K-major) -- 1.5x the tile instead of the 9x an im2col gather would move;
+//   2. issues 9 taps x 4 K-steps of tcgen05.mma (M=128, N=64|128, K=16, kind::f16, FP32 accumulate
+//      in TMEM); tap (dy,dx) is just the shared-memory matrix descriptor advanced by that many
+//      128-byte rows -- no data is moved between taps;
+//   3. drains the accumulator with tcgen05.ld in 4 epilogue warps: y = acc*scale[c]+shift[c], ReLU,
+//      convert, store valid positions (halo positions are never written and stay zero).
+// The 9*Cin x Cout weights stay resident in shared memory for the lifetime of the persistent CTA.
+// Warp roles: warp 0 = TMA producer, warp 1 = MMA issuer (one thread), warps 2..5 = epilogue;
+// smem full/empty ring (TMA <-> MMA) and a 2-deep TMEM full/empty ring (MMA <-> epilogue).
+//
+// Replaces NNlib.conv / ∇conv_data (im2col + SGEMM) behind Flux.Conv at
+// /root/reference/src/train_brain.jl:113-140 (forward) and Zygote's pullback (:267-269).
 #pragma once
+#include <cuda.h>
+#include <map>
+#include <tuple>
 #include "common.cuh"
 
 namespace ddpm {
 namespace tc {
 
-inline bool available() { return false; }
-inline void init() {}
+// ------------------------------------------------------------------------------------ PTX wrappers
+__device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
 
+__device__ __forceinline__ void mbar_init(uint32_t bar, uint32_t count) {
+    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(bar), "r"(count) : "memory");
+}
+__device__ __forceinline__ void mbar_expect_tx(uint32_t bar, uint32_t bytes) {
+    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bar), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void mbar_arrive(uint32_t bar) {
+    asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(bar) : "memory");
+}
+__device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t parity) {
+    uint32_t done = 0;
+    unsigned long long spins = 0;
+    do {
+        asm volatile(
+            "{\n\t.reg .pred p;\n\t"
+            "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\t"
+            "selp.u32 %0, 1, 0, p;\n\t}"
+            : "=r"(done)
+            : "r"(bar), "r"(parity)
+            : "memory");
+        if (!done && ++spins > (1ull << 26)) __trap();  // a lost arrival must fault, never hang the GPU
+    } while (!done);
+}
+__device__ __forceinline__ void fence_barrier_init() { asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory"); }
+__device__ __forceinline__ void fence_proxy_async() { asm volatile("fence.proxy.async.shared::cta;" ::: "memory"); }
+__device__ __forceinline__ void tc_fence_before() { asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory"); }
+__device__ __forceinline__ void tc_fence_after() { asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory"); }
+
+__device__ __forceinline__ void tma_load_2d(uint32_t dst, const CUtensorMap* map, int c0, int c1, uint32_t bar) {
+    asm volatile(
+        "cp.async.bulk.tensor.2d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4}], [%2];"
+        ::"r"(dst), "l"(map), "r"(bar), "r"(c0), "r"(c1)
+        : "memory");
+}
+__device__ __forceinline__ void prefetch_tmap(const CUtensorMap* map) {
+    asm volatile("prefetch.tensormap [%0];" ::"l"(map) : "memory");
+}
+
+template <int COLS>
+__device__ __forceinline__ void tmem_alloc(uint32_t dst_smem) {
+    uint32_t ncols = COLS;
+    asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(dst_smem), "r"(ncols) : "memory");
+    asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+}
+template <int COLS>
+__device__ __forceinline__ void tmem_dealloc(uint32_t taddr) {
+    uint32_t ncols = COLS;
+    asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(taddr), "r"(ncols) : "memory");
+}
+// D[tmem] (+)= A[smem] * B[smem], single-CTA, kind::f16 (FP16/BF16 inputs, FP32 accumulate)
+__device__ __forceinline__ void umma_f16(uint32_t d_tmem, uint64_t a_desc, uint64_t b_desc, uint32_t idesc, uint32_t accumulate) {
+    asm volatile(
+        "{\n\t.reg .pred p;\n\t"
+        "setp.ne.b32 p, %4, 0;\n\t"
+        "tcgen05.mma.cta_group::1.kind::f16 [%0], %1, %2, %3, p;\n\t}"
+        ::"r"(d_tmem), "l"(a_desc), "l"(b_desc), "r"(idesc), "r"(accumulate)
+        : "memory");
+}
+// arrive on an mbarrier when all previously issued tcgen05.mma of this thread have completed
+__device__ __forceinline__ void umma_commit(uint32_t bar) {
+    asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(bar) : "memory");
+}
+// 32 lanes x 16 consecutive 32-bit columns -> 16 registers per thread (thread i <-> lane base+i)
+__device__ __forceinline__ void tmem_ld16(uint32_t taddr, uint32_t r[16]) {
+    asm volatile(
+        "tcgen05.ld.sync.aligned.32x32b.x16.b32 {%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15}, [%16];"
+        : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]), "=r"(r[8]),
+          "=r"(r[9]), "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15])
+        : "r"(taddr)
+        : "memory");
+}
+__device__ __forceinline__ void tmem_ld_wait() { asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory"); }
+
+// shared-memory matrix descriptor, K-major operand, 128-byte swizzle: rows of 64 16-bit elements
+// (128 B), 8-row core groups 1024 B apart (SBO); start may be advanced by whole rows and by
+// 32-byte K-steps inside the swizzle atom (the XOR pattern is a function of the address bits).
+__device__ __forceinline__ uint64_t make_desc_sw128(uint32_t saddr, uint32_t base_offset_mode) {
+    uint64_t d = 0;
+    d |= (uint64_t)((saddr & 0x3FFFFu) >> 4);
+    d |= (uint64_t)1 << 16;                      // LBO (unused for swizzled K-major) = 16 B
+    d |= (uint64_t)(1024 >> 4) << 32;            // SBO = 1024 B
+    d |= (uint64_t)1 << 46;                      // descriptor version (Blackwell)
+    if (base_offset_mode) d |= (uint64_t)((saddr >> 7) & 7u) << 49;
+    d |= (uint64_t)2 << 61;                      // SWIZZLE_128B
+    return d;
+}
+
+template <typename T> struct IsBf16 { static constexpr uint32_t v = 0; };
+template <> struct IsBf16<__nv_bfloat16> { static constexpr uint32_t v = 1; };
+
+// instruction descriptor for kind::f16: D=F32, A/B = F16 or BF16, both K-major, M x N tile
+__host__ __device__ constexpr uint32_t make_idesc(uint32_t fmt, uint32_t M, uint32_t N) {
+    return (1u << 4) | (fmt << 7) | (fmt << 10) | ((N >> 3) << 17) | ((M >> 4) << 24);
+}
+
+// ------------------------------------------------------------------------------------ kernel
+constexpr int TC_THREADS = 192;
+constexpr int TC_BM = 128;
+
+template <typename TOut>
+__device__ __forceinline__ void store16(TOut* p, const float v[16]);
+template <>
+__device__ __forceinline__ void store16<__half>(__half* p, const float v[16]) {
+    uint4 a, b;
+    __half2* ha = reinterpret_cast<__half2*>(&a);
+    __half2* hb = reinterpret_cast<__half2*>(&b);
+#pragma unroll
+    for (int i = 0; i < 4; ++i) { ha[i] = __floats2half2_rn(v[2 * i], v[2 * i + 1]); hb[i] = __floats2half2_rn(v[8 + 2 * i], v[9 + 2 * i]); }
+    *reinterpret_cast<uint4*>(p) = a;
+    *reinterpret_cast<uint4*>(p + 8) = b;
+}
+template <>
+__device__ __forceinline__ void store16<__nv_bfloat16>(__nv_bfloat16* p, const float v[16]) {
+    uint4 a, b;
+    __nv_bfloat162* ha = reinterpret_cast<__nv_bfloat162*>(&a);
+    __nv_bfloat162* hb = reinterpret_cast<__nv_bfloat162*>(&b);
+#pragma unroll
+    for (int i = 0; i < 4; ++i) { ha[i] = __floats2bfloat162_rn(v[2 * i], v[2 * i + 1]); hb[i] = __floats2bfloat162_rn(v[8 + 2 * i], v[9 + 2 * i]); }
+    *reinterpret_cast<uint4*>(p) = a;
+    *reinterpret_cast<uint4*>(p + 8) = b;
+}
+
+struct TcParams {
+    void* out;            // position 0 of the output tensor
+    int out_cs;           // channel stride (elements) of the output tensor
+    Geo g;                // geometry of the A operand rows (== output geometry for convs)
+    Geo g_out;            // EPI==1 only: fine geometry of the ConvTranspose output
+    const float* scale;   // per output channel, nullptr -> 1
+    const float* shift;   // per output channel, nullptr -> 0   (EPI==1: bias)
+    int relu;
+    int num_m_tiles;
+    int chunk1_src1;      // 1: K-chunk 1 comes from the second tensor map (channel concat), 0: channels 64.. of the first
+    int base_offset_mode; // descriptor base-offset variant (hardware probe, see tests)
+};
+
+// TAPS: 9 (3x3 conv, halo'ed slab) or 1 (plain GEMM rows); CHUNKS: 64-channel K chunks (1|2);
+// NOUT: output channels handled by this CTA (64|128); WP: padded row width (W+2) for TAPS==9
+// EPI: 0 = conv store on the same geometry, 1 = ConvTranspose 2x2 pixel shuffle (blockIdx.y = q)
+template <int TAPS, int CHUNKS, int NOUT, int WP, int STAGES, int EPI, typename TIn, typename TOut>
+__global__ void __launch_bounds__(TC_THREADS, 1)
+conv_tc_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constant__ CUtensorMap tmA1,
+               const __grid_constant__ CUtensorMap tmW, const TcParams p) {
+    constexpr int HALO = (TAPS == 9) ? (WP + 1) : 0;
+    constexpr int R = ((TC_BM + 2 * HALO + 7) / 8) * 8;       // slab rows (multiple of 8 -> 1024 B multiple)
+    constexpr uint32_t A_STAGE_BYTES = R * 128;
+    constexpr uint32_t W_TILE_BYTES = NOUT * 128;              // one (tap, chunk) weight tile [NOUT][64]
+    constexpr uint32_t W_BYTES = TAPS * CHUNKS * W_TILE_BYTES;
+    constexpr int TMEM_COLS = (2 * NOUT <= 128) ? 128 : 256;
+    constexpr uint32_t IDESC = make_idesc(IsBf16<TIn>::v, TC_BM, NOUT);
+
+    extern __shared__ uint8_t smem_raw[];
+    uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
+    const uint32_t s_w = smem_u32(smem);
+    const uint32_t s_a = s_w + W_BYTES;
+    const uint32_t s_bar = s_a + STAGES * A_STAGE_BYTES;
+    // barrier slots (8 B each): [0] w_full, [1..S] a_full, [1+S..2S] a_empty, [1+2S, 2+2S] acc_full, [3+2S, 4+2S] acc_empty
+    auto bar_w = [&]() { return s_bar; };
+    auto bar_afull = [&](int s) { return s_bar + 8u * (1 + s); };
+    auto bar_aempty = [&](int s) { return s_bar + 8u * (1 + STAGES + s); };
+    auto bar_accfull = [&](int b) { return s_bar + 8u * (1 + 2 * STAGES + b); };
+    auto bar_accempty = [&](int b) { return s_bar + 8u * (3 + 2 * STAGES + b); };
+    uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(smem + W_BYTES + STAGES * A_STAGE_BYTES + 8 * (5 + 2 * STAGES));
+
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const int n_blk = blockIdx.y;                 // N-slice (conv: half of Cout; up2: sub-position q)
+
+    if (warp == 0 && lane == 0) {
+        prefetch_tmap(&tmA0); prefetch_tmap(&tmW);
+        if (p.chunk1_src1) prefetch_tmap(&tmA1);
+        mbar_init(bar_w(), 1);
+        for (int s = 0; s < STAGES; ++s) { mbar_init(bar_afull(s), 1); mbar_init(bar_aempty(s), 1); }
+        for (int b = 0; b < 2; ++b) { mbar_init(bar_accfull(b), 1); mbar_init(bar_accempty(b), 4); }
+        fence_barrier_init();
+    }
+    if (warp == 2) tmem_alloc<TMEM_COLS>(smem_u32(tmem_slot));
+    tc_fence_before();
+    __syncthreads();
+    tc_fence_after();
+    const uint32_t tmem_base = *tmem_slot;
+
+    if (warp == 0) {
+        // ================= TMA producer =================
+        if (lane == 0) {
+            mbar_expect_tx(bar_w(), W_BYTES);
+            for (int t = 0; t < TAPS; ++t)
+                for (int c = 0; c < CHUNKS; ++c)
+                    tma_load_2d(s_w + (t * CHUNKS + c) * W_TILE_BYTES, &tmW, (t * CHUNKS + c) * 64, n_blk * NOUT, bar_w());
+            int stage = 0;
+            uint32_t phase = 0;
+            for (int tile = blockIdx.x; tile < p.num_m_tiles; tile += gridDim.x) {
+                const int row0 = tile * TC_BM - HALO + p.g.guard;   // row coordinate in the tensor map (base = allocation start)
+                for (int c = 0; c < CHUNKS; ++c) {
+                    mbar_wait(bar_aempty(stage), phase ^ 1);
+                    mbar_expect_tx(bar_afull(stage), A_STAGE_BYTES);
+                    const bool second = (c == 1) && p.chunk1_src1;
+                    tma_load_2d(s_a + stage * A_STAGE_BYTES, second ? &tmA1 : &tmA0, second ? 0 : c * 64, row0, bar_afull(stage));
+                    if (++stage == STAGES) { stage = 0; phase ^= 1; }
+                }
+            }
+        }
+        __syncwarp();
+    } else if (warp == 1) {
+        // ================= MMA issuer (one thread) =================
+        if (lane == 0) {
+            mbar_wait(bar_w(), 0);
+            tc_fence_after();
+            int stage = 0;
+            uint32_t phase = 0;
+            int buf = 0;
+            uint32_t acc_phase = 0;
+            for (int tile = blockIdx.x; tile < p.num_m_tiles; tile += gridDim.x) {
+                mbar_wait(bar_accempty(buf), acc_phase ^ 1);
+                tc_fence_after();
+                const uint32_t d_tmem = tmem_base + buf * NOUT;
+                uint32_t accumulate = 0;
+                for (int c = 0; c < CHUNKS; ++c) {
+                    mbar_wait(bar_afull(stage), phase);
+                    tc_fence_after();
+                    const uint32_t a_base = s_a + stage * A_STAGE_BYTES;
+#pragma unroll
+                    for (int t = 0; t < TAPS; ++t) {
+                        const int shift = (TAPS == 9) ? (HALO + (t / 3 - 1) * WP + (t % 3 - 1)) : 0;
+                        const uint32_t a_tap = a_base + shift * 128;
+                        const uint32_t b_tap = s_w + (t * CHUNKS + c) * W_TILE_BYTES;
+#pragma unroll
+                        for (int ks = 0; ks < 4; ++ks) {
+                            umma_f16(d_tmem, make_desc_sw128(a_tap + ks * 32, p.base_offset_mode),
+                                     make_desc_sw128(b_tap + ks * 32, 0), IDESC, accumulate);
+                            accumulate = 1;
+                        }
+                    }
+                    umma_commit(bar_aempty(stage));          // slab may be overwritten once these MMAs retire
+                    if (++stage == STAGES) { stage = 0; phase ^= 1; }
+                }
+                umma_commit(bar_accfull(buf));               // accumulator ready for the epilogue
+                if (++buf == 2) { buf = 0; acc_phase ^= 1; }
+            }
+        }
+        __syncwarp();
+    } else {
+        // ================= epilogue warps (TMEM -> registers -> global) =================
+        const int lane_grp = warp & 3;                       // TMEM lanes 32*lane_grp .. +31 are visible to this warp
+        const int row = lane_grp * 32 + lane;
+        int buf = 0;
+        uint32_t acc_phase = 0;
+        TOut* out = reinterpret_cast<TOut*>(p.out);
+        for (int tile = blockIdx.x; tile < p.num_m_tiles; tile += gridDim.x) {
+            const long long pos = (long long)tile * TC_BM + row;
+            int n_img, hh, ww;
+            const bool valid = p.g.decode(pos, n_img, hh, ww);
+            long long opos = pos;
+            int ch_off = n_blk * NOUT;
+            if (EPI == 1) {
+                if (valid) opos = p.g_out.pos(n_img, 2 * hh + (n_blk >> 1), 2 * ww + (n_blk & 1));
+                ch_off = 0;
+            }
+            mbar_wait(bar_accfull(buf), acc_phase);
+            tc_fence_after();
+            const uint32_t taddr = tmem_base + ((uint32_t)(lane_grp * 32) << 16) + buf * NOUT;
+#pragma unroll
+            for (int c0 = 0; c0 < NOUT; c0 += 32) {
+                uint32_t r0[16], r1[16];
+                tmem_ld16(taddr + c0, r0);
+                tmem_ld16(taddr + c0 + 16, r1);
+                tmem_ld_wait();
+                if (valid) {
+                    float v[16];
+#pragma unroll
+                    for (int half = 0; half < 2; ++half) {
+                        const uint32_t* r = half ? r1 : r0;
+                        const int cb = c0 + half * 16;
+#pragma unroll
+                        for (int j = 0; j < 16; ++j) {
+                            const int co = (EPI == 1) ? (cb + j) : (ch_off + cb + j);
+                            float x = __uint_as_float(r[j]);
+                            x = x * (p.scale ? __ldg(p.scale + co) : 1.f) + (p.shift ? __ldg(p.shift + co) : 0.f);
+                            v[j] = p.relu ? fmaxf(x, 0.f) : x;
+                        }
+                        store16<TOut>(out + opos * p.out_cs + ch_off + cb, v);
+                    }
+                }
+            }
+            tc_fence_before();
+            __syncwarp();
+            if (lane == 0) mbar_arrive(bar_accempty(buf));
+            if (++buf == 2) { buf = 0; acc_phase ^= 1; }
+        }
+    }
+    tc_fence_before();
+    __syncthreads();
+    if (warp == 2) {
+        tc_fence_after();
+        tmem_dealloc<TMEM_COLS>(tmem_base);
+    }
+}
+
+// ------------------------------------------------------------------------------------ host side
+typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*, const cuuint64_t*,
+                                  const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave, CUtensorMapSwizzle,
+                                  CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+
+struct State {
+    EncodeTiledFn encode = nullptr;
+    bool ok = false;
+    int num_sms = 148;
+    int base_offset_mode = 0;
+    bool enabled = true;
+};
+inline State& state() {
+    static State s;
+    return s;
+}
+
+inline void init() {
+    State& s = state();
+    if (s.encode) return;
+    void* fn = nullptr;
+    cudaDriverEntryPointQueryResult qres;
+    cudaError_t e = cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &fn, cudaEnableDefault, &qres);
+    if (e != cudaSuccess || qres != cudaDriverEntryPointSuccess || !fn) {
+        cudaGetLastError();
+        s.ok = false;
+        return;
+    }
+    s.encode = reinterpret_cast<EncodeTiledFn>(fn);
+    int dev = 0;
+    cudaGetDevice(&dev);
+    cudaDeviceGetAttribute(&s.num_sms, cudaDevAttrMultiProcessorCount, dev);
+    s.ok = true;
+}
+inline bool available() { return state().ok && state().enabled; }
+
+template <typename T> struct TmType;
+template <> struct TmType<__half> { static constexpr CUtensorMapDataType v = CU_TENSOR_MAP_DATA_TYPE_FLOAT16; };
+template <> struct TmType<__nv_bfloat16> { static constexpr CUtensorMapDataType v = CU_TENSOR_MAP_DATA_TYPE_BFLOAT16; };
+
+// 2-D map over a row-major [rows][cols] matrix of 16-bit elements, box = 64 columns x box_rows, 128B swizzle
+template <typename T>
+CUtensorMap make_map_2d(const void* base, uint64_t rows, uint64_t cols, uint32_t box_rows) {
+    CUtensorMap m;
+    cuuint64_t gdim[2] = {cols, rows};
+    cuuint64_t gstride[1] = {cols * sizeof(T)};
+    cuuint32_t box[2] = {64, box_rows};
+    cuuint32_t estr[2] = {1, 1};
+    CUresult r = state().encode(&m, TmType<T>::v, 2, const_cast<void*>(base), gdim, gstride, box, estr,
+                                CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+                                CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+    if (r != CUDA_SUCCESS) {
+        char buf[128];
+        snprintf(buf, sizeof buf, "cuTensorMapEncodeTiled failed with CUresult %d", (int)r);
+        throw Error(buf);
+    }
+    return m;
+}
+
+template <int TAPS, int CHUNKS, int NOUT, int WP>
+constexpr int pick_stages() {
+    constexpr int HALO = (TAPS == 9) ? (WP + 1) : 0;
+    constexpr int R = ((TC_BM + 2 * HALO + 7) / 8) * 8;
+    constexpr int budget = 227 * 1024 - 1024 /*align*/ - 512 /*barriers*/ - TAPS * CHUNKS * NOUT * 128;
+    constexpr int s = budget / (R * 128);
+    return s > 8 ? 8 : s;
+}
+
+template <int TAPS, int CHUNKS, int NOUT, int WP, int EPI, typename TIn, typename TOut>
+void launch(cudaStream_t st, const CUtensorMap& a0, const CUtensorMap& a1, const CUtensorMap& w, const TcParams& p, int n_blocks_y) {
+    constexpr int STAGES = pick_stages<TAPS, CHUNKS, NOUT, WP>();
+    static_assert(STAGES >= 2, "not enough shared memory for a 2-stage pipeline");
+    constexpr int HALO = (TAPS == 9) ? (WP + 1) : 0;
+    constexpr int R = ((TC_BM + 2 * HALO + 7) / 8) * 8;
+    constexpr size_t smem = 1024 + (size_t)TAPS * CHUNKS * NOUT * 128 + (size_t)STAGES * R * 128 + 512;
+    auto kern = conv_tc_kernel<TAPS, CHUNKS, NOUT, WP, STAGES, EPI, TIn, TOut>;
+    static bool attr_set = false;
+    if (!attr_set) {
+        DDPM_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        attr_set = true;
+    }
+    int ctas_x = state().num_sms / n_blocks_y;
+    if (ctas_x > p.num_m_tiles) ctas_x = p.num_m_tiles;
+    if (ctas_x < 1) ctas_x = 1;
+    dim3 grid(ctas_x, n_blocks_y);
+    kern<<<grid, TC_THREADS, smem, st>>>(a0, a1, w, p);
+    DDPM_LAUNCH_CHECK();
+}
+
+// Conv((3,3), C0+C1 => Cout, pad=1) on the padded layout.  src pointers are POSITION 0 pointers;
+// the tensor maps are based at the allocation start (position -guard).
 template <typename TIn, typename TOut>
-bool conv3x3(cudaStream_t, const TIn*, int, const TIn*, int, const TIn*, int, TOut*, const Geo&, const float*,
-             const float*, int, double*) {
-    return false;
+bool conv3x3(cudaStream_t st, const TIn* s0, int C0, const TIn* s1, int C1, const TIn* Wt, int Cout, TOut* out,
+             const Geo& g, const float* scale, const float* shift, int relu, double* stats) {
+    if (!available() || stats != nullptr) return false;
+    if constexpr (sizeof(TIn) != 2 || sizeof(TOut) != 2) {
+        return false;
+    } else {
+    const int Cin = C0 + C1;
+    const uint64_t rows = (uint64_t)g.alloc_positions();
+    const int WP = g.Wp;
+    TcParams p{};
+    p.out = out; p.out_cs = Cout; p.g = g; p.g_out = g; p.scale = scale; p.shift = shift; p.relu = relu;
+    p.num_m_tiles = cdiv(g.npos, TC_BM);
+    p.chunk1_src1 = (s1 != nullptr) ? 1 : 0;
+    p.base_offset_mode = state().base_offset_mode;
+    const TIn* base0 = s0 - (size_t)g.guard * C0;
+    constexpr int R32 = ((TC_BM + 2 * 35 + 7) / 8) * 8, R16 = ((TC_BM + 2 * 19 + 7) / 8) * 8;
+    CUtensorMap a0 = make_map_2d<TIn>(base0, rows, C0, WP == 34 ? R32 : R16);
+    CUtensorMap a1 = a0;
+    if (s1) a1 = make_map_2d<TIn>(s1 - (size_t)g.guard * C1, rows, C1, WP == 34 ? R32 : R16);
+    if (WP == 34 && Cin == 64 && Cout == 64 && !s1) {
+        CUtensorMap w = make_map_2d<TIn>(Wt, 64, 9 * 64, 64);
+        launch<9, 1, 64, 34, 0, TIn, TOut>(st, a0, a1, w, p, 1);
+    } else if (WP == 34 && Cin == 128 && Cout == 64) {
+        CUtensorMap w = make_map_2d<TIn>(Wt, 64, 9 * 128, 64);
+        launch<9, 2, 64, 34, 0, TIn, TOut>(st, a0, a1, w, p, 1);
+    } else if (WP == 18 && Cin == 64 && Cout == 128 && !s1) {
+        CUtensorMap w = make_map_2d<TIn>(Wt, 128, 9 * 64, 128);
+        launch<9, 1, 128, 18, 0, TIn, TOut>(st, a0, a1, w, p, 1);
+    } else if (WP == 18 && Cin == 128 && Cout == 128 && !s1) {
+        CUtensorMap w = make_map_2d<TIn>(Wt, 128, 9 * 128, 64);
+        launch<9, 2, 64, 18, 0, TIn, TOut>(st, a0, a1, w, p, 2);      // Cout split over blockIdx.y so the weights fit
+    } else if (WP == 18 && Cin == 128 && Cout == 64 && !s1) {
+        CUtensorMap w = make_map_2d<TIn>(Wt, 64, 9 * 128, 64);         // dgrad of down2.conv1
+        launch<9, 2, 64, 18, 0, TIn, TOut>(st, a0, a1, w, p, 1);
+    } else if (WP == 34 && Cin == 64 && Cout == 128 && !s1) {
+        CUtensorMap w = make_map_2d<TIn>(Wt, 128, 9 * 64, 128);        // dgrad of up1.conv1 (d cat)
+        launch<9, 1, 128, 34, 0, TIn, TOut>(st, a0, a1, w, p, 1);
+    } else {
+        return false;
+    }
+    return true;
+    }
 }
+
+// ConvTranspose((2,2), 128 => 64, stride=2): [pos16][128] x Wt[q*64+co][128]^T, pixel-shuffle epilogue + bias
 template <typename TA>
-bool up2(cudaStream_t, const TA*, const TA*, TA*, const Geo&, const Geo&, const float*) {
-    return false;
+bool up2(cudaStream_t st, const TA* a6, const TA* Wt, TA* u, const Geo& gi, const Geo& go, const float* bias) {
+    if (!available()) return false;
+    if constexpr (sizeof(TA) != 2) {
+        return false;
+    } else {
+    TcParams p{};
+    p.out = u; p.out_cs = 64; p.g = gi; p.g_out = go; p.scale = nullptr; p.shift = bias; p.relu = 0;
+    p.num_m_tiles = cdiv(gi.npos, TC_BM);
+    p.chunk1_src1 = 0;
+    p.base_offset_mode = 0;
+    CUtensorMap a0 = make_map_2d<TA>(a6 - (size_t)gi.guard * 128, (uint64_t)gi.alloc_positions(), 128, TC_BM);
+    CUtensorMap w = make_map_2d<TA>(Wt, 256, 128, 64);
+    launch<1, 2, 64, 18, 1, TA, TA>(st, a0, a0, w, p, 4);
+    return true;
+    }
 }
+
 template <typename TG, typename TA>
 bool wgrad3x3(cudaStream_t, const TG*, int, const TA*, int, const Geo&, float*, int, int) {
     return false;

@@ -514,8 +514,14 @@ void Engine::conv3(const Tensor& s0, const Tensor* s1, int l, Tensor& out, const
     DDPM_CHECK(C0 + C1 == c.cin && out.C == c.cout, "conv3: channel mismatch");
     if (use_tc()) {
         if (tc::conv3x3<TA, TA>(stream, s0.pos0<TA>(), C0, s1 ? s1->pos0<TA>() : nullptr, C1, (const TA*)Wf[l], c.cout,
-                                out.pos0<TA>(), g, scale, shift, relu, stats)) {
+                                out.pos0<TA>(), g, scale, shift, relu, nullptr)) {
             cnt_launches += 1;
+            if (stats) {  // train-mode BatchNorm statistics of the stored (rounded) y
+                long long pixels = (long long)g.N * g.H * g.W;
+                bn_stats_kernel<TA><<<cdiv(pixels, BNB_PIX_PER_BLOCK), 256, 0, stream>>>(out.cview<TA>(), g, c.cout, stats);
+                DDPM_LAUNCH_CHECK();
+                cnt_launches += 1;
+            }
             return;
         }
     }

@@ -676,6 +676,39 @@ channel_sum_kernel(View<const TG> d, Geo g, int C, double* __restrict__ sums) {
     if (t < C) atomicAdd(&sums[t], (double)red[t]);
 }
 
+// per-channel sum and sum of squares over valid pixels (train-mode BatchNorm statistics when the
+// producing convolution is the tensor-core kernel, whose epilogue does not reduce)
+template <typename TA>
+__global__ void __launch_bounds__(256)
+bn_stats_kernel(View<const TA> y, Geo g, int C, double* __restrict__ sums) {
+    __shared__ float red[2][128];
+    const int t = threadIdx.x;
+    if (t < 128) { red[0][t] = 0.f; red[1][t] = 0.f; }
+    __syncthreads();
+    const int groups = C / 8, lanes = 256 / groups;
+    const int c0 = (t % groups) * 8, pl = t / groups;
+    const long long total = (long long)g.N * g.H * g.W;
+    const long long pbeg = (long long)blockIdx.x * BNB_PIX_PER_BLOCK;
+    long long pend = pbeg + BNB_PIX_PER_BLOCK;
+    if (pend > total) pend = total;
+    float r[8], q[8];
+#pragma unroll
+    for (int j = 0; j < 8; ++j) { r[j] = 0.f; q[j] = 0.f; }
+    const int HW = g.H * g.W;
+    for (long long pix = pbeg + pl; pix < pend; pix += lanes) {
+        int n = (int)(pix / HW);
+        int rem = (int)(pix - (long long)n * HW);
+        float v[8];
+        V8<TA>::ld(y.p + g.pos(n, rem / g.W, rem % g.W) * y.cs + c0, v);
+#pragma unroll
+        for (int j = 0; j < 8; ++j) { r[j] += v[j]; q[j] = fmaf(v[j], v[j], q[j]); }
+    }
+#pragma unroll
+    for (int j = 0; j < 8; ++j) { atomicAdd(&red[0][c0 + j], r[j]); atomicAdd(&red[1][c0 + j], q[j]); }
+    __syncthreads();
+    if (t < C) { atomicAdd(&sums[t], (double)red[0][t]); atomicAdd(&sums[C + t], (double)red[1][t]); }
+}
+
 // ------------------------------------------------------------------------------------ Adam (Optimisers.jl 0.4.6)
 // m = b1*m + (1-b1)*g ; v = b2*v + (1-b2)*g^2 ; p -= m/(1-bt1) / (sqrt(v/(1-bt2)) + eps) * eta
 // over the whole flat parameter arena (running statistics have g = m = v = 0 => unchanged).

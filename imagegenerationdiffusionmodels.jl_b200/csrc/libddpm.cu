@@ -366,6 +366,7 @@ int ddpm_set_option(ddpm_handle* h, const char* key, int64_t value) {
     else if (k == "use_graph") e.opt_use_graph = value;
     else if (k == "conv_impl") { e.opt_conv_impl = value; for (auto& kv : e.infer_sets) kv.second->drop_graphs(); }
     else if (k == "sync_bn") e.sync_bn = (int)value;
+    else if (k == "tc_base_offset") { tc::state().base_offset_mode = (int)value; for (auto& kv : e.infer_sets) kv.second->drop_graphs(); }
     else throw Error("unknown option: " + k);
     API_END
 }

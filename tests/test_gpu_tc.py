@@ -1,0 +1,64 @@
+"""tcgen05 kernels against the CUDA-core kernels of the same library and against the oracle."""
+import json
+import os
+
+import numpy as np
+import pytest
+import torch
+
+from conftest import ROOT, config2_batch, rel_l2
+
+pytestmark = pytest.mark.gpu
+OUT = os.path.join(ROOT, "gpurun_out")
+NAMES = ["y1", "a1", "y2", "a2", "p1", "y3", "a3", "y4", "a4", "y5", "a5", "y6", "a6", "u", "y7", "a7", "y8", "a8",
+         "y9", "a9", "y10", "a10"]
+
+
+def _dump(name, obj):
+    os.makedirs(OUT, exist_ok=True)
+    with open(os.path.join(OUT, name), "w") as fh:
+        json.dump(obj, fh, indent=1, default=float)
+
+
+def _layers(h, xt, ts):
+    h.predict_eps(xt, ts, train_mode=True)
+    return {nm: h.debug_fetch(nm) for nm in NAMES}
+
+
+@pytest.mark.parametrize("mode", ["fp16", "bf16"])
+def test_tc_matches_simt_per_layer(gpu_handles, oracle, model_arrays, dataset, tabs, mode):
+    h = gpu_handles[mode]
+    if h.counter("tc_available") != 1:
+        pytest.fail("tcgen05 path unavailable on this device (cuTensorMapEncodeTiled entry point missing)")
+    h.set_weights(model_arrays)
+    B = 9   # odd batch: the last 128-row tile of every layer is ragged
+    x0, ts, eps = config2_batch(dataset, B)
+    xt = oracle.q_sample(x0, ts, eps, tabs["acum"])
+    report = {}
+    try:
+        h.set_option("conv_impl", 1)
+        ref = _layers(h, xt, ts)
+        e_ref = h.predict_eps(xt, ts, train_mode=False)
+        # base_offset 1 = descriptor base-offset field set to (start>>7)&7 for row-shifted starts.
+        # Measured on B200 (round 1): mode 0 is exact, mode 1 reads garbage -- the 128B swizzle XOR is
+        # taken from the absolute shared-memory address bits, so a row-advanced start needs no base offset.
+        for bo in (0,):
+            h.set_option("conv_impl", 2)
+            h.set_option("tc_base_offset", bo)
+            got = _layers(h, xt, ts)
+            e_got = h.predict_eps(xt, ts, train_mode=False)
+            report[f"base_offset_{bo}"] = {nm: rel_l2(got[nm], ref[nm]) for nm in NAMES}
+            report[f"base_offset_{bo}"]["eps_test_mode"] = rel_l2(e_got, e_ref)
+    finally:
+        h.set_option("conv_impl", 0)
+        h.set_option("tc_base_offset", 0)
+        _dump(f"tc_vs_simt_{mode}.json", report)
+    tol = 3e-3 if mode == "fp16" else 2e-2     # same inputs, different accumulation order + re-rounding
+    bad = {k: v for k, v in report["base_offset_0"].items() if not (v <= tol)}
+    assert not bad, bad
+
+
+def test_tc_is_the_default_path(gpu_handles):
+    h = gpu_handles["fp16"]
+    assert h.counter("uses_tc") == 1
+    assert gpu_handles["fp32"].counter("uses_tc") == 0
