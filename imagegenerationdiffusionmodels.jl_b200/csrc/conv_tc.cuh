@@ -52,6 +52,17 @@ __device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t parity) {
         if (!done && ++spins > (1ull << 26)) __trap();  // a lost arrival must fault, never hang the GPU
     } while (!done);
 }
+// one lane of a fully converged warp (keeps the surrounding control flow warp-uniform, so descriptors
+// and barrier addresses stay in uniform registers instead of per-MMA R2UR/ELECT loops)
+__device__ __forceinline__ bool elect_one() {
+    uint32_t pred;
+    asm volatile(
+        "{\n\t.reg .pred P;\n\t"
+        "elect.sync _|P, 0xffffffff;\n\t"
+        "selp.u32 %0, 1, 0, P;\n\t}"
+        : "=r"(pred));
+    return pred != 0;
+}
 __device__ __forceinline__ void fence_barrier_init() { asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory"); }
 __device__ __forceinline__ void fence_proxy_async() { asm volatile("fence.proxy.async.shared::cta;" ::: "memory"); }
 __device__ __forceinline__ void tc_fence_before() { asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory"); }
@@ -62,6 +73,19 @@ __device__ __forceinline__ void tma_load_2d(uint32_t dst, const CUtensorMap* map
         "cp.async.bulk.tensor.2d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4}], [%2];"
         ::"r"(dst), "l"(map), "r"(bar), "r"(c0), "r"(c1)
         : "memory");
+}
+// shared -> global tile store (bulk async group); the box is clipped at the tensor bounds
+__device__ __forceinline__ void tma_store_2d(const CUtensorMap* map, uint32_t src, int c0, int c1) {
+    asm volatile("cp.async.bulk.tensor.2d.global.shared::cta.bulk_group [%0, {%2, %3}], [%1];"
+                 ::"l"(map), "r"(src), "r"(c0), "r"(c1)
+                 : "memory");
+}
+__device__ __forceinline__ void tma_store_commit() { asm volatile("cp.async.bulk.commit_group;" ::: "memory"); }
+template <int N>
+__device__ __forceinline__ void tma_store_wait_read() { asm volatile("cp.async.bulk.wait_group.read %0;" ::"n"(N) : "memory"); }
+__device__ __forceinline__ void tma_store_wait_all() { asm volatile("cp.async.bulk.wait_group 0;" ::: "memory"); }
+__device__ __forceinline__ void named_bar_sync(int id, int nthreads) {
+    asm volatile("bar.sync %0, %1;" ::"r"(id), "r"(nthreads) : "memory");
 }
 __device__ __forceinline__ void prefetch_tmap(const CUtensorMap* map) {
     asm volatile("prefetch.tensormap [%0];" ::"l"(map) : "memory");
@@ -85,6 +109,18 @@ __device__ __forceinline__ void umma_f16(uint32_t d_tmem, uint64_t a_desc, uint6
         "setp.ne.b32 p, %4, 0;\n\t"
         "tcgen05.mma.cta_group::1.kind::f16 [%0], %1, %2, %3, p;\n\t}"
         ::"r"(d_tmem), "l"(a_desc), "l"(b_desc), "r"(idesc), "r"(accumulate)
+        : "memory");
+}
+// same, descriptors passed as (lo, hi) halves so that advancing the start address is one 32-bit add
+__device__ __forceinline__ void umma_f16_lh(uint32_t d_tmem, uint32_t a_lo, uint32_t b_lo, uint32_t desc_hi, uint32_t idesc,
+                                            uint32_t accumulate) {
+    asm volatile(
+        "{\n\t.reg .pred p;\n\t.reg .b64 da, db;\n\t"
+        "mov.b64 da, {%1, %3};\n\t"
+        "mov.b64 db, {%2, %3};\n\t"
+        "setp.ne.b32 p, %5, 0;\n\t"
+        "tcgen05.mma.cta_group::1.kind::f16 [%0], da, db, %4, p;\n\t}"
+        ::"r"(d_tmem), "r"(a_lo), "r"(b_lo), "r"(desc_hi), "r"(idesc), "r"(accumulate)
         : "memory");
 }
 // arrive on an mbarrier when all previously issued tcgen05.mma of this thread have completed
@@ -151,26 +187,45 @@ __device__ __forceinline__ void store16<__nv_bfloat16>(__nv_bfloat16* p, const f
     *reinterpret_cast<uint4*>(p + 8) = b;
 }
 
+template <typename TOut>
+__device__ __forceinline__ void pack16(const float v[16], uint4& a, uint4& b);
+template <>
+__device__ __forceinline__ void pack16<__half>(const float v[16], uint4& a, uint4& b) {
+    __half2* ha = reinterpret_cast<__half2*>(&a);
+    __half2* hb = reinterpret_cast<__half2*>(&b);
+#pragma unroll
+    for (int i = 0; i < 4; ++i) { ha[i] = __floats2half2_rn(v[2 * i], v[2 * i + 1]); hb[i] = __floats2half2_rn(v[8 + 2 * i], v[9 + 2 * i]); }
+}
+template <>
+__device__ __forceinline__ void pack16<__nv_bfloat16>(const float v[16], uint4& a, uint4& b) {
+    __nv_bfloat162* ha = reinterpret_cast<__nv_bfloat162*>(&a);
+    __nv_bfloat162* hb = reinterpret_cast<__nv_bfloat162*>(&b);
+#pragma unroll
+    for (int i = 0; i < 4; ++i) { ha[i] = __floats2bfloat162_rn(v[2 * i], v[2 * i + 1]); hb[i] = __floats2bfloat162_rn(v[8 + 2 * i], v[9 + 2 * i]); }
+}
+
 struct TcParams {
     void* out;            // position 0 of the output tensor
     int out_cs;           // channel stride (elements) of the output tensor
     Geo g;                // geometry of the A operand rows (== output geometry for convs)
     Geo g_out;            // EPI==1 only: fine geometry of the ConvTranspose output
-    const float* scale;   // per output channel, nullptr -> 1
-    const float* shift;   // per output channel, nullptr -> 0   (EPI==1: bias)
+    const float* shift;   // per output channel, nullptr -> 0   (EPI==1: bias).  Any per-channel SCALE is
+                          // folded into the packed weights by the caller (inference BatchNorm fold).
     int relu;
     int num_m_tiles;
     int chunk1_src1;      // 1: K-chunk 1 comes from the second tensor map (channel concat), 0: channels 64.. of the first
-    int base_offset_mode; // descriptor base-offset variant (hardware probe, see tests)
+    long long* dbg;       // optional [gridDim.x*gridDim.y][8] cycle counters (role wait/busy breakdown), nullptr = off
 };
 
 // TAPS: 9 (3x3 conv, halo'ed slab) or 1 (plain GEMM rows); CHUNKS: 64-channel K chunks (1|2);
 // NOUT: output channels handled by this CTA (64|128); WP: padded row width (W+2) for TAPS==9
 // EPI: 0 = conv store on the same geometry, 1 = ConvTranspose 2x2 pixel shuffle (blockIdx.y = q)
-template <int TAPS, int CHUNKS, int NOUT, int WP, int STAGES, int EPI, typename TIn, typename TOut>
+// TMAST: 1 = epilogue stages the tile in swizzled shared memory and writes it with a TMA store
+// (halo rows are written as zeros, which is what they must hold), 0 = predicated 16-byte stores.
+template <int TAPS, int CHUNKS, int NOUT, int WP, int STAGES, int EPI, int TMAST, typename TIn, typename TOut>
 __global__ void __launch_bounds__(TC_THREADS, 1)
 conv_tc_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constant__ CUtensorMap tmA1,
-               const __grid_constant__ CUtensorMap tmW, const TcParams p) {
+               const __grid_constant__ CUtensorMap tmW, const __grid_constant__ CUtensorMap tmO, const TcParams p) {
     constexpr int HALO = (TAPS == 9) ? (WP + 1) : 0;
     constexpr int R = ((TC_BM + 2 * HALO + 7) / 8) * 8;       // slab rows (multiple of 8 -> 1024 B multiple)
     constexpr uint32_t A_STAGE_BYTES = R * 128;
@@ -181,18 +236,24 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constant__
 
     extern __shared__ uint8_t smem_raw[];
     uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
+    constexpr uint32_t O_BYTES = TMAST ? 2u * TC_BM * NOUT * 2u : 0u;   // two staging tiles [128][NOUT] (16-bit)
     const uint32_t s_w = smem_u32(smem);
     const uint32_t s_a = s_w + W_BYTES;
-    const uint32_t s_bar = s_a + STAGES * A_STAGE_BYTES;
+    const uint32_t s_o = s_a + STAGES * A_STAGE_BYTES;
+    const uint32_t s_bar = s_o + O_BYTES;
     // barrier slots (8 B each): [0] w_full, [1..S] a_full, [1+S..2S] a_empty, [1+2S, 2+2S] acc_full, [3+2S, 4+2S] acc_empty
     auto bar_w = [&]() { return s_bar; };
     auto bar_afull = [&](int s) { return s_bar + 8u * (1 + s); };
     auto bar_aempty = [&](int s) { return s_bar + 8u * (1 + STAGES + s); };
     auto bar_accfull = [&](int b) { return s_bar + 8u * (1 + 2 * STAGES + b); };
     auto bar_accempty = [&](int b) { return s_bar + 8u * (3 + 2 * STAGES + b); };
-    uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(smem + W_BYTES + STAGES * A_STAGE_BYTES + 8 * (5 + 2 * STAGES));
+    uint8_t* misc = smem + W_BYTES + STAGES * A_STAGE_BYTES + O_BYTES;
+    uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(misc + 8 * (5 + 2 * STAGES));
+    float* s_shift = reinterpret_cast<float*>(misc + 256);               // [NOUT] per-channel shift of this CTA's N-slice
 
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    long long dbg_acc[8] = {0, 0, 0, 0, 0, 0, 0, 0};
+    const long long t_kernel0 = p.dbg ? clock64() : 0;
     const int n_blk = blockIdx.y;                 // N-slice (conv: half of Cout; up2: sub-position q)
 
     if (warp == 0 && lane == 0) {
@@ -204,70 +265,91 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constant__
         fence_barrier_init();
     }
     if (warp == 2) tmem_alloc<TMEM_COLS>(smem_u32(tmem_slot));
+    if (threadIdx.x >= 64 && threadIdx.x < 64 + NOUT) {
+        const int c = threadIdx.x - 64;
+        const int co = (EPI == 1) ? c : (n_blk * NOUT + c);
+        s_shift[c] = p.shift ? p.shift[co] : 0.f;
+    }
+    if (warp == 0 && lane == 0 && TMAST) prefetch_tmap(&tmO);
     tc_fence_before();
     __syncthreads();
     tc_fence_after();
     const uint32_t tmem_base = *tmem_slot;
 
     if (warp == 0) {
-        // ================= TMA producer =================
-        if (lane == 0) {
+        // ================= TMA producer (warp-uniform loop, one elected lane issues) =================
+        if (elect_one()) {
             mbar_expect_tx(bar_w(), W_BYTES);
             for (int t = 0; t < TAPS; ++t)
                 for (int c = 0; c < CHUNKS; ++c)
                     tma_load_2d(s_w + (t * CHUNKS + c) * W_TILE_BYTES, &tmW, (t * CHUNKS + c) * 64, n_blk * NOUT, bar_w());
-            int stage = 0;
-            uint32_t phase = 0;
-            for (int tile = blockIdx.x; tile < p.num_m_tiles; tile += gridDim.x) {
-                const int row0 = tile * TC_BM - HALO + p.g.guard;   // row coordinate in the tensor map (base = allocation start)
-                for (int c = 0; c < CHUNKS; ++c) {
-                    mbar_wait(bar_aempty(stage), phase ^ 1);
+        }
+        __syncwarp();
+        int stage = 0;
+        uint32_t phase = 0;
+        for (int tile = blockIdx.x; tile < p.num_m_tiles; tile += gridDim.x) {
+            const int row0 = tile * TC_BM - HALO + p.g.guard;   // row coordinate in the tensor map (base = allocation start)
+#pragma unroll
+            for (int c = 0; c < CHUNKS; ++c) {
+                long long t0 = p.dbg ? clock64() : 0;
+                mbar_wait(bar_aempty(stage), phase ^ 1);
+                if (p.dbg) dbg_acc[0] += clock64() - t0;
+                if (elect_one()) {
                     mbar_expect_tx(bar_afull(stage), A_STAGE_BYTES);
                     const bool second = (c == 1) && p.chunk1_src1;
                     tma_load_2d(s_a + stage * A_STAGE_BYTES, second ? &tmA1 : &tmA0, second ? 0 : c * 64, row0, bar_afull(stage));
-                    if (++stage == STAGES) { stage = 0; phase ^= 1; }
                 }
+                __syncwarp();
+                if (++stage == STAGES) { stage = 0; phase ^= 1; }
             }
         }
-        __syncwarp();
     } else if (warp == 1) {
-        // ================= MMA issuer (one thread) =================
-        if (lane == 0) {
-            mbar_wait(bar_w(), 0);
+        // ================= MMA issuer (warp-uniform loop, one elected lane issues) =================
+        mbar_wait(bar_w(), 0);
+        tc_fence_after();
+        // matrix descriptor halves (see make_desc_sw128): lo = start>>4 | LBO<<16, hi = SBO | version | SWIZZLE_128B
+        constexpr uint32_t DESC_HI = (1024u >> 4) | (1u << 14) | (2u << 29);
+        const uint32_t a_lo_base = ((s_a & 0x3FFFFu) >> 4) | (1u << 16);
+        const uint32_t b_lo_base = ((s_w & 0x3FFFFu) >> 4) | (1u << 16);
+        int stage = 0;
+        uint32_t phase = 0;
+        int buf = 0;
+        uint32_t acc_phase = 0;
+        for (int tile = blockIdx.x; tile < p.num_m_tiles; tile += gridDim.x) {
+            long long t0 = p.dbg ? clock64() : 0;
+            mbar_wait(bar_accempty(buf), acc_phase ^ 1);
+            if (p.dbg) dbg_acc[1] += clock64() - t0;
             tc_fence_after();
-            int stage = 0;
-            uint32_t phase = 0;
-            int buf = 0;
-            uint32_t acc_phase = 0;
-            for (int tile = blockIdx.x; tile < p.num_m_tiles; tile += gridDim.x) {
-                mbar_wait(bar_accempty(buf), acc_phase ^ 1);
+            const uint32_t d_tmem = tmem_base + buf * NOUT;
+#pragma unroll
+            for (int c = 0; c < CHUNKS; ++c) {
+                t0 = p.dbg ? clock64() : 0;
+                mbar_wait(bar_afull(stage), phase);
+                if (p.dbg) dbg_acc[2] += clock64() - t0;
                 tc_fence_after();
-                const uint32_t d_tmem = tmem_base + buf * NOUT;
-                uint32_t accumulate = 0;
-                for (int c = 0; c < CHUNKS; ++c) {
-                    mbar_wait(bar_afull(stage), phase);
-                    tc_fence_after();
-                    const uint32_t a_base = s_a + stage * A_STAGE_BYTES;
+                t0 = p.dbg ? clock64() : 0;
+                if (elect_one()) {
+                    const uint32_t a_lo = a_lo_base + stage * (A_STAGE_BYTES >> 4);
 #pragma unroll
                     for (int t = 0; t < TAPS; ++t) {
+                        constexpr int dummy = 0; (void)dummy;
                         const int shift = (TAPS == 9) ? (HALO + (t / 3 - 1) * WP + (t % 3 - 1)) : 0;
-                        const uint32_t a_tap = a_base + shift * 128;
-                        const uint32_t b_tap = s_w + (t * CHUNKS + c) * W_TILE_BYTES;
 #pragma unroll
                         for (int ks = 0; ks < 4; ++ks) {
-                            umma_f16(d_tmem, make_desc_sw128(a_tap + ks * 32, p.base_offset_mode),
-                                     make_desc_sw128(b_tap + ks * 32, 0), IDESC, accumulate);
-                            accumulate = 1;
+                            umma_f16_lh(d_tmem, a_lo + ((shift * 128 + ks * 32) >> 4),
+                                        b_lo_base + (((t * CHUNKS + c) * W_TILE_BYTES + ks * 32) >> 4), DESC_HI, IDESC,
+                                        (c | t | ks) ? 1u : 0u);
                         }
                     }
-                    umma_commit(bar_aempty(stage));          // slab may be overwritten once these MMAs retire
-                    if (++stage == STAGES) { stage = 0; phase ^= 1; }
+                    umma_commit(bar_aempty(stage));                       // slab reusable once these MMAs retire
+                    if (c == CHUNKS - 1) umma_commit(bar_accfull(buf));   // accumulator ready for the epilogue
                 }
-                umma_commit(bar_accfull(buf));               // accumulator ready for the epilogue
-                if (++buf == 2) { buf = 0; acc_phase ^= 1; }
+                __syncwarp();
+                if (p.dbg) dbg_acc[3] += clock64() - t0;
+                if (++stage == STAGES) { stage = 0; phase ^= 1; }
             }
+            if (++buf == 2) { buf = 0; acc_phase ^= 1; }
         }
-        __syncwarp();
     } else {
         // ================= epilogue warps (TMEM -> registers -> global) =================
         const int lane_grp = warp & 3;                       // TMEM lanes 32*lane_grp .. +31 are visible to this warp
@@ -285,37 +367,86 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constant__
                 if (valid) opos = p.g_out.pos(n_img, 2 * hh + (n_blk >> 1), 2 * ww + (n_blk & 1));
                 ch_off = 0;
             }
+            long long t0 = p.dbg ? clock64() : 0;
             mbar_wait(bar_accfull(buf), acc_phase);
+            long long t1 = p.dbg ? clock64() : 0;
+            if (p.dbg) dbg_acc[4] += t1 - t0;
             tc_fence_after();
             const uint32_t taddr = tmem_base + ((uint32_t)(lane_grp * 32) << 16) + buf * NOUT;
+            uint32_t stage_o = 0;
+            if (TMAST) {
+                // the TMA store that last read this staging tile (two tiles ago) must have drained it
+                stage_o = s_o + (uint32_t)buf * (TC_BM * NOUT * 2);
+                if (threadIdx.x == 64) tma_store_wait_read<1>();
+                named_bar_sync(1, 128);
+            }
 #pragma unroll
             for (int c0 = 0; c0 < NOUT; c0 += 32) {
                 uint32_t r0[16], r1[16];
                 tmem_ld16(taddr + c0, r0);
                 tmem_ld16(taddr + c0 + 16, r1);
                 tmem_ld_wait();
-                if (valid) {
+#pragma unroll
+                for (int half = 0; half < 2; ++half) {
+                    const uint32_t* r = half ? r1 : r0;
+                    const int cb = c0 + half * 16;
                     float v[16];
 #pragma unroll
-                    for (int half = 0; half < 2; ++half) {
-                        const uint32_t* r = half ? r1 : r0;
-                        const int cb = c0 + half * 16;
+                    for (int j4 = 0; j4 < 4; ++j4) {
+                        const float4 sh = *reinterpret_cast<const float4*>(s_shift + cb + 4 * j4);
+                        v[4 * j4 + 0] = __uint_as_float(r[4 * j4 + 0]) + sh.x;
+                        v[4 * j4 + 1] = __uint_as_float(r[4 * j4 + 1]) + sh.y;
+                        v[4 * j4 + 2] = __uint_as_float(r[4 * j4 + 2]) + sh.z;
+                        v[4 * j4 + 3] = __uint_as_float(r[4 * j4 + 3]) + sh.w;
+                    }
+                    if (p.relu) {
 #pragma unroll
-                        for (int j = 0; j < 16; ++j) {
-                            const int co = (EPI == 1) ? (cb + j) : (ch_off + cb + j);
-                            float x = __uint_as_float(r[j]);
-                            x = x * (p.scale ? __ldg(p.scale + co) : 1.f) + (p.shift ? __ldg(p.shift + co) : 0.f);
-                            v[j] = p.relu ? fmaxf(x, 0.f) : x;
+                        for (int j = 0; j < 16; ++j) v[j] = fmaxf(v[j], 0.f);
+                    }
+                    if (TMAST) {
+                        if (!valid) {
+#pragma unroll
+                            for (int j = 0; j < 16; ++j) v[j] = 0.f;
                         }
+                        uint4 qa, qb;
+                        pack16<TOut>(v, qa, qb);
+                        // staging tile = [NOUT/64] x [128 rows][128 B], 128B-swizzled like the tensor map expects
+                        const uint32_t half_tile = stage_o + (uint32_t)(cb >> 6) * (TC_BM * 128);
+                        const uint32_t rbase = half_tile + (uint32_t)row * 128;
+                        const uint32_t ch = (uint32_t)(cb & 63) >> 3;            // 16-byte chunk index 0..7 (even)
+                        const uint32_t sw = (uint32_t)row & 7u;
+                        asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(rbase + ((ch ^ sw) << 4)), "r"(qa.x),
+                                     "r"(qa.y), "r"(qa.z), "r"(qa.w) : "memory");
+                        asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(rbase + (((ch + 1) ^ sw) << 4)), "r"(qb.x),
+                                     "r"(qb.y), "r"(qb.z), "r"(qb.w) : "memory");
+                    } else if (valid) {
                         store16<TOut>(out + opos * p.out_cs + ch_off + cb, v);
                     }
+                }
+            }
+            if (TMAST) {
+                fence_proxy_async();                 // generic-proxy smem writes -> visible to the TMA engine
+                named_bar_sync(1, 128);
+                if (threadIdx.x == 64) {
+#pragma unroll
+                    for (int hsel = 0; hsel < NOUT / 64; ++hsel)
+                        tma_store_2d(&tmO, stage_o + hsel * (TC_BM * 128), n_blk * NOUT + hsel * 64, tile * TC_BM + p.g.guard);
+                    tma_store_commit();
                 }
             }
             tc_fence_before();
             __syncwarp();
             if (lane == 0) mbar_arrive(bar_accempty(buf));
+            if (p.dbg) { dbg_acc[5] += clock64() - t1; dbg_acc[6] += 1; }
             if (++buf == 2) { buf = 0; acc_phase ^= 1; }
         }
+    }
+    if (TMAST && threadIdx.x == 64) tma_store_wait_all();
+    if (p.dbg && lane == 0 && warp <= 2) {
+        long long* d = p.dbg + (size_t)(blockIdx.y * gridDim.x + blockIdx.x) * 8;
+        if (warp == 0) d[0] = dbg_acc[0];
+        if (warp == 1) { d[1] = dbg_acc[1]; d[2] = dbg_acc[2]; d[3] = dbg_acc[3]; }
+        if (warp == 2) { d[4] = dbg_acc[4]; d[5] = dbg_acc[5]; d[6] = dbg_acc[6]; d[7] = clock64() - t_kernel0; }
     }
     tc_fence_before();
     __syncthreads();
@@ -331,6 +462,7 @@ typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t,
                                   CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
 
 struct State {
+    long long* dbg = nullptr;   // device buffer [512][8] when role profiling is on
     EncodeTiledFn encode = nullptr;
     bool ok = false;
     int num_sms = 148;
@@ -384,23 +516,26 @@ CUtensorMap make_map_2d(const void* base, uint64_t rows, uint64_t cols, uint32_t
     return m;
 }
 
-template <int TAPS, int CHUNKS, int NOUT, int WP>
+template <int TAPS, int CHUNKS, int NOUT, int WP, int TMAST>
 constexpr int pick_stages() {
     constexpr int HALO = (TAPS == 9) ? (WP + 1) : 0;
     constexpr int R = ((TC_BM + 2 * HALO + 7) / 8) * 8;
-    constexpr int budget = 227 * 1024 - 1024 /*align*/ - 512 /*barriers*/ - TAPS * CHUNKS * NOUT * 128;
+    constexpr int budget = 227 * 1024 - 1024 /*align*/ - 1024 /*barriers, shift*/ - TAPS * CHUNKS * NOUT * 128 -
+                           (TMAST ? 2 * TC_BM * NOUT * 2 : 0);
     constexpr int s = budget / (R * 128);
     return s > 8 ? 8 : s;
 }
 
-template <int TAPS, int CHUNKS, int NOUT, int WP, int EPI, typename TIn, typename TOut>
-void launch(cudaStream_t st, const CUtensorMap& a0, const CUtensorMap& a1, const CUtensorMap& w, const TcParams& p, int n_blocks_y) {
-    constexpr int STAGES = pick_stages<TAPS, CHUNKS, NOUT, WP>();
+template <int TAPS, int CHUNKS, int NOUT, int WP, int EPI, int TMAST, typename TIn, typename TOut>
+void launch(cudaStream_t st, const CUtensorMap& a0, const CUtensorMap& a1, const CUtensorMap& w, const CUtensorMap& o,
+            const TcParams& p, int n_blocks_y) {
+    constexpr int STAGES = pick_stages<TAPS, CHUNKS, NOUT, WP, TMAST>();
     static_assert(STAGES >= 2, "not enough shared memory for a 2-stage pipeline");
     constexpr int HALO = (TAPS == 9) ? (WP + 1) : 0;
     constexpr int R = ((TC_BM + 2 * HALO + 7) / 8) * 8;
-    constexpr size_t smem = 1024 + (size_t)TAPS * CHUNKS * NOUT * 128 + (size_t)STAGES * R * 128 + 512;
-    auto kern = conv_tc_kernel<TAPS, CHUNKS, NOUT, WP, STAGES, EPI, TIn, TOut>;
+    constexpr size_t smem = 1024 + (size_t)TAPS * CHUNKS * NOUT * 128 + (size_t)STAGES * R * 128 +
+                            (TMAST ? 2 * TC_BM * NOUT * 2 : 0) + 1024;
+    auto kern = conv_tc_kernel<TAPS, CHUNKS, NOUT, WP, STAGES, EPI, TMAST, TIn, TOut>;
     static bool attr_set = false;
     if (!attr_set) {
         DDPM_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
@@ -410,7 +545,7 @@ void launch(cudaStream_t st, const CUtensorMap& a0, const CUtensorMap& a1, const
     if (ctas_x > p.num_m_tiles) ctas_x = p.num_m_tiles;
     if (ctas_x < 1) ctas_x = 1;
     dim3 grid(ctas_x, n_blocks_y);
-    kern<<<grid, TC_THREADS, smem, st>>>(a0, a1, w, p);
+    kern<<<grid, TC_THREADS, smem, st>>>(a0, a1, w, o, p);
     DDPM_LAUNCH_CHECK();
 }
 
@@ -418,8 +553,8 @@ void launch(cudaStream_t st, const CUtensorMap& a0, const CUtensorMap& a1, const
 // the tensor maps are based at the allocation start (position -guard).
 template <typename TIn, typename TOut>
 bool conv3x3(cudaStream_t st, const TIn* s0, int C0, const TIn* s1, int C1, const TIn* Wt, int Cout, TOut* out,
-             const Geo& g, const float* scale, const float* shift, int relu, double* stats) {
-    if (!available() || stats != nullptr) return false;
+             const Geo& g, const float* shift, int relu) {
+    if (!available()) return false;
     if constexpr (sizeof(TIn) != 2 || sizeof(TOut) != 2) {
         return false;
     } else {
@@ -427,10 +562,10 @@ bool conv3x3(cudaStream_t st, const TIn* s0, int C0, const TIn* s1, int C1, cons
     const uint64_t rows = (uint64_t)g.alloc_positions();
     const int WP = g.Wp;
     TcParams p{};
-    p.out = out; p.out_cs = Cout; p.g = g; p.g_out = g; p.scale = scale; p.shift = shift; p.relu = relu;
+    p.out = out; p.out_cs = Cout; p.g = g; p.g_out = g; p.shift = shift; p.relu = relu;
     p.num_m_tiles = cdiv(g.npos, TC_BM);
     p.chunk1_src1 = (s1 != nullptr) ? 1 : 0;
-    p.base_offset_mode = state().base_offset_mode;
+    p.dbg = state().dbg;
     const TIn* base0 = s0 - (size_t)g.guard * C0;
     constexpr int R32 = ((TC_BM + 2 * 35 + 7) / 8) * 8, R16 = ((TC_BM + 2 * 19 + 7) / 8) * 8;
     CUtensorMap a0 = make_map_2d<TIn>(base0, rows, C0, WP == 34 ? R32 : R16);
@@ -438,22 +573,23 @@ bool conv3x3(cudaStream_t st, const TIn* s0, int C0, const TIn* s1, int C1, cons
     if (s1) a1 = make_map_2d<TIn>(s1 - (size_t)g.guard * C1, rows, C1, WP == 34 ? R32 : R16);
     if (WP == 34 && Cin == 64 && Cout == 64 && !s1) {
         CUtensorMap w = make_map_2d<TIn>(Wt, 64, 9 * 64, 64);
-        launch<9, 1, 64, 34, 0, TIn, TOut>(st, a0, a1, w, p, 1);
+        CUtensorMap o = make_map_2d<TOut>(out - (size_t)g.guard * Cout, rows, Cout, TC_BM);
+        launch<9, 1, 64, 34, 0, 1, TIn, TOut>(st, a0, a1, w, o, p, 1);
     } else if (WP == 34 && Cin == 128 && Cout == 64) {
         CUtensorMap w = make_map_2d<TIn>(Wt, 64, 9 * 128, 64);
-        launch<9, 2, 64, 34, 0, TIn, TOut>(st, a0, a1, w, p, 1);
+        launch<9, 2, 64, 34, 0, 0, TIn, TOut>(st, a0, a1, w, a0, p, 1);
     } else if (WP == 18 && Cin == 64 && Cout == 128 && !s1) {
         CUtensorMap w = make_map_2d<TIn>(Wt, 128, 9 * 64, 128);
-        launch<9, 1, 128, 18, 0, TIn, TOut>(st, a0, a1, w, p, 1);
+        launch<9, 1, 128, 18, 0, 0, TIn, TOut>(st, a0, a1, w, a0, p, 1);
     } else if (WP == 18 && Cin == 128 && Cout == 128 && !s1) {
         CUtensorMap w = make_map_2d<TIn>(Wt, 128, 9 * 128, 64);
-        launch<9, 2, 64, 18, 0, TIn, TOut>(st, a0, a1, w, p, 2);      // Cout split over blockIdx.y so the weights fit
+        launch<9, 2, 64, 18, 0, 0, TIn, TOut>(st, a0, a1, w, a0, p, 2);      // Cout split over blockIdx.y so the weights fit
     } else if (WP == 18 && Cin == 128 && Cout == 64 && !s1) {
         CUtensorMap w = make_map_2d<TIn>(Wt, 64, 9 * 128, 64);         // dgrad of down2.conv1
-        launch<9, 2, 64, 18, 0, TIn, TOut>(st, a0, a1, w, p, 1);
+        launch<9, 2, 64, 18, 0, 0, TIn, TOut>(st, a0, a1, w, a0, p, 1);
     } else if (WP == 34 && Cin == 64 && Cout == 128 && !s1) {
         CUtensorMap w = make_map_2d<TIn>(Wt, 128, 9 * 64, 128);        // dgrad of up1.conv1 (d cat)
-        launch<9, 1, 128, 34, 0, TIn, TOut>(st, a0, a1, w, p, 1);
+        launch<9, 1, 128, 34, 0, 0, TIn, TOut>(st, a0, a1, w, a0, p, 1);
     } else {
         return false;
     }
@@ -469,13 +605,12 @@ bool up2(cudaStream_t st, const TA* a6, const TA* Wt, TA* u, const Geo& gi, cons
         return false;
     } else {
     TcParams p{};
-    p.out = u; p.out_cs = 64; p.g = gi; p.g_out = go; p.scale = nullptr; p.shift = bias; p.relu = 0;
+    p.out = u; p.out_cs = 64; p.g = gi; p.g_out = go; p.shift = bias; p.relu = 0;
     p.num_m_tiles = cdiv(gi.npos, TC_BM);
     p.chunk1_src1 = 0;
-    p.base_offset_mode = 0;
     CUtensorMap a0 = make_map_2d<TA>(a6 - (size_t)gi.guard * 128, (uint64_t)gi.alloc_positions(), 128, TC_BM);
     CUtensorMap w = make_map_2d<TA>(Wt, 256, 128, 64);
-    launch<1, 2, 64, 18, 1, TA, TA>(st, a0, a0, w, p, 4);
+    launch<1, 2, 64, 18, 1, 0, TA, TA>(st, a0, a0, w, a0, p, 4);
     return true;
     }
 }

@@ -165,6 +165,7 @@ struct Engine {
     // packed weights
     void* Wf[NUM_CONV + 1] = {};   // [cout][9][cin]  (TA)  -- L1 unused
     void* Wd[NUM_CONV + 1] = {};   // [cin][9][cout]  (TG)  -- L1 unused
+    void* Wfi[NUM_CONV + 1] = {};  // Wf with the inference BatchNorm scale folded in (TA)
     void *Wt = nullptr, *Wtd = nullptr;  // convT fwd (TA) [256][128], dgrad (TG) [128][256]
     float *Wimg = nullptr, *Wemb = nullptr;  // first conv, FP32
     float *Ptab = nullptr, *Ecls = nullptr;  // [T][9][64] embedding contributions
@@ -217,12 +218,13 @@ struct Engine {
     ActSet& get_set(int N, bool training);
 
     template <typename TA, typename TG> void pack_weights_t();
+    template <typename TA, typename TG> void pack_infer_weights_t();
     void pack_weights();
     void prepare_ecls();
     void prepare_infer_affine();
 
     template <typename TA, typename TG>
-    void conv3(const Tensor& s0, const Tensor* s1, int l, Tensor& out, const float* scale, const float* shift, int relu,
+    void conv3(const Tensor& s0, const Tensor* s1, int l, Tensor& out, const void* weights, const float* shift, int relu,
                double* stats);
     template <typename TA, typename TG>
     void dgrad3(const Tensor& dy, int l, Tensor& out, int out_c_total);
@@ -291,6 +293,7 @@ inline Engine::Engine(int T_, int D_, int H_, int W_, int prec_, int dev_)
             size_t n = (size_t)9 * kConv[l].cin * kConv[l].cout;
             DDPM_CUDA(cudaMalloc(&Wf[l], n * esz_a()));
             DDPM_CUDA(cudaMalloc(&Wd[l], n * esz_g()));
+            DDPM_CUDA(cudaMalloc(&Wfi[l], n * esz_a()));
         }
     }
     DDPM_CUDA(cudaMalloc(&Wt, (size_t)4 * 128 * 64 * esz_a()));
@@ -324,7 +327,7 @@ inline Engine::~Engine() {
     for (int l = 1; l <= NUM_CONV; ++l) {
         float* v[] = {inf_scale[l], inf_shift[l], tr_mean[l], tr_istd[l], tr_scale[l], tr_shift[l], bw_mg[l], bw_mgx[l]};
         for (float* p : v) cudaFree(p);
-        cudaFree(Wf[l]); cudaFree(Wd[l]);
+        cudaFree(Wf[l]); cudaFree(Wd[l]); cudaFree(Wfi[l]);
     }
     cudaFree(Wt); cudaFree(Wtd); cudaFree(sums); cudaFree(sums_g); cudaFree(misc_sums); cudaFree(d_rng);
     DevBuf* bufs[] = {&d_x0, &d_eps, &d_xt, &d_deps, &d_ts, &d_idx, &d_Tw, &d_Ccls, &d_S, &d_z, &d_dataset, &d_sample_out};
@@ -461,8 +464,8 @@ void Engine::pack_weights_t() {
     for (int l = 2; l <= NUM_CONV; ++l) {
         const ConvSpec& c = kConv[l];
         long long n = 9LL * c.cin * c.cout;
-        pack_conv3_kernel<TA><<<cdiv(n, 256), 256, 0, stream>>>(arr(c.w), c.cin, 0, c.cin, c.cout, 0, (TA*)Wf[l]);
-        pack_conv3_kernel<TG><<<cdiv(n, 256), 256, 0, stream>>>(arr(c.w), c.cin, 0, c.cin, c.cout, 1, (TG*)Wd[l]);
+        pack_conv3_kernel<TA><<<cdiv(n, 256), 256, 0, stream>>>(arr(c.w), c.cin, 0, c.cin, c.cout, 0, nullptr, (TA*)Wf[l]);
+        pack_conv3_kernel<TG><<<cdiv(n, 256), 256, 0, stream>>>(arr(c.w), c.cin, 0, c.cin, c.cout, 1, nullptr, (TG*)Wd[l]);
     }
     long long nt = 4LL * 128 * 64;
     pack_up2_kernel<TA><<<cdiv(nt, 256), 256, 0, stream>>>(arr(kUpW), 128, 64, 0, (TA*)Wt);
@@ -491,6 +494,19 @@ inline void Engine::prepare_ecls() {
     ecls_valid = true;
 }
 
+template <typename TA, typename TG>
+void Engine::pack_infer_weights_t() {
+    for (int l = 2; l <= NUM_CONV; ++l) {
+        const ConvSpec& c = kConv[l];
+        long long n = 9LL * c.cin * c.cout;
+        pack_conv3_kernel<TA><<<cdiv(n, 256), 256, 0, stream>>>(arr(c.w), c.cin, 0, c.cin, c.cout, 0, inf_scale[l], (TA*)Wfi[l]);
+    }
+    DDPM_LAUNCH_CHECK();
+    cnt_launches += NUM_CONV - 1;
+}
+
+// Inference: BatchNorm with running statistics is a per-channel affine map; its scale is folded into
+// the packed weights (Wfi) and its shift into the conv epilogue.
 inline void Engine::prepare_infer_affine() {
     if (infer_affine_valid) return;
     for (int l = 1; l <= NUM_CONV; ++l) {
@@ -500,21 +516,22 @@ inline void Engine::prepare_infer_affine() {
     }
     DDPM_LAUNCH_CHECK();
     cnt_launches += NUM_CONV;
+    DDPM_DISPATCH(prec, (pack_infer_weights_t<TA, TG>()));
     infer_affine_valid = true;
 }
 
 // ------------------------------------------------------------------------------------ convolutions
 // Conv((3,3), cin=>cout, pad=1) of layer l on s0 (and s1 concatenated along channels)
 template <typename TA, typename TG>
-void Engine::conv3(const Tensor& s0, const Tensor* s1, int l, Tensor& out, const float* scale, const float* shift,
+void Engine::conv3(const Tensor& s0, const Tensor* s1, int l, Tensor& out, const void* weights, const float* shift,
                    int relu, double* stats) {
     const ConvSpec& c = kConv[l];
     const Geo& g = out.g;
     int C0 = s0.C, C1 = s1 ? s1->C : 0;
     DDPM_CHECK(C0 + C1 == c.cin && out.C == c.cout, "conv3: channel mismatch");
     if (use_tc()) {
-        if (tc::conv3x3<TA, TA>(stream, s0.pos0<TA>(), C0, s1 ? s1->pos0<TA>() : nullptr, C1, (const TA*)Wf[l], c.cout,
-                                out.pos0<TA>(), g, scale, shift, relu, nullptr)) {
+        if (tc::conv3x3<TA, TA>(stream, s0.pos0<TA>(), C0, s1 ? s1->pos0<TA>() : nullptr, C1, (const TA*)weights, c.cout,
+                                out.pos0<TA>(), g, shift, relu)) {
             cnt_launches += 1;
             if (stats) {  // train-mode BatchNorm statistics of the stored (rounded) y
                 long long pixels = (long long)g.N * g.H * g.W;
@@ -526,9 +543,9 @@ void Engine::conv3(const Tensor& s0, const Tensor* s1, int l, Tensor& out, const
         }
     }
     MapConv3 map{g.Wp, -(long long)g.guard, g.npos + g.guard};
-    EpiConv<TA> epi{out.view<TA>(), g, scale, shift, relu, stats};
+    EpiConv<TA> epi{out.view<TA>(), g, nullptr, shift, relu, stats};
     View<const TA> v1 = s1 ? s1->cview<TA>() : View<const TA>{nullptr, 0};
-    launch_igemm_simt<TA, TA>(stream, s0.cview<TA>(), C0, v1, C1, (const TA*)Wf[l], c.cout, 9, g.npos, map, epi);
+    launch_igemm_simt<TA, TA>(stream, s0.cview<TA>(), C0, v1, C1, (const TA*)weights, c.cout, 9, g.npos, map, epi);
     cnt_launches += 1;
 }
 
@@ -540,7 +557,7 @@ void Engine::dgrad3(const Tensor& dy, int l, Tensor& out, int out_c_total) {
     DDPM_CHECK(dy.C == c.cout && out.C == out_c_total && out_c_total == c.cin, "dgrad3: channel mismatch");
     if (use_tc()) {
         if (tc::conv3x3<TG, TG>(stream, dy.pos0<TG>(), c.cout, nullptr, 0, (const TG*)Wd[l], c.cin, out.pos0<TG>(), g,
-                                nullptr, nullptr, 0, nullptr)) {
+                                nullptr, 0)) {
             cnt_launches += 1;
             return;
         }
@@ -591,10 +608,10 @@ void Engine::forward_t(ActSet& s, const float* x_dev, const int* ts_dev, int t_f
     auto layer = [&](int l, const Tensor& in0, const Tensor* in1) {
         const ConvSpec& c = kConv[l];
         if (train) {
-            conv3<TA, TG>(in0, in1, l, s.y[l], nullptr, arr(c.b), 0, lsum(l));
+            conv3<TA, TG>(in0, in1, l, s.y[l], Wf[l], arr(c.b), 0, lsum(l));
             bn(l, l == 2);
         } else {
-            conv3<TA, TG>(in0, in1, l, s.a[l], inf_scale[l], inf_shift[l], 1, nullptr);
+            conv3<TA, TG>(in0, in1, l, s.a[l], Wfi[l], inf_shift[l], 1, nullptr);
         }
     };
 

@@ -730,16 +730,19 @@ adam_kernel(float* __restrict__ p, const float* __restrict__ g, float* __restric
 // Flux Conv weight w[a,b,ci,co] (column-major; true convolution) -> cross-correlation, K-major:
 //   fwd  : Wf[co][tap][ci]  = w[1-dx, 1-dy, ci+ci_off, co]              tap = (dy+1)*3 + (dx+1)
 //   dgrad: Wd[ci][tap][co]  = w[1+dx, 1+dy, ci, co]                     (transposed, un-flipped)
+// row_scale (forward packing only): per-output-channel factor folded into the weights in FP32 before
+// rounding (inference BatchNorm fold: W' = W * gamma/sqrt(var_run+eps)).
 template <typename TW>
 __global__ void pack_conv3_kernel(const float* __restrict__ w, int Cin_total, int ci_off, int Cin, int Cout,
-                                  int dgrad, TW* __restrict__ out) {
+                                  int dgrad, const float* __restrict__ row_scale, TW* __restrict__ out) {
     long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
     long long total = 9LL * Cin * Cout;
     if (i >= total) return;
     if (!dgrad) {
         int ci = (int)(i % Cin), tap = (int)((i / Cin) % 9), co = (int)(i / (9LL * Cin));
         int dy = tap / 3 - 1, dx = tap % 3 - 1;
-        out[i] = from_f<TW>(w[(1 - dx) + 3 * (1 - dy) + 9LL * (ci + ci_off) + 9LL * Cin_total * co]);
+        float v = w[(1 - dx) + 3 * (1 - dy) + 9LL * (ci + ci_off) + 9LL * Cin_total * co];
+        out[i] = from_f<TW>(row_scale ? v * row_scale[co] : v);
     } else {
         int co = (int)(i % Cout), tap = (int)((i / Cout) % 9), ci = (int)(i / (9LL * Cout));
         int dy = tap / 3 - 1, dx = tap % 3 - 1;

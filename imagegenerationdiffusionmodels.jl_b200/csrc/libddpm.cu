@@ -366,7 +366,13 @@ int ddpm_set_option(ddpm_handle* h, const char* key, int64_t value) {
     else if (k == "use_graph") e.opt_use_graph = value;
     else if (k == "conv_impl") { e.opt_conv_impl = value; for (auto& kv : e.infer_sets) kv.second->drop_graphs(); }
     else if (k == "sync_bn") e.sync_bn = (int)value;
-    else if (k == "tc_base_offset") { tc::state().base_offset_mode = (int)value; for (auto& kv : e.infer_sets) kv.second->drop_graphs(); }
+    else if (k == "tc_role_profile") {
+        // per-CTA cycle breakdown of the tcgen05 kernel roles, read back with ddpm_debug_fetch("tc_roles")
+        if (value && !tc::state().dbg) DDPM_CUDA(cudaMalloc(&tc::state().dbg, 512 * 8 * sizeof(long long)));
+        if (tc::state().dbg) DDPM_CUDA(cudaMemset(tc::state().dbg, 0, 512 * 8 * sizeof(long long)));
+        if (!value && tc::state().dbg) { cudaFree(tc::state().dbg); tc::state().dbg = nullptr; }
+        for (auto& kv : e.infer_sets) kv.second->drop_graphs();
+    }
     else throw Error("unknown option: " + k);
     API_END
 }
@@ -487,7 +493,7 @@ int ddpm_time_kernel(ddpm_handle* h, const char* name, int64_t n_images, int ite
             }
             // inference aliasing: a[l] may alias an input two layers back, never in0/in1
             DDPM_DISPATCH(e.prec, time_it([&] {
-                e.conv3<TA, TG>(*in0, in1, l, s.a[l], e.inf_scale[l], e.inf_shift[l], 1, nullptr);
+                e.conv3<TA, TG>(*in0, in1, l, s.a[l], e.Wfi[l], e.inf_shift[l], 1, nullptr);
             }));
             double px = (double)N * c.hw * c.hw;
             fl = 2.0 * px * c.cout * 9.0 * c.cin;
@@ -509,6 +515,15 @@ int ddpm_debug_fetch(ddpm_handle* h, const char* name, float* out, int64_t capac
     Engine& e = E(h);
     std::string k = name ? name : "";
     DDPM_CUDA(cudaStreamSynchronize(e.stream));
+    if (k == "tc_roles") {
+        DDPM_CHECK(tc::state().dbg != nullptr, "role profiling is off");
+        if (written) *written = 512 * 8;
+        DDPM_CHECK(out && capacity >= 512 * 8, "output buffer too small");
+        std::vector<long long> hbuf(512 * 8);
+        DDPM_CUDA(cudaMemcpy(hbuf.data(), tc::state().dbg, hbuf.size() * 8, cudaMemcpyDeviceToHost));
+        for (size_t i = 0; i < hbuf.size(); ++i) out[i] = (float)hbuf[i];
+        return 0;
+    }
     ActSet* sp = &e.train_set;
     if (k.rfind("infer:", 0) == 0) {
         DDPM_CHECK(!e.infer_sets.empty(), "no inference activations");

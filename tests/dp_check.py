@@ -1,0 +1,91 @@
+"""Run under torchrun (one rank per GPU): data-parallel training and sharded sampling must reproduce
+the single-GPU result.  Rank 0 prints a JSON verdict and exits non-zero on failure."""
+import json
+import os
+import sys
+
+import numpy as np
+import torch
+import torch.distributed as td
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+sys.path.insert(0, ROOT)
+import igdm_b200  # noqa: E402,F401
+from igdm_b200 import api, capi, dist, tables  # noqa: E402
+
+
+def make_handle(device, prec):
+    h = capi.Handle(T=500, precision=prec, device=device)
+    beta, _, acum = tables.beta_schedule(500)
+    h.set_tables(beta, acum, tables.embedding_table(500))
+    h.set_weights(api.SimpleUNet.load().arrays)
+    h.set_adam(1e-4, 0.9, 0.999, 1e-8)
+    return h
+
+
+def main():
+    rank, world, local = dist.env_rank_world()
+    torch.cuda.set_device(local)
+    td.init_process_group("nccl", device_id=torch.device("cuda", local))
+    prec = capi.PREC_FP32 if os.environ.get("DP_PREC", "fp32") == "fp32" else capi.PREC_FP16
+    data = (api.load_dataset() * np.float32(2) - np.float32(1)).astype(np.float32)
+    Bg = 64
+    b0, b1 = dist.shard_range(Bg, rank, world)
+    verdict = {"world": world}
+    ok = True
+
+    # ---- data-parallel training with SyncBN == single-GPU global batch
+    h = make_handle(local, prec)
+    dist.init_data_parallel(h, sync_bn=True)
+    dp_losses = []
+    for k in range(3):
+        ts = np.random.default_rng(100 + k).integers(1, 501, Bg)
+        eps = np.random.default_rng(200 + k).standard_normal((Bg, 1, 32, 32)).astype(np.float32)
+        x0 = data[k * Bg:(k + 1) * Bg]
+        dp_losses.append(h.train_step(x0[b0:b1], ts[b0:b1], eps[b0:b1]))
+    w_dp = h.get_weights()
+    if rank == 0:
+        ref = make_handle(local, prec)
+        ref_losses = []
+        for k in range(3):
+            ts = np.random.default_rng(100 + k).integers(1, 501, Bg)
+            eps = np.random.default_rng(200 + k).standard_normal((Bg, 1, 32, 32)).astype(np.float32)
+            ref_losses.append(ref.train_step(data[k * Bg:(k + 1) * Bg], ts, eps))
+        w_ref = ref.get_weights()
+        rel = [abs(a - b) / b for a, b in zip(dp_losses, ref_losses)]
+        wrel = max(float(np.linalg.norm(a - b) / max(np.linalg.norm(b), 1e-12)) for a, b in zip(w_dp, w_ref)
+                   if np.linalg.norm(b) > 1e-3)
+        verdict.update(dp_losses=dp_losses, ref_losses=ref_losses, loss_rel=rel, weight_rel=wrel)
+        ok &= max(rel) < (1e-4 if prec == capi.PREC_FP32 else 2e-3) and wrel < 5e-3
+        ref.close()
+    # every rank must hold identical weights after the all-reduced update
+    w0 = torch.tensor(np.concatenate([w.ravel() for w in w_dp])).cuda()
+    wmax, wmin = w0.clone(), w0.clone()
+    td.all_reduce(wmax, op=td.ReduceOp.MAX)
+    td.all_reduce(wmin, op=td.ReduceOp.MIN)
+    same = bool(torch.equal(wmax, wmin))
+    verdict["replicas_identical"] = same
+    ok &= same
+    h.close()
+
+    # ---- sampling shards: union of the shards == one-GPU run, bit for bit, no collective in the path
+    hs = make_handle(local, capi.PREC_FP16)
+    N, t0 = 12, 10
+    s0, s1 = dist.shard_range(N, rank, world)
+    mine = hs.sample(s1 - s0, seed=77, first_index=1000 + s0, t_start=t0)
+    full = dist.gather_shards(mine, N)
+    if rank == 0:
+        whole = hs.sample(N, seed=77, first_index=1000, t_start=t0)
+        verdict["sampling_bit_identical"] = bool(np.array_equal(full, whole))
+        ok &= verdict["sampling_bit_identical"]
+    hs.close()
+    if rank == 0:
+        verdict["ok"] = bool(ok)
+        print(json.dumps(verdict), flush=True)
+    td.barrier()
+    td.destroy_process_group()
+    sys.exit(0 if ok else 1)
+
+
+if __name__ == "__main__":
+    main()
