@@ -132,6 +132,7 @@ struct ActSet {
     std::vector<void*> owned;
     DevBuf x, eps_hat;  // boundary-layout Float32 [N][H*W]
     DevBuf z;           // host-supplied sampler noise [steps][N][H*W]
+    DevBuf zstep;       // device-generated noise of the current step [N][H*W]
     // captured reverse loops, keyed by (t_start, zmode); they bake in this set's pointers
     std::map<std::pair<int, int>, GraphEntry> graphs;
     void drop_graphs() {
@@ -401,7 +402,7 @@ inline void Engine::free_set(ActSet& s) {
     s.drop_graphs();
     for (void* p : s.owned) cudaFree(p);
     s.owned.clear();
-    s.x.release(); s.eps_hat.release(); s.z.release();
+    s.x.release(); s.eps_hat.release(); s.z.release(); s.zstep.release();
     s = ActSet();
 }
 
@@ -433,6 +434,7 @@ inline void Engine::build_set(ActSet& s, int N, bool training) {
     }
     s.x.ensure((size_t)N * HW * 4);
     s.eps_hat.ensure((size_t)N * HW * 4);
+    if (!training) s.zstep.ensure((size_t)N * HW * 4);
 }
 
 inline ActSet& Engine::get_set(int N, bool training) {
@@ -618,9 +620,9 @@ void Engine::forward_t(ActSet& s, const float* x_dev, const int* ts_dev, int t_f
     // ---- down1.conv1 (+ folded embedding)
     {
         const ConvSpec& c = kConv[1];
-        long long work = (long long)N * HW * 8;
+        long long pixels = (long long)N * HW;
         Tensor& o = train ? s.y[1] : s.a[1];
-        conv1_kernel<TA><<<cdiv(work, 256), 256, 0, stream>>>(x_dev, ts_dev, t_fixed, Wimg, Ecls,
+        conv1_kernel<TA><<<cdiv(pixels, CONV1_PIX_PER_BLOCK), 256, 0, stream>>>(x_dev, ts_dev, t_fixed, Wimg, Ecls,
                                                               train ? nullptr : inf_scale[1], train ? arr(c.b) : inf_shift[1],
                                                               train ? 0 : 1, o.view<TA>(), o.g, train ? lsum(1) : nullptr);
         DDPM_LAUNCH_CHECK();
@@ -865,13 +867,21 @@ inline void Engine::train_core(int B, bool gather, bool update, float* loss_out_
 template <typename TA, typename TG>
 void Engine::sample_steps_t(ActSet& s, float* x_dev, const float* z_dev, int N, int t_start) {
     for (int t = t_start, k = 0; t >= 2; --t, ++k) {
+        const float* zstep = z_dev ? z_dev + (size_t)k * N * HW : nullptr;
+        if (!zstep) {
+            // fresh noise of this step, Philox keyed by (seed, global image index, t): one fully parallel
+            // launch (4 draws per thread) instead of one divergent generator lane per 8 in the fused kernel
+            long long quads = (long long)N * HW / 4;
+            randn_dev_kernel<<<cdiv(quads, 256), 256, 0, stream>>>(s.zstep.as<float>(), N, HW, d_rng, (uint32_t)t);
+            cnt_launches += 1;
+            zstep = s.zstep.as<float>();
+        }
         forward_t<TA, TG>(s, x_dev, nullptr, t, Mode::Infer, false);
         const float* sc = &h_samp[(size_t)(t - 1) * 4];
         long long work = (long long)N * HW * 8;
         final_conv_kernel<TA><<<cdiv(work, 256), 256, 0, stream>>>(
             s.a[10].cview<TA>(), s.a[10].g, arr(kFinalW), arr(kFinalB), nullptr, 1, x_dev,
-            z_dev ? z_dev + (size_t)k * N * HW : nullptr, make_float4(sc[0], sc[1], sc[2], sc[3]), d_rng, (uint32_t)t,
-            t == 2 ? 1 : 0);
+            zstep, make_float4(sc[0], sc[1], sc[2], sc[3]), d_rng, (uint32_t)t, t == 2 ? 1 : 0);
         cnt_launches += 1;
     }
     DDPM_LAUNCH_CHECK();

@@ -93,6 +93,18 @@ __global__ void randn_kernel(float* __restrict__ x, long long n_img, int hw, uns
     *reinterpret_cast<float4*>(x + n * hw + 4 * q) = z;
 }
 
+// same with (seed, first_index) read from device memory, so one captured graph serves every chunk
+__global__ void randn_dev_kernel(float* __restrict__ x, long long n_img, int hw, const unsigned long long* __restrict__ rng_dev,
+                                 uint32_t step) {
+    long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    int qpi = hw / 4;
+    if (i >= n_img * qpi) return;
+    long long n = i / qpi;
+    int q = (int)(i - n * qpi);
+    float4 z = Philox::normal4(rng_dev[0], rng_dev[1] + (unsigned long long)n, step, (uint32_t)q);
+    *reinterpret_cast<float4*>(x + n * hw + 4 * q) = z;
+}
+
 // ts[n] ~ U{1..T}: mulhi of a Philox word (step-keyed, component by image index)
 __global__ void randint_ts_kernel(int* __restrict__ ts, int B, int T, unsigned long long seed,
                                   long long first_index, uint32_t step) {
@@ -154,54 +166,70 @@ __global__ void apply_noise_f64_kernel(const double* __restrict__ img, const dou
 // image); only the image channel is convolved (K = 9), in FP32 on CUDA cores.
 //   y = (sum_tap x[h+dy,w+dx]*Wimg[tap][co] + Ecls[t][cls][co]) * scale[co] + shift[co]
 // x is the unpadded boundary layout [N][H][W].
+constexpr int CONV1_PIX_PER_BLOCK = 512;
+
+// Thread layout: 8 lanes per pixel, 8 output channels per lane.  The 72 image-channel weights, scale and
+// shift of a lane's 8 channels live in registers for the whole block (no shared-memory traffic in the
+// pixel loop); H = W = 32 is a compile-time constant (the engine rejects other sizes).
 template <typename TA>
 __global__ void __launch_bounds__(256)
 conv1_kernel(const float* __restrict__ x, const int* __restrict__ ts, int t_fixed, const float* __restrict__ Wimg,
              const float* __restrict__ Ecls, const float* __restrict__ scale, const float* __restrict__ shift, int relu,
              View<TA> out, Geo g, double* __restrict__ stats) {
-    __shared__ float w_s[9 * 64];
-    __shared__ float sc_s[64], sh_s[64];
+    constexpr int H = 32, W = 32, HW = H * W;
     __shared__ float red[2][64];
     const int t = threadIdx.x;
-    for (int i = t; i < 576; i += 256) w_s[i] = Wimg[i];
-    if (t < 64) {
-        sc_s[t] = scale ? scale[t] : 1.f;
-        sh_s[t] = shift ? shift[t] : 0.f;
-        red[0][t] = 0.f; red[1][t] = 0.f;
+    const int cg = (t & 7) * 8;
+    float wr[9][8], sc[8], sh[8];
+#pragma unroll
+    for (int tap = 0; tap < 9; ++tap) {
+        const float4 a = *reinterpret_cast<const float4*>(Wimg + tap * 64 + cg);
+        const float4 b = *reinterpret_cast<const float4*>(Wimg + tap * 64 + cg + 4);
+        wr[tap][0] = a.x; wr[tap][1] = a.y; wr[tap][2] = a.z; wr[tap][3] = a.w;
+        wr[tap][4] = b.x; wr[tap][5] = b.y; wr[tap][6] = b.z; wr[tap][7] = b.w;
     }
-    __syncthreads();
-    const int H = g.H, W = g.W;
-    long long idx = (long long)blockIdx.x * 256 + t;
-    long long pix = idx >> 3;
-    const int cg = (int)(idx & 7) * 8;
+#pragma unroll
+    for (int j = 0; j < 8; ++j) {
+        sc[j] = scale ? scale[cg + j] : 1.f;
+        sh[j] = shift ? shift[cg + j] : 0.f;
+    }
+    if (stats) {
+        if (t < 64) { red[0][t] = 0.f; red[1][t] = 0.f; }
+        __syncthreads();
+    }
+    const long long total = (long long)g.N * HW;
     float s1[8], s2[8];
 #pragma unroll
     for (int j = 0; j < 8; ++j) { s1[j] = 0.f; s2[j] = 0.f; }
-    if (pix < (long long)g.N * H * W) {
-        int n = (int)(pix / (H * W));
-        int rem = (int)(pix - (long long)n * H * W);
-        int h = rem / W, w = rem - h * W;
-        const float* xi = x + (long long)n * H * W;
+    const long long pbeg = (long long)blockIdx.x * CONV1_PIX_PER_BLOCK;
+    for (long long pix = pbeg + (t >> 3); pix < pbeg + CONV1_PIX_PER_BLOCK && pix < total; pix += 32) {
+        const int n = (int)(pix >> 10);
+        const int rem = (int)(pix & (HW - 1));
+        const int h = rem >> 5, w = rem & 31;
+        const float* xi = x + (long long)n * HW;
         float xv[9];
 #pragma unroll
         for (int tap = 0; tap < 9; ++tap) {
-            int hh = h + tap / 3 - 1, ww = w + tap % 3 - 1;
-            xv[tap] = (hh >= 0 && hh < H && ww >= 0 && ww < W) ? xi[hh * W + ww] : 0.f;
+            const int hh = h + tap / 3 - 1, ww = w + tap % 3 - 1;
+            xv[tap] = (hh >= 0 && hh < H && ww >= 0 && ww < W) ? __ldg(xi + hh * W + ww) : 0.f;
         }
-        int cls = (h == 0 ? 0 : (h == H - 1 ? 2 : 1)) * 3 + (w == 0 ? 0 : (w == W - 1 ? 2 : 1));
-        int trow = ts ? (ts[n] - 1) : (t_fixed - 1);
+        const int cls = (h == 0 ? 0 : (h == H - 1 ? 2 : 1)) * 3 + (w == 0 ? 0 : (w == W - 1 ? 2 : 1));
+        const int trow = ts ? (ts[n] - 1) : (t_fixed - 1);
         const float* e = Ecls + ((long long)trow * 9 + cls) * 64 + cg;
+        const float4 e0 = __ldg(reinterpret_cast<const float4*>(e));
+        const float4 e1 = __ldg(reinterpret_cast<const float4*>(e + 4));
+        const float ev[8] = {e0.x, e0.y, e0.z, e0.w, e1.x, e1.y, e1.z, e1.w};
         float o[8];
 #pragma unroll
         for (int j = 0; j < 8; ++j) {
             float acc = 0.f;
 #pragma unroll
-            for (int tap = 0; tap < 9; ++tap) acc = fmaf(xv[tap], w_s[tap * 64 + cg + j], acc);
-            float v = (acc + e[j]) * sc_s[cg + j] + sh_s[cg + j];
-            s1[j] = v; s2[j] = v * v;
+            for (int tap = 0; tap < 9; ++tap) acc = fmaf(xv[tap], wr[tap][j], acc);
+            const float v = (acc + ev[j]) * sc[j] + sh[j];
+            s1[j] += v; s2[j] = fmaf(v, v, s2[j]);
             o[j] = relu ? fmaxf(v, 0.f) : v;
         }
-        V8<TA>::st(out.p + g.pos(n, h, w) * out.cs + cg, o);
+        V8<TA>::st(out.p + ((long long)(n * (H + 1) + 1 + h) * (W + 2) + (w + 1)) * out.cs + cg, o);
     }
     if (stats) {
 #pragma unroll

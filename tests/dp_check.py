@@ -53,8 +53,11 @@ def main():
             ref_losses.append(ref.train_step(data[k * Bg:(k + 1) * Bg], ts, eps))
         w_ref = ref.get_weights()
         rel = [abs(a - b) / b for a, b in zip(dp_losses, ref_losses)]
-        wrel = max(float(np.linalg.norm(a - b) / max(np.linalg.norm(b), 1e-12)) for a, b in zip(w_dp, w_ref)
-                   if np.linalg.norm(b) > 1e-3)
+        # conv biases in front of a train-mode BatchNorm have a mathematically zero gradient; Adam turns the
+        # rounding noise there into +-eta steps, so those ten arrays are not comparable between any two runs
+        free = {1, 7, 13, 19, 25, 31, 39, 45, 51, 57}
+        wrel = max(float(np.linalg.norm(a - b) / max(np.linalg.norm(b), 1e-12))
+                   for k, (a, b) in enumerate(zip(w_dp, w_ref)) if k not in free and np.linalg.norm(b) > 1e-3)
         verdict.update(dp_losses=dp_losses, ref_losses=ref_losses, loss_rel=rel, weight_rel=wrel)
         ok &= max(rel) < (1e-4 if prec == capi.PREC_FP32 else 2e-3) and wrel < 5e-3
         ref.close()

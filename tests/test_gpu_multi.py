@@ -36,9 +36,10 @@ def test_data_parallel_matches_single_gpu(prec):
            "--master-port", str(_free_port()), os.path.join(ROOT, "tests", "dp_check.py")]
     res = subprocess.run(cmd, capture_output=True, text=True, timeout=600, env=env)
     lines = [l for l in res.stdout.splitlines() if l.startswith("{")]
-    assert res.returncode == 0 and lines, res.stdout[-2000:] + res.stderr[-2000:]
+    assert lines, res.stdout[-2000:] + res.stderr[-2000:]
     v = json.loads(lines[-1])
+    print(v)
     os.makedirs(os.path.join(ROOT, "gpurun_out"), exist_ok=True)
     with open(os.path.join(ROOT, "gpurun_out", f"dp_check_{prec}.json"), "w") as fh:
         json.dump(v, fh, indent=1)
-    assert v["ok"], v
+    assert v["ok"] and res.returncode == 0, v

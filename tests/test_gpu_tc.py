@@ -44,14 +44,12 @@ def test_tc_matches_simt_per_layer(gpu_handles, oracle, model_arrays, dataset, t
         # taken from the absolute shared-memory address bits, so a row-advanced start needs no base offset.
         for bo in (0,):
             h.set_option("conv_impl", 2)
-            h.set_option("tc_base_offset", bo)
             got = _layers(h, xt, ts)
             e_got = h.predict_eps(xt, ts, train_mode=False)
             report[f"base_offset_{bo}"] = {nm: rel_l2(got[nm], ref[nm]) for nm in NAMES}
             report[f"base_offset_{bo}"]["eps_test_mode"] = rel_l2(e_got, e_ref)
     finally:
         h.set_option("conv_impl", 0)
-        h.set_option("tc_base_offset", 0)
         _dump(f"tc_vs_simt_{mode}.json", report)
     tol = 3e-3 if mode == "fp16" else 2e-2     # same inputs, different accumulation order + re-rounding
     bad = {k: v for k, v in report["base_offset_0"].items() if not (v <= tol)}
