@@ -21,6 +21,7 @@
 #include <cuda.h>
 #include <map>
 #include <tuple>
+#include <type_traits>
 #include "common.cuh"
 
 namespace ddpm {
@@ -615,9 +616,241 @@ bool up2(cudaStream_t st, const TA* a6, const TA* Wt, TA* u, const Geo& gi, cons
     }
 }
 
+// =====================================================================================
+// Weight gradient of a 3x3 convolution on tensor cores.
+//   dWcc[co][ty,tx][ci] = sum_pos dy[pos][co] * x[pos + ty*Wp + tx][ci]      (halo rows of dy are zero)
+// is a GEMM over the POSITION dimension whose operands are both "MN-major" (channels contiguous):
+//   A'[k][(ty,co)] = dy[k - ty*Wp][co]     M = 128 = two kernel rows ty at once: the second 64-row group of
+//                                          the descriptor is the SAME shared-memory slab, LBO = Wp rows further
+//   B'[k][(tx,ci)] = x [k + tx    ][ci]     N = 192 = the three kernel columns tx: groups LBO = 1 row apart
+// so per 16 positions two tcgen05.mma (M=128,N=192,K=16) produce all nine 64x64 tap blocks:
+//   MMA1 -> (ty=+1 | ty=0) x (tx=-1,0,+1),   MMA2 -> (ty=-1 | unused) x (tx=-1,0,+1).
+// Each CTA streams its share of the positions through a TMA ring (dy slab [KB+2Wp][64], x slab [KB+2][64]),
+// accumulates in TMEM for the whole launch (2 x 192 columns) and writes ONE partial [9][64][64] FP32 block;
+// wgrad_reduce_kernel sums the partials into the gradient arena in Flux layout (deterministic, no atomics).
+// Replaces NNlib.∇conv_filter (im2col + SGEMM) behind Zygote's pullback (train_brain.jl:267-269).
+constexpr int WG_KB = 128;        // positions per pipeline stage
+constexpr int WG_THREADS = 192;
+
+__host__ __device__ constexpr uint32_t make_idesc_mn(uint32_t afmt, uint32_t bfmt, uint32_t M, uint32_t N) {
+    return (1u << 4) | (afmt << 7) | (bfmt << 10) | (1u << 15) | (1u << 16) | ((N >> 3) << 17) | ((M >> 4) << 24);
+}
+
+struct WgParams {
+    float* partial;      // [gridDim.y][gridDim.x][9][64][64]
+    int num_kblocks;     // ceil(npos / WG_KB)
+    int guard;
+    int dy_chunk[4], x_chunk[4];   // per blockIdx.y: 64-channel chunk index of dy (co) and x (ci)
+};
+
+template <int WP, int STAGES, typename TDy, typename TX>
+__global__ void __launch_bounds__(WG_THREADS, 1)
+wgrad_tc_kernel(const __grid_constant__ CUtensorMap tmDy, const __grid_constant__ CUtensorMap tmX, const WgParams p) {
+    constexpr int RDY = ((WG_KB + 2 * WP + 7) / 8) * 8;    // dy slab rows: positions k0-Wp .. k0+KB+Wp
+    constexpr int RX = ((WG_KB + 2 + 7) / 8) * 8;          // x slab rows:  positions k0-1  .. k0+KB+1
+    constexpr uint32_t DY_BYTES = RDY * 128, X_BYTES = RX * 128, STAGE_BYTES = DY_BYTES + X_BYTES;
+    constexpr uint32_t IDESC = make_idesc_mn(IsBf16<TDy>::v, IsBf16<TX>::v, 128, 192);
+
+    extern __shared__ uint8_t smem_raw[];
+    uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
+    const uint32_t s_base = smem_u32(smem);
+    const uint32_t s_bar = s_base + STAGES * STAGE_BYTES;
+    auto bar_full = [&](int s) { return s_bar + 8u * s; };
+    auto bar_empty = [&](int s) { return s_bar + 8u * (STAGES + s); };
+    const uint32_t bar_acc = s_bar + 8u * (2 * STAGES);
+    uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(smem + STAGES * STAGE_BYTES + 8 * (2 * STAGES + 1));
+
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    if (warp == 0 && lane == 0) {
+        prefetch_tmap(&tmDy); prefetch_tmap(&tmX);
+        for (int s = 0; s < STAGES; ++s) { mbar_init(bar_full(s), 1); mbar_init(bar_empty(s), 1); }
+        mbar_init(bar_acc, 1);
+        fence_barrier_init();
+    }
+    if (warp == 2) tmem_alloc<512>(smem_u32(tmem_slot));
+    tc_fence_before();
+    __syncthreads();
+    tc_fence_after();
+    const uint32_t tmem_base = *tmem_slot;
+    const int dyc = p.dy_chunk[blockIdx.y] * 64, xc = p.x_chunk[blockIdx.y] * 64;
+
+    if (warp == 0) {
+        int stage = 0;
+        uint32_t phase = 0;
+        for (int kb = blockIdx.x; kb < p.num_kblocks; kb += gridDim.x) {
+            mbar_wait(bar_empty(stage), phase ^ 1);
+            if (elect_one()) {
+                const int k0 = kb * WG_KB + p.guard;
+                mbar_expect_tx(bar_full(stage), STAGE_BYTES);
+                tma_load_2d(s_base + stage * STAGE_BYTES, &tmDy, dyc, k0 - WP, bar_full(stage));
+                tma_load_2d(s_base + stage * STAGE_BYTES + DY_BYTES, &tmX, xc, k0 - 1, bar_full(stage));
+            }
+            __syncwarp();
+            if (++stage == STAGES) { stage = 0; phase ^= 1; }
+        }
+    } else if (warp == 1) {
+        // MN-major, 128B swizzle: hi = SBO (8 K-rows = 1024 B) | version | SWIZZLE_128B ; lo = start>>4 | LBO<<16
+        constexpr uint32_t DESC_HI = (1024u >> 4) | (1u << 14) | (2u << 29);
+        constexpr uint32_t LBO_A = (uint32_t)(WP * 128) >> 4;     // second M group = Wp positions further (ty one lower)
+        constexpr uint32_t LBO_B = 128u >> 4;                     // N groups = consecutive positions (tx = -1, 0, +1)
+        int stage = 0;
+        uint32_t phase = 0;
+        uint32_t first = 1;
+        for (int kb = blockIdx.x; kb < p.num_kblocks; kb += gridDim.x) {
+            mbar_wait(bar_full(stage), phase);
+            tc_fence_after();
+            if (elect_one()) {
+                const uint32_t a0 = (((s_base + stage * STAGE_BYTES) & 0x3FFFFu) >> 4);
+                const uint32_t b0 = (((s_base + stage * STAGE_BYTES + DY_BYTES) & 0x3FFFFu) >> 4) | (LBO_B << 16);
+#pragma unroll
+                for (int ks = 0; ks < WG_KB / 16; ++ks) {
+                    const uint32_t acc = (first && ks == 0) ? 0u : 1u;
+                    // rows of the dy slab: ty=+1 at +0, ty=0 at +Wp, ty=-1 at +2Wp (slab starts at k0-Wp)
+                    umma_f16_lh(tmem_base, (a0 + ((ks * 16 * 128) >> 4)) | (LBO_A << 16), b0 + ((ks * 16 * 128) >> 4), DESC_HI,
+                                IDESC, acc);
+                    umma_f16_lh(tmem_base + 192, (a0 + (((2 * WP + ks * 16) * 128) >> 4)) | (LBO_B << 16),
+                                b0 + ((ks * 16 * 128) >> 4), DESC_HI, IDESC, acc);
+                }
+                umma_commit(bar_empty(stage));
+            }
+            __syncwarp();
+            first = 0;
+            if (++stage == STAGES) { stage = 0; phase ^= 1; }
+        }
+        if (elect_one()) umma_commit(bar_acc);
+        __syncwarp();
+    } else {
+        // epilogue: one partial block per CTA.  TMEM lane l: D1 -> (ty = l<64 ? +1 : 0, co = l%64), D2 lanes 0..63 -> ty=-1
+        const int lane_grp = warp & 3;
+        const int l = lane_grp * 32 + lane;
+        const int co = l & 63;
+        float* dst = p.partial + ((size_t)blockIdx.y * gridDim.x + blockIdx.x) * (9 * 64 * 64);
+        mbar_wait(bar_acc, 0);
+        tc_fence_after();
+        const bool has_work = blockIdx.x < p.num_kblocks;   // always true (grid <= kblocks), kept for safety
+#pragma unroll 1
+        for (int d = 0; d < 2; ++d) {
+            const int ty = (d == 0) ? (l < 64 ? 1 : 0) : -1;
+            const bool live = has_work && (d == 0 || l < 64);
+#pragma unroll 1
+            for (int txi = 0; txi < 3; ++txi) {
+                const int tap = (ty + 1) * 3 + txi;
+                float* row = dst + ((size_t)tap * 64 + co) * 64;
+#pragma unroll
+                for (int c0 = 0; c0 < 64; c0 += 16) {
+                    uint32_t r[16];
+                    tmem_ld16(tmem_base + ((uint32_t)(lane_grp * 32) << 16) + d * 192 + txi * 64 + c0, r);
+                    tmem_ld_wait();
+                    if (live) {
+#pragma unroll
+                        for (int j = 0; j < 16; j += 4)
+                            *reinterpret_cast<float4*>(row + c0 + j) = make_float4(__uint_as_float(r[j]), __uint_as_float(r[j + 1]),
+                                                                                   __uint_as_float(r[j + 2]), __uint_as_float(r[j + 3]));
+                    }
+                }
+            }
+        }
+    }
+    tc_fence_before();
+    __syncthreads();
+    if (warp == 2) {
+        tc_fence_after();
+        tmem_dealloc<512>(tmem_base);
+    }
+}
+
+// arena[flux index of (tap, co_off+co, ci_off+ci)] = alpha * sum_cta partial[y][cta][tap][co][ci]
+__global__ void wgrad_reduce_kernel(const float* __restrict__ partial, int n_cta, int n_sub, const int* __restrict__ sub_co,
+                                    const int* __restrict__ sub_ci, int Cin_total, int ci_base, float alpha,
+                                    float* __restrict__ dW) {
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;      // over n_sub * 9*64*64
+    if (i >= n_sub * 36864) return;
+    const int y = i / 36864, e = i - y * 36864;
+    const int ci = e & 63, co = (e >> 6) & 63, tap = e >> 12;
+    const float* src = partial + (size_t)y * n_cta * 36864 + e;
+    float s = 0.f;
+    for (int c = 0; c < n_cta; ++c) s += src[(size_t)c * 36864];
+    const int dy = tap / 3 - 1, dx = tap % 3 - 1;
+    const long long idx = (long long)(1 - dx) + 3 * (1 - dy) + 9LL * (ci_base + sub_ci[y] * 64 + ci) +
+                          9LL * Cin_total * (sub_co[y] * 64 + co);
+    dW[idx] = alpha * s;
+}
+
+struct WgScratch {
+    float* partial = nullptr;
+    size_t cap = 0;
+    int* sub = nullptr;     // device [8]: co chunk [0..3], ci chunk [4..7]
+};
+inline WgScratch& wg_scratch() {
+    static WgScratch s;
+    return s;
+}
+
+template <int WP, typename TDy, typename TX>
+void launch_wgrad(cudaStream_t st, const CUtensorMap& mdy, const CUtensorMap& mx, const WgParams& p, int ctas_x, int n_sub) {
+    constexpr int RDY = ((WG_KB + 2 * WP + 7) / 8) * 8, RX = ((WG_KB + 2 + 7) / 8) * 8;
+    constexpr int STAGE = (RDY + RX) * 128;
+    constexpr int STAGES = (227 * 1024 - 2048) / STAGE > 6 ? 6 : (227 * 1024 - 2048) / STAGE;
+    constexpr size_t smem = 1024 + (size_t)STAGES * STAGE + 512;
+    auto kern = wgrad_tc_kernel<WP, STAGES, TDy, TX>;
+    static bool attr_set = false;
+    if (!attr_set) {
+        DDPM_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        attr_set = true;
+    }
+    kern<<<dim3(ctas_x, n_sub), WG_THREADS, smem, st>>>(mdy, mx, p);
+    DDPM_LAUNCH_CHECK();
+}
+
+// dW of Conv((3,3)) for dy [pos][Cout] and x [pos][Cx] (one source of the input; ci_off = its offset in the
+// layer's Cin_total input channels).  Writes (not accumulates) the Flux-layout block of the gradient arena.
 template <typename TG, typename TA>
-bool wgrad3x3(cudaStream_t, const TG*, int, const TA*, int, const Geo&, float*, int, int) {
-    return false;
+bool wgrad3x3(cudaStream_t st, const TG* dy, int Cout, const TA* x, int Cx, const Geo& g, float* dW, int Cin_total, int ci_off,
+              float alpha) {
+    if (!available()) return false;
+    // kind::f16 requires A and B of the SAME 16-bit format (mixed bf16 x f16 raises an illegal-instruction
+    // fault on B200, measured in round 1), hence gradients share the activation format.
+    if constexpr (sizeof(TG) != 2 || sizeof(TA) != 2 || !std::is_same<TG, TA>::value) {
+        return false;
+    } else {
+    if ((Cout != 64 && Cout != 128) || (Cx != 64 && Cx != 128) || (g.Wp != 34 && g.Wp != 18)) return false;
+    const int nco = Cout / 64, nci = Cx / 64, n_sub = nco * nci;
+    const int num_kblocks = cdiv(g.npos, WG_KB);
+    int ctas_x = state().num_sms / n_sub;
+    if (ctas_x > num_kblocks) ctas_x = num_kblocks;
+    if (ctas_x < 1) ctas_x = 1;
+    WgScratch& sc = wg_scratch();
+    const size_t need = (size_t)n_sub * ctas_x * 36864 * sizeof(float);
+    if (sc.cap < need) {
+        DDPM_CUDA(cudaStreamSynchronize(st));
+        if (sc.partial) cudaFree(sc.partial);
+        DDPM_CUDA(cudaMalloc(&sc.partial, (size_t)4 * state().num_sms * 36864 * sizeof(float)));
+        sc.cap = (size_t)4 * state().num_sms * 36864 * sizeof(float);
+    }
+    if (!sc.sub) {
+        // all (co chunk, ci chunk) enumerations for nco x nci in {1,2}x{1,2}, indexed by (nco-1)*2 + (nci-1)
+        int h[4][8] = {{0, 0, 0, 0, 0, 0, 0, 0}, {0, 0, 0, 0, 0, 1, 0, 0}, {0, 1, 0, 0, 0, 0, 0, 0}, {0, 0, 1, 1, 0, 1, 0, 1}};
+        DDPM_CUDA(cudaMalloc(&sc.sub, sizeof h));
+        DDPM_CUDA(cudaMemcpy(sc.sub, h, sizeof h, cudaMemcpyHostToDevice));
+    }
+    const int cfg = (nco - 1) * 2 + (nci - 1);
+    static const int hsub[4][8] = {{0, 0, 0, 0, 0, 0, 0, 0}, {0, 0, 0, 0, 0, 1, 0, 0}, {0, 1, 0, 0, 0, 0, 0, 0}, {0, 0, 1, 1, 0, 1, 0, 1}};
+    WgParams p{};
+    p.partial = sc.partial; p.num_kblocks = num_kblocks; p.guard = g.guard;
+    for (int y = 0; y < 4; ++y) { p.dy_chunk[y] = hsub[cfg][y]; p.x_chunk[y] = hsub[cfg][4 + y]; }
+    const uint64_t rows = (uint64_t)g.alloc_positions();
+    constexpr int RX = ((WG_KB + 2 + 7) / 8) * 8;
+    const int RDY = ((WG_KB + 2 * g.Wp + 7) / 8) * 8;
+    CUtensorMap mdy = make_map_2d<TG>(dy - (size_t)g.guard * Cout, rows, Cout, RDY);
+    CUtensorMap mx = make_map_2d<TA>(x - (size_t)g.guard * Cx, rows, Cx, RX);
+    if (g.Wp == 34) launch_wgrad<34, TG, TA>(st, mdy, mx, p, ctas_x, n_sub);
+    else launch_wgrad<18, TG, TA>(st, mdy, mx, p, ctas_x, n_sub);
+    const int total = n_sub * 36864;
+    wgrad_reduce_kernel<<<cdiv(total, 256), 256, 0, st>>>(sc.partial, ctas_x, n_sub, sc.sub + cfg * 8, sc.sub + cfg * 8 + 4,
+                                                          Cin_total, ci_off, alpha, dW);
+    DDPM_LAUNCH_CHECK();
+    return true;
+    }
 }
 
 }  // namespace tc

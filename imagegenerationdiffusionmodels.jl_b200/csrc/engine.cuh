@@ -162,6 +162,11 @@ struct Engine {
     // parameters
     float *P = nullptr, *G = nullptr, *M1 = nullptr, *M2 = nullptr;
     float eta = 1e-4f, b1 = 0.9f, b2 = 0.999f, aeps = 1e-8f, bt1 = 0.9f, bt2 = 0.999f;
+    // Static loss scale of the 16-bit gradient tensors: d(loss)/d(eps_hat) is multiplied by
+    // S = B_global*H*W/8 (so it is (eps_hat-eps)/4, O(1)) and every FP32 gradient written to the arena is
+    // multiplied by 1/S.  Powers of two when B is: exact.  Keeps FP16 gradients ~3 decades below overflow
+    // and the bulk above the subnormal range (measured ranges in DESIGN.md).  1 in FP32 mode.
+    float grad_scale(int B) const { return prec == 0 ? 1.f : (float)B * (float)world * (float)HW / 8.f; }
 
     // packed weights
     void* Wf[NUM_CONV + 1] = {};   // [cout][9][cin]  (TA)  -- L1 unused
@@ -232,7 +237,7 @@ struct Engine {
     template <typename TA, typename TG> void forward_t(ActSet& s, const float* x_dev, const int* ts_dev, int t_fixed, Mode mode, bool update_running);
     void forward(ActSet& s, const float* x_dev, const int* ts_dev, int t_fixed, Mode mode, bool update_running);
     template <typename TA, typename TG> void final_conv_t(ActSet& s, float* eps_hat_dev);
-    template <typename TA, typename TG> void backward_t(ActSet& s, const float* xt_dev, const int* ts_dev, const float* deps_dev, float inv_world);
+    template <typename TA, typename TG> void backward_t(ActSet& s, const float* xt_dev, const int* ts_dev, const float* deps_dev, float alpha);
     void allreduce_sums(double* local, double* global, int n);
 
     void train_core(int B, bool device_inputs, bool update, float* loss_out_host);
@@ -245,7 +250,7 @@ struct Engine {
 #define DDPM_DISPATCH(prec, ...)                                                         \
     do {                                                                                 \
         if ((prec) == 0) { using TA = float; using TG = float; __VA_ARGS__; }            \
-        else if ((prec) == 1) { using TA = __half; using TG = __nv_bfloat16; __VA_ARGS__; } \
+        else if ((prec) == 1) { using TA = __half; using TG = __half; __VA_ARGS__; }     \
         else { using TA = __nv_bfloat16; using TG = __nv_bfloat16; __VA_ARGS__; }        \
     } while (0)
 
@@ -700,10 +705,11 @@ void Engine::backward_t(ActSet& s, const float* xt_dev, const int* ts_dev, const
             allreduce_sums(lsum(l), gsum(l), 2 * c.cout);
             m *= world;
         }
-        bn_bwd_means_kernel<<<1, 128, 0, stream>>>(lsum(l), gsum(l), m, c.cout, bw_mg[l], bw_mgx[l], garr(c.bn), garr(c.bn + 1));
+        bn_bwd_means_kernel<<<1, 128, 0, stream>>>(lsum(l), gsum(l), m, c.cout, bw_mg[l], bw_mgx[l], garr(c.bn), garr(c.bn + 1),
+                                                   alpha);
         bn_bwd_kernel<TA, TG, 2><<<blocks, 256, 0, stream>>>(s.y[l].cview<TA>(), da, dy.view<TG>(), g, c.cout, tr_scale[l],
                                                              tr_shift[l], tr_mean[l], tr_istd[l], bw_mg[l], bw_mgx[l], lsum(l));
-        f64_to_f32_kernel<<<1, 128, 0, stream>>>(lsum(l) + 2 * c.cout, garr(c.b), c.cout, 1.0);
+        f64_to_f32_kernel<<<1, 128, 0, stream>>>(lsum(l) + 2 * c.cout, garr(c.b), c.cout, (double)alpha);
         DDPM_LAUNCH_CHECK();
         cnt_launches += 4;
     };
@@ -713,11 +719,11 @@ void Engine::backward_t(ActSet& s, const float* xt_dev, const int* ts_dev, const
         const Geo& g = dy.g;
         bool done = false;
         if (use_tc())
-            done = tc::wgrad3x3<TG, TA>(stream, dy.pos0<TG>(), c.cout, x.pos0<TA>(), x.C, g, garr(c.w), c.cin, ci_off);
+            done = tc::wgrad3x3<TG, TA>(stream, dy.pos0<TG>(), c.cout, x.pos0<TA>(), x.C, g, garr(c.w), c.cin, ci_off, alpha);
         if (!done) {
             MapConv3 mapB{g.Wp, -(long long)g.guard, g.npos + g.guard};
             launch_wgrad_simt<TG, TA>(stream, dy.cview<TG>(), x.cview<TA>(), g.npos, 9, c.cout, x.C, MapId{g.npos}, mapB,
-                                      IdxConv3{c.cin, ci_off}, 1.f, garr(c.w));
+                                      IdxConv3{c.cin, ci_off}, alpha, garr(c.w));
         }
         cnt_launches += 1;
     };
@@ -730,8 +736,8 @@ void Engine::backward_t(ActSet& s, const float* xt_dev, const int* ts_dev, const
         long long work = (long long)N * HW * 8;
         final_bwd_kernel<TA, TG><<<cdiv(work, 256), 256, 0, stream>>>(s.a[10].cview<TA>(), s.g32a.view<TG>(), s.a[10].g,
                                                                       arr(kFinalW), deps_dev, misc_sums + 8);
-        f64_to_f32_kernel<<<1, 128, 0, stream>>>(misc_sums + 8, garr(kFinalW), 64, 1.0);
-        f64_to_f32_kernel<<<1, 32, 0, stream>>>(misc_sums + 72, garr(kFinalB), 1, 1.0);
+        f64_to_f32_kernel<<<1, 128, 0, stream>>>(misc_sums + 8, garr(kFinalW), 64, (double)alpha);
+        f64_to_f32_kernel<<<1, 32, 0, stream>>>(misc_sums + 72, garr(kFinalB), 1, (double)alpha);
         DDPM_LAUNCH_CHECK();
         cnt_launches += 3;
     }
@@ -755,10 +761,10 @@ void Engine::backward_t(ActSet& s, const float* xt_dev, const int* ts_dev, const
         const Geo& go = s.u.g;
         long long pixels = (long long)N * HW;
         channel_sum_kernel<TG><<<cdiv(pixels, BNB_PIX_PER_BLOCK), 256, 0, stream>>>(s.g32a.cview<TG>(), go, 64, misc_sums + 128);
-        f64_to_f32_kernel<<<1, 128, 0, stream>>>(misc_sums + 128, garr(kUpB), 64, 1.0);
+        f64_to_f32_kernel<<<1, 128, 0, stream>>>(misc_sums + 128, garr(kUpB), 64, (double)alpha);
         // dW[a,b,co,ci] = sum_in du[outpos(in,q)][co] * a6[in][ci]
         launch_wgrad_simt<TG, TA>(stream, s.g32a.cview<TG>(), s.a[6].cview<TA>(), gi.npos, 4, 64, 128, MapUp2{gi, go},
-                                  MapValid{gi}, IdxUp2{64}, 1.f, garr(kUpW));
+                                  MapValid{gi}, IdxUp2{64}, alpha, garr(kUpW));
         // da6[in][ci] = sum_{q,co} du[outpos(in,q)][co] * Wtd[ci][q*64+co]
         EpiConv<TG> epi{s.g16a.view<TG>(), gi, nullptr, nullptr, 0, nullptr};
         launch_igemm_simt<TG, TG>(stream, s.g32a.cview<TG>(), 64, View<const TG>{nullptr, 0}, 0, (const TG*)Wtd, 128, 4,
@@ -803,10 +809,10 @@ void Engine::backward_t(ActSet& s, const float* xt_dev, const int* ts_dev, const
         d_Tw.ensure((size_t)N * 576 * 4); d_Ccls.ensure((size_t)N * 576 * 4); d_S.ensure((size_t)N * 576 * 4);
         l1_bwd_kernel<TG><<<N, 256, 0, stream>>>(s.g32b.cview<TG>(), s.g32b.g, xt_dev, d_Tw.as<float>(), d_Ccls.as<float>());
         l1_tap_sums_kernel<<<cdiv((long long)N * 576, 256), 256, 0, stream>>>(d_Ccls.as<float>(), d_S.as<float>(), N);
-        l1_wimg_grad_kernel<<<576, 256, 0, stream>>>(d_Tw.as<float>(), N, 1.f, 129, garr(0));
+        l1_wimg_grad_kernel<<<576, 256, 0, stream>>>(d_Tw.as<float>(), N, alpha, 129, garr(0));
         View<const float> Sv{d_S.as<float>(), 576}, pev{d_pe, D};
         launch_wgrad_simt<float, float>(stream, Sv, pev, (long long)N, 1, 576, D, MapId{(long long)N}, MapTs{ts_dev, (long long)N},
-                                        IdxEmb{129, 64}, 1.f, garr(0));
+                                        IdxEmb{129, 64}, alpha, garr(0));
         DDPM_LAUNCH_CHECK();
         cnt_launches += 4;
     }
@@ -818,7 +824,6 @@ void Engine::backward_t(ActSet& s, const float* xt_dev, const int* ts_dev, const
         DDPM_CUDA(cudaEventRecord(ev_comm_done, comm_stream));
         DDPM_CUDA(cudaStreamWaitEvent(stream, ev_comm_done, 0));
     }
-    (void)alpha;
 }
 
 // ------------------------------------------------------------------------------------ one training iteration
@@ -839,11 +844,12 @@ inline void Engine::train_core(int B, bool gather, bool update, float* loss_out_
     DDPM_CUDA(cudaMemsetAsync(misc_sums, 0, sizeof(double), stream));
     // loss = mean over the GLOBAL batch; every rank contributes its local sum / (B*world*HW)
     float inv_count = 1.f / ((float)B * (float)world * (float)HW);
-    mse_kernel<<<cdiv(n4, 256), 256, 0, stream>>>(s.eps_hat.as<float>(), d_eps.as<float>(), n4, inv_count, misc_sums,
+    const float gs = grad_scale(B);
+    mse_kernel<<<cdiv(n4, 256), 256, 0, stream>>>(s.eps_hat.as<float>(), d_eps.as<float>(), n4, inv_count * gs, misc_sums,
                                                   d_deps.as<float>());
     DDPM_LAUNCH_CHECK();
     cnt_launches += 1;
-    DDPM_DISPATCH(prec, (backward_t<TA, TG>(s, d_xt.as<float>(), d_ts.as<int>(), d_deps.as<float>(), 1.f)));
+    DDPM_DISPATCH(prec, (backward_t<TA, TG>(s, d_xt.as<float>(), d_ts.as<int>(), d_deps.as<float>(), 1.f / gs)));
     if (update) {
         adam_kernel<<<cdiv(n_params, 256), 256, 0, stream>>>(P, G, M1, M2, n_params, eta, b1, b2, aeps, bt1, bt2);
         DDPM_LAUNCH_CHECK();
@@ -859,7 +865,7 @@ inline void Engine::train_core(int B, bool gather, bool update, float* loss_out_
         }
         DDPM_CUDA(cudaMemcpyAsync(&ls, misc_sums, sizeof(double), cudaMemcpyDeviceToHost, stream));
         DDPM_CUDA(cudaStreamSynchronize(stream));
-        *loss_out_host = (float)(ls * (double)inv_count);
+        *loss_out_host = (float)(ls * (double)inv_count);   // mse_kernel accumulates the UNscaled squared error
     }
 }
 

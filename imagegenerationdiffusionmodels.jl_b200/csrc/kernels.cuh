@@ -403,7 +403,7 @@ final_conv_kernel(View<const TA> a, Geo g, const float* __restrict__ wf, const f
 // Flux.Losses.mse = mean(abs2.(pred .- target)) (train_brain.jl:240).  Warp-shuffle + block
 // reduction, one Float64 atomic per block; also emits d(loss)/d(pred) = 2(pred-target)*inv_count.
 __global__ void __launch_bounds__(256)
-mse_kernel(const float* __restrict__ pred, const float* __restrict__ target, long long n4, float inv_count,
+mse_kernel(const float* __restrict__ pred, const float* __restrict__ target, long long n4, float dscale /*inv_count * loss scale*/,
            double* __restrict__ loss_sum, float* __restrict__ dpred) {
     __shared__ float wsum[8];
     long long i = (long long)blockIdx.x * 256 + threadIdx.x;
@@ -414,7 +414,7 @@ mse_kernel(const float* __restrict__ pred, const float* __restrict__ target, lon
         float4 d = make_float4(p.x - t.x, p.y - t.y, p.z - t.z, p.w - t.w);
         s = d.x * d.x + d.y * d.y + d.z * d.z + d.w * d.w;
         if (dpred) {
-            float k = 2.f * inv_count;
+            float k = 2.f * dscale;
             *reinterpret_cast<float4*>(dpred + 4 * i) = make_float4(k * d.x, k * d.y, k * d.z, k * d.w);
         }
     }
@@ -534,11 +534,11 @@ bn_bwd_kernel(View<const TA> y, View<const TG> da, View<TG> dy, Geo g, int C, co
 // after pass 1: local sums -> gradient arena (d beta, d gamma); global sums -> means for pass 2
 __global__ void bn_bwd_means_kernel(const double* __restrict__ local_sums, const double* __restrict__ global_sums,
                                     double count, int C, float* __restrict__ mg, float* __restrict__ mgx,
-                                    float* __restrict__ dbeta, float* __restrict__ dgamma) {
+                                    float* __restrict__ dbeta, float* __restrict__ dgamma, float alpha) {
     int c = blockIdx.x * blockDim.x + threadIdx.x;
     if (c >= C) return;
-    dbeta[c] = (float)local_sums[c];
-    dgamma[c] = (float)local_sums[C + c];
+    dbeta[c] = (float)((double)alpha * local_sums[c]);        // alpha = 1/loss-scale
+    dgamma[c] = (float)((double)alpha * local_sums[C + c]);
     mg[c] = (float)(global_sums[c] / count);
     mgx[c] = (float)(global_sums[C + c] / count);
 }

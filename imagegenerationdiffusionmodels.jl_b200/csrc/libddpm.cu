@@ -533,11 +533,10 @@ int ddpm_debug_fetch(ddpm_handle* h, const char* name, float* out, int64_t capac
     ActSet& s = *sp;
     DDPM_CHECK(s.N > 0, "no activations recorded yet");
     const Tensor* t = nullptr;
-    bool grad_type = false;
     if (k == "p1") t = &s.p1;
     else if (k == "u") t = &s.u;
-    else if (k == "g32a") { t = &s.g32a; grad_type = true; }
-    else if (k == "g32b") { t = &s.g32b; grad_type = true; }
+    else if (k == "g32a") { t = &s.g32a; }
+    else if (k == "g32b") { t = &s.g32b; }
     else if (k[0] == 'y') t = &s.y[std::atoi(k.c_str() + 1)];
     else if (k[0] == 'a') t = &s.a[std::atoi(k.c_str() + 1)];
     DDPM_CHECK(t && t->base, "unknown or unallocated tensor name");
@@ -556,7 +555,7 @@ int ddpm_debug_fetch(ddpm_handle* h, const char* name, float* out, int64_t capac
                     const unsigned char* src = host.data() + (p + c) * esz;
                     float v;
                     if (esz == 4) v = *reinterpret_cast<const float*>(src);
-                    else if (grad_type || e.prec == 2) v = __bfloat162float(*reinterpret_cast<const __nv_bfloat16*>(src));
+                    else if (e.prec == 2) v = __bfloat162float(*reinterpret_cast<const __nv_bfloat16*>(src));
                     else v = __half2float(*reinterpret_cast<const __half*>(src));
                     out[(((size_t)n * t->C + c) * g.H + hh) * g.W + ww] = v;
                 }

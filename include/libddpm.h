@@ -31,7 +31,7 @@ typedef struct ddpm_handle ddpm_handle;
 /* arithmetic mode of the convolution contractions */
 enum {
     DDPM_PREC_FP32 = 0, /* CUDA-core FP32 everywhere (parity/debug mode)                                   */
-    DDPM_PREC_FP16 = 1, /* tcgen05 kind::f16, FP16 activations+weights, BF16 gradients, FP32 accumulate     */
+    DDPM_PREC_FP16 = 1, /* tcgen05 kind::f16, FP16 activations+weights+gradients (loss-scaled), FP32 accum */
     DDPM_PREC_BF16 = 2  /* tcgen05 kind::f16, BF16 activations+weights+gradients, FP32 accumulate           */
 };
 
