@@ -616,6 +616,27 @@ bool up2(cudaStream_t st, const TA* a6, const TA* Wt, TA* u, const Geo& gi, cons
     }
 }
 
+// out[pos][N=128] = A[pos][K=256] * Wt[n][k]^T over the valid positions of g (ConvTranspose data gradient
+// on the pixel-un-shuffled gradient): the conv kernel with one tap and four 64-channel K chunks.
+template <typename T>
+bool gemm_rows(cudaStream_t st, const T* a, int K, const T* Wt, int Nout, T* out, const Geo& g) {
+    if (!available()) return false;
+    if constexpr (sizeof(T) != 2) {
+        return false;
+    } else {
+    if (K != 256 || Nout != 128) return false;
+    TcParams p{};
+    p.out = out; p.out_cs = Nout; p.g = g; p.g_out = g; p.shift = nullptr; p.relu = 0;
+    p.num_m_tiles = cdiv(g.npos, TC_BM);
+    p.chunk1_src1 = 0;
+    p.dbg = nullptr;
+    CUtensorMap a0 = make_map_2d<T>(a - (size_t)g.guard * K, (uint64_t)g.alloc_positions(), K, TC_BM);
+    CUtensorMap w = make_map_2d<T>(Wt, Nout, K, 128);
+    launch<1, 4, 128, 18, 0, 0, T, T>(st, a0, a0, w, a0, p, 1);
+    return true;
+    }
+}
+
 // =====================================================================================
 // Weight gradient of a 3x3 convolution on tensor cores.
 //   dWcc[co][ty,tx][ci] = sum_pos dy[pos][co] * x[pos + ty*Wp + tx][ci]      (halo rows of dy are zero)
@@ -776,6 +797,119 @@ __global__ void wgrad_reduce_kernel(const float* __restrict__ partial, int n_cta
     dW[idx] = alpha * s;
 }
 
+// Weight gradient of ConvTranspose((2,2), 128=>64, stride 2) on the un-shuffled gradient:
+//   dWt[q*64+co][ci] = sum_pos du4[pos][q*64+co] * a6[pos][ci]
+// Plain MN-major GEMM over coarse positions: M = 128 = two q blocks per MMA (second 64-row group = the next
+// 64-channel slab, LBO = slab size), N = 128 = both 64-channel slabs of a6; two MMAs cover q = 0..3.
+constexpr int WU_KB = 64;
+template <int STAGES, typename T>
+__global__ void __launch_bounds__(WG_THREADS, 1)
+wgrad_up2_tc_kernel(const __grid_constant__ CUtensorMap tmDu4, const __grid_constant__ CUtensorMap tmA6, float* partial,
+                    int num_kblocks, int guard) {
+    constexpr uint32_t SLAB = WU_KB * 128;                 // [64 positions][64 ch]
+    constexpr uint32_t STAGE_BYTES = 6 * SLAB;             // du4 chunks 0..3, a6 chunks 0..1
+    constexpr uint32_t IDESC = make_idesc_mn(IsBf16<T>::v, IsBf16<T>::v, 128, 128);
+    extern __shared__ uint8_t smem_raw[];
+    uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
+    const uint32_t s_base = smem_u32(smem);
+    const uint32_t s_bar = s_base + STAGES * STAGE_BYTES;
+    auto bar_full = [&](int s) { return s_bar + 8u * s; };
+    auto bar_empty = [&](int s) { return s_bar + 8u * (STAGES + s); };
+    const uint32_t bar_acc = s_bar + 8u * (2 * STAGES);
+    uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(smem + STAGES * STAGE_BYTES + 8 * (2 * STAGES + 1));
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    if (warp == 0 && lane == 0) {
+        prefetch_tmap(&tmDu4); prefetch_tmap(&tmA6);
+        for (int s = 0; s < STAGES; ++s) { mbar_init(bar_full(s), 1); mbar_init(bar_empty(s), 1); }
+        mbar_init(bar_acc, 1);
+        fence_barrier_init();
+    }
+    if (warp == 2) tmem_alloc<256>(smem_u32(tmem_slot));
+    tc_fence_before();
+    __syncthreads();
+    tc_fence_after();
+    const uint32_t tmem_base = *tmem_slot;
+    if (warp == 0) {
+        int stage = 0;
+        uint32_t phase = 0;
+        for (int kb = blockIdx.x; kb < num_kblocks; kb += gridDim.x) {
+            mbar_wait(bar_empty(stage), phase ^ 1);
+            if (elect_one()) {
+                const int k0 = kb * WU_KB + guard;
+                const uint32_t dst = s_base + stage * STAGE_BYTES;
+                mbar_expect_tx(bar_full(stage), STAGE_BYTES);
+                for (int c = 0; c < 4; ++c) tma_load_2d(dst + c * SLAB, &tmDu4, c * 64, k0, bar_full(stage));
+                for (int c = 0; c < 2; ++c) tma_load_2d(dst + (4 + c) * SLAB, &tmA6, c * 64, k0, bar_full(stage));
+            }
+            __syncwarp();
+            if (++stage == STAGES) { stage = 0; phase ^= 1; }
+        }
+    } else if (warp == 1) {
+        constexpr uint32_t DESC_HI = (1024u >> 4) | (1u << 14) | (2u << 29);
+        constexpr uint32_t LBO = SLAB >> 4;
+        int stage = 0;
+        uint32_t phase = 0, first = 1;
+        for (int kb = blockIdx.x; kb < num_kblocks; kb += gridDim.x) {
+            mbar_wait(bar_full(stage), phase);
+            tc_fence_after();
+            if (elect_one()) {
+                const uint32_t a0 = (((s_base + stage * STAGE_BYTES) & 0x3FFFFu) >> 4) | (LBO << 16);
+                const uint32_t b0 = (((s_base + stage * STAGE_BYTES + 4 * SLAB) & 0x3FFFFu) >> 4) | (LBO << 16);
+#pragma unroll
+                for (int ks = 0; ks < WU_KB / 16; ++ks) {
+                    const uint32_t acc = (first && ks == 0) ? 0u : 1u;
+                    umma_f16_lh(tmem_base, a0 + ((ks * 16 * 128) >> 4), b0 + ((ks * 16 * 128) >> 4), DESC_HI, IDESC, acc);
+                    umma_f16_lh(tmem_base + 128, a0 + ((2 * SLAB + ks * 16 * 128) >> 4), b0 + ((ks * 16 * 128) >> 4), DESC_HI,
+                                IDESC, acc);
+                }
+                umma_commit(bar_empty(stage));
+            }
+            __syncwarp();
+            first = 0;
+            if (++stage == STAGES) { stage = 0; phase ^= 1; }
+        }
+        if (elect_one()) umma_commit(bar_acc);
+        __syncwarp();
+    } else {
+        const int lane_grp = warp & 3;
+        const int l = lane_grp * 32 + lane;
+        float* dst = partial + (size_t)blockIdx.x * (256 * 128);
+        mbar_wait(bar_acc, 0);
+        tc_fence_after();
+#pragma unroll 1
+        for (int d = 0; d < 2; ++d) {
+            const int row = (2 * d + (l >> 6)) * 64 + (l & 63);      // q*64 + co
+#pragma unroll
+            for (int c0 = 0; c0 < 128; c0 += 16) {
+                uint32_t r[16];
+                tmem_ld16(tmem_base + ((uint32_t)(lane_grp * 32) << 16) + d * 128 + c0, r);
+                tmem_ld_wait();
+#pragma unroll
+                for (int j = 0; j < 16; j += 4)
+                    *reinterpret_cast<float4*>(dst + (size_t)row * 128 + c0 + j) =
+                        make_float4(__uint_as_float(r[j]), __uint_as_float(r[j + 1]), __uint_as_float(r[j + 2]), __uint_as_float(r[j + 3]));
+            }
+        }
+    }
+    tc_fence_before();
+    __syncthreads();
+    if (warp == 2) {
+        tc_fence_after();
+        tmem_dealloc<256>(tmem_base);
+    }
+}
+
+// arena (Flux ConvTranspose layout w[a,b,co,ci], a = 1-px, b = 1-py) = alpha * sum_cta partial[cta][q*64+co][ci]
+__global__ void wgrad_up2_reduce_kernel(const float* __restrict__ partial, int n_cta, float alpha, float* __restrict__ dW) {
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= 256 * 128) return;
+    float s = 0.f;
+    for (int c = 0; c < n_cta; ++c) s += partial[(size_t)c * (256 * 128) + i];
+    const int ci = i & 127, row = i >> 7, q = row >> 6, co = row & 63;
+    const int py = q >> 1, px = q & 1;
+    dW[(1 - px) + 2 * (1 - py) + 4 * co + 256 * ci] = alpha * s;
+}
+
 struct WgScratch {
     float* partial = nullptr;
     size_t cap = 0;
@@ -848,6 +982,41 @@ bool wgrad3x3(cudaStream_t st, const TG* dy, int Cout, const TA* x, int Cx, cons
     const int total = n_sub * 36864;
     wgrad_reduce_kernel<<<cdiv(total, 256), 256, 0, st>>>(sc.partial, ctas_x, n_sub, sc.sub + cfg * 8, sc.sub + cfg * 8 + 4,
                                                           Cin_total, ci_off, alpha, dW);
+    DDPM_LAUNCH_CHECK();
+    return true;
+    }
+}
+
+template <typename T>
+bool wgrad_up2(cudaStream_t st, const T* du4, const T* a6, const Geo& g, float* dW, float alpha) {
+    if (!available()) return false;
+    if constexpr (sizeof(T) != 2) {
+        return false;
+    } else {
+    const int num_kblocks = cdiv(g.npos, WU_KB);
+    int ctas = state().num_sms;
+    if (ctas > num_kblocks) ctas = num_kblocks;
+    WgScratch& sc = wg_scratch();
+    const size_t need = (size_t)4 * state().num_sms * 36864 * sizeof(float);   // shared with wgrad3x3 (>= ctas*256*128)
+    if (sc.cap < need) {
+        DDPM_CUDA(cudaStreamSynchronize(st));
+        if (sc.partial) cudaFree(sc.partial);
+        DDPM_CUDA(cudaMalloc(&sc.partial, need));
+        sc.cap = need;
+    }
+    constexpr int STAGES = 4;
+    constexpr size_t smem = 1024 + (size_t)STAGES * 6 * WU_KB * 128 + 512;
+    auto kern = wgrad_up2_tc_kernel<STAGES, T>;
+    static bool attr_set = false;
+    if (!attr_set) {
+        DDPM_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        attr_set = true;
+    }
+    const uint64_t rows = (uint64_t)g.alloc_positions();
+    CUtensorMap m4 = make_map_2d<T>(du4 - (size_t)g.guard * 256, rows, 256, WU_KB);
+    CUtensorMap m6 = make_map_2d<T>(a6 - (size_t)g.guard * 128, rows, 128, WU_KB);
+    kern<<<ctas, WG_THREADS, smem, st>>>(m4, m6, sc.partial, num_kblocks, g.guard);
+    wgrad_up2_reduce_kernel<<<cdiv(256 * 128, 256), 256, 0, st>>>(sc.partial, ctas, alpha, dW);
     DDPM_LAUNCH_CHECK();
     return true;
     }

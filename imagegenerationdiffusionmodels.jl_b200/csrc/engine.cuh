@@ -128,7 +128,7 @@ struct ActSet {
     bool training = false;
     Tensor y[NUM_CONV + 1], a[NUM_CONV + 1], p1, u;
     // gradient scratch (training only)
-    Tensor g32a, g32b, gcat, g16a, g16b, gp1;
+    Tensor g32a, g32b, gcat, g16a, g16b, gp1, gdu4;
     std::vector<void*> owned;
     DevBuf x, eps_hat;  // boundary-layout Float32 [N][H*W]
     DevBuf z;           // host-supplied sampler noise [steps][N][H*W]
@@ -428,6 +428,7 @@ inline void Engine::build_set(ActSet& s, int N, bool training) {
         alloc_tensor(s, s.g16a, N, 16, 128, eg);
         alloc_tensor(s, s.g16b, N, 16, 128, eg);
         alloc_tensor(s, s.gp1, N, 16, 64, eg);
+        alloc_tensor(s, s.gdu4, N, 16, 256, eg);
     } else {
         Tensor i32[4], i16[2];
         for (auto& t : i32) alloc_tensor(s, t, N, 32, 64, ea);
@@ -733,8 +734,8 @@ void Engine::backward_t(ActSet& s, const float* xt_dev, const int* ts_dev, const
 
     // ---- final 1x1 conv
     {
-        long long work = (long long)N * HW * 8;
-        final_bwd_kernel<TA, TG><<<cdiv(work, 256), 256, 0, stream>>>(s.a[10].cview<TA>(), s.g32a.view<TG>(), s.a[10].g,
+        long long pixels = (long long)N * HW;
+        final_bwd_kernel<TA, TG><<<cdiv(pixels, FINAL_BWD_PIX_PER_BLOCK), 256, 0, stream>>>(s.a[10].cview<TA>(), s.g32a.view<TG>(), s.a[10].g,
                                                                       arr(kFinalW), deps_dev, misc_sums + 8);
         f64_to_f32_kernel<<<1, 128, 0, stream>>>(misc_sums + 8, garr(kFinalW), 64, (double)alpha);
         f64_to_f32_kernel<<<1, 32, 0, stream>>>(misc_sums + 72, garr(kFinalB), 1, (double)alpha);
@@ -762,13 +763,28 @@ void Engine::backward_t(ActSet& s, const float* xt_dev, const int* ts_dev, const
         long long pixels = (long long)N * HW;
         channel_sum_kernel<TG><<<cdiv(pixels, BNB_PIX_PER_BLOCK), 256, 0, stream>>>(s.g32a.cview<TG>(), go, 64, misc_sums + 128);
         f64_to_f32_kernel<<<1, 128, 0, stream>>>(misc_sums + 128, garr(kUpB), 64, (double)alpha);
-        // dW[a,b,co,ci] = sum_in du[outpos(in,q)][co] * a6[in][ci]
-        launch_wgrad_simt<TG, TA>(stream, s.g32a.cview<TG>(), s.a[6].cview<TA>(), gi.npos, 4, 64, 128, MapUp2{gi, go},
-                                  MapValid{gi}, IdxUp2{64}, alpha, garr(kUpW));
         // da6[in][ci] = sum_{q,co} du[outpos(in,q)][co] * Wtd[ci][q*64+co]
-        EpiConv<TG> epi{s.g16a.view<TG>(), gi, nullptr, nullptr, 0, nullptr};
-        launch_igemm_simt<TG, TG>(stream, s.g32a.cview<TG>(), 64, View<const TG>{nullptr, 0}, 0, (const TG*)Wtd, 128, 4,
-                                  gi.npos, MapUp2{gi, go}, epi);
+        bool done = false;
+        if (use_tc()) {
+            long long work = (long long)N * 16 * 16 * 4 * 8;
+            unshuffle2_kernel<TG><<<cdiv(work, 256), 256, 0, stream>>>(s.g32a.cview<TG>(), s.gdu4.view<TG>(), go, gi, 64);
+            done = tc::gemm_rows<TG>(stream, s.gdu4.pos0<TG>(), 256, (const TG*)Wtd, 128, s.g16a.pos0<TG>(), gi);
+            cnt_launches += 1;
+        }
+        if (!done) {
+            EpiConv<TG> epi{s.g16a.view<TG>(), gi, nullptr, nullptr, 0, nullptr};
+            launch_igemm_simt<TG, TG>(stream, s.g32a.cview<TG>(), 64, View<const TG>{nullptr, 0}, 0, (const TG*)Wtd, 128, 4,
+                                      gi.npos, MapUp2{gi, go}, epi);
+        }
+        // dW[a,b,co,ci] = sum_in du[outpos(in,q)][co] * a6[in][ci]
+        bool wdone = false;
+        if (done) {
+            if constexpr (std::is_same<TG, TA>::value)
+                wdone = tc::wgrad_up2<TG>(stream, s.gdu4.pos0<TG>(), s.a[6].pos0<TA>(), gi, garr(kUpW), alpha);
+        }
+        if (!wdone)
+            launch_wgrad_simt<TG, TA>(stream, s.g32a.cview<TG>(), s.a[6].cview<TA>(), gi.npos, 4, 64, 128, MapUp2{gi, go},
+                                      MapValid{gi}, IdxUp2{64}, alpha, garr(kUpW));
         DDPM_LAUNCH_CHECK();
         cnt_launches += 4;
     }

@@ -428,6 +428,8 @@ mse_kernel(const float* __restrict__ pred, const float* __restrict__ target, lon
     }
 }
 
+constexpr int FINAL_BWD_PIX_PER_BLOCK = 512;
+
 // ------------------------------------------------------------------------------------ backward: final conv
 // da[p][c] = deps[p]*wf[c];  dwf[c] = sum_p deps[p]*a[p][c];  dbf = sum_p deps[p]   (sums -> Float64)
 template <typename TA, typename TG>
@@ -438,25 +440,28 @@ final_bwd_kernel(View<const TA> a, View<TG> da, Geo g, const float* __restrict__
     const int t = threadIdx.x;
     if (t < 65) red[t] = 0.f;
     __syncthreads();
-    long long idx = (long long)blockIdx.x * 256 + t;
-    long long pix = idx >> 3;
-    int c0 = (int)(idx & 7) * 8;
+    const int c0 = (t & 7) * 8, pl = t >> 3;          // 8 lanes per pixel, 32 pixels per pass
     const int HW = g.H * g.W;
-    if (pix < (long long)g.N * HW) {
-        int n = (int)(pix / HW);
-        int rem = (int)(pix - (long long)n * HW);
-        long long p = g.pos(n, rem / g.W, rem % g.W);
-        float d = deps[pix];
+    const long long total = (long long)g.N * HW;
+    const long long pbeg = (long long)blockIdx.x * FINAL_BWD_PIX_PER_BLOCK;
+    float w8[8], acc[8], accb = 0.f;
+#pragma unroll
+    for (int j = 0; j < 8; ++j) { w8[j] = wf[c0 + j]; acc[j] = 0.f; }
+    for (long long pix = pbeg + pl; pix < pbeg + FINAL_BWD_PIX_PER_BLOCK && pix < total; pix += 32) {
+        const int n = (int)(pix / HW);
+        const int rem = (int)(pix - (long long)n * HW);
+        const long long p = g.pos(n, rem / g.W, rem % g.W);
+        const float d = deps[pix];
         float v[8], o[8];
         V8<TA>::ld(a.p + p * a.cs + c0, v);
 #pragma unroll
-        for (int j = 0; j < 8; ++j) {
-            o[j] = d * wf[c0 + j];
-            atomicAdd(&red[c0 + j], d * v[j]);
-        }
+        for (int j = 0; j < 8; ++j) { o[j] = d * w8[j]; acc[j] = fmaf(d, v[j], acc[j]); }
         V8<TG>::st(da.p + p * da.cs + c0, o);
-        if (c0 == 0) atomicAdd(&red[64], d);
+        if (c0 == 0) accb += d;
     }
+#pragma unroll
+    for (int j = 0; j < 8; ++j) atomicAdd(&red[c0 + j], acc[j]);
+    if (c0 == 0) atomicAdd(&red[64], accb);
     __syncthreads();
     if (t < 65) atomicAdd(&sums[t], (double)red[t]);
 }
@@ -604,18 +609,22 @@ l1_bwd_kernel(View<const TG> dy, Geo g, const float* __restrict__ x, float* __re
     const int H = g.H, W = g.W;
     const int c0 = (t & 7) * 8, pl = t >> 3;
     const float* xi = x + (long long)n * H * W;
-    float tw[9][8];
+    float tw[9][8], cl[9][8];
 #pragma unroll
     for (int a = 0; a < 9; ++a)
 #pragma unroll
-        for (int j = 0; j < 8; ++j) tw[a][j] = 0.f;
+        for (int j = 0; j < 8; ++j) { tw[a][j] = 0.f; cl[a][j] = 0.f; }
     for (int pix = pl; pix < H * W; pix += 32) {
         int h = pix / W, w = pix - h * W;
         float d[8];
         V8<TG>::ld(dy.p + g.pos(n, h, w) * dy.cs + c0, d);
         int cls = (h == 0 ? 0 : (h == H - 1 ? 2 : 1)) * 3 + (w == 0 ? 0 : (w == W - 1 ? 2 : 1));
 #pragma unroll
-        for (int j = 0; j < 8; ++j) atomicAdd(&cl_s[cls * 64 + c0 + j], d[j]);
+        for (int a = 0; a < 9; ++a) {
+            const float m = (a == cls) ? 1.f : 0.f;
+#pragma unroll
+            for (int j = 0; j < 8; ++j) cl[a][j] = fmaf(m, d[j], cl[a][j]);
+        }
 #pragma unroll
         for (int tap = 0; tap < 9; ++tap) {
             int hh = h + tap / 3 - 1, ww = w + tap % 3 - 1;
@@ -627,7 +636,10 @@ l1_bwd_kernel(View<const TG> dy, Geo g, const float* __restrict__ x, float* __re
 #pragma unroll
     for (int tap = 0; tap < 9; ++tap)
 #pragma unroll
-        for (int j = 0; j < 8; ++j) atomicAdd(&tw_s[tap * 64 + c0 + j], tw[tap][j]);
+        for (int j = 0; j < 8; ++j) {
+            atomicAdd(&tw_s[tap * 64 + c0 + j], tw[tap][j]);
+            atomicAdd(&cl_s[tap * 64 + c0 + j], cl[tap][j]);
+        }
     __syncthreads();
     for (int i = t; i < 576; i += 256) {
         Tw[(long long)n * 576 + i] = tw_s[i];
@@ -735,6 +747,26 @@ bn_stats_kernel(View<const TA> y, Geo g, int C, double* __restrict__ sums) {
     for (int j = 0; j < 8; ++j) { atomicAdd(&red[0][c0 + j], r[j]); atomicAdd(&red[1][c0 + j], q[j]); }
     __syncthreads();
     if (t < C) { atomicAdd(&sums[t], (double)red[0][t]); atomicAdd(&sums[C + t], (double)red[1][t]); }
+}
+
+// ConvTranspose((2,2), stride 2) backward operand: du4[coarse pos][q*C + c] = du[fine pos(2i+py, 2j+px)][c],
+// q = py*2+px.  With it both the data gradient (K = 4C GEMM) and the weight gradient are plain GEMMs
+// over coarse positions that the tensor-core kernels can TMA-load.
+template <typename TG>
+__global__ void __launch_bounds__(256)
+unshuffle2_kernel(View<const TG> du, View<TG> du4, Geo gf, Geo gc, int C) {
+    const int groups = C / 8;
+    long long idx = (long long)blockIdx.x * 256 + threadIdx.x;
+    long long pix = idx / (4 * groups);
+    int rem4 = (int)(idx - pix * 4 * groups);
+    int q = rem4 / groups, c0 = (rem4 - q * groups) * 8;
+    if (pix >= (long long)gc.N * gc.H * gc.W) return;
+    int n = (int)(pix / (gc.H * gc.W));
+    int rem = (int)(pix - (long long)n * gc.H * gc.W);
+    int i = rem / gc.W, j = rem % gc.W;
+    float v[8];
+    V8<TG>::ld(du.p + gf.pos(n, 2 * i + (q >> 1), 2 * j + (q & 1)) * du.cs + c0, v);
+    V8<TG>::st(du4.p + gc.pos(n, i, j) * du4.cs + q * C + c0, v);
 }
 
 // ------------------------------------------------------------------------------------ Adam (Optimisers.jl 0.4.6)
