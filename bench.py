@@ -31,6 +31,9 @@ T_STEPS = 500
 FLOP_PER_EVAL_FOLDED = 735.31e6     # SURVEY.md Appendix A with the embedding fold (what the kernels execute)
 FLOP_PER_EVAL_REFERENCE = 886.31e6  # the reference's 129-channel formulation
 FLOP_PER_TRAIN_IMG = 2204.76e6      # fwd + dgrad + wgrad with the fold
+# dram__bytes_read.sum + dram__bytes_write.sum of ONE conv3x3 64->64 @32x32 launch from `ncu --set full`
+# (profiles/conv_l2_r1_ncu.txt), keyed by images per launch
+NCU_TRAFFIC_CONV_L2 = {512: 98.6e6}
 
 
 def load_peaks():
@@ -191,15 +194,33 @@ def run_ours(args):
     model = api.SimpleUNet.load()
     h.set_weights(model.arrays)
     h.set_option("sample_chunk", args.chunk)
-    N = args.images
     t_start = args.t_start
     evals = t_start - 1
 
     def first_index(step_no):
-        return (step_no * world + rank) * N
+        return (step_no * world + rank) * args.images
 
-    out = {}
-    if args.workload == "sample":
+    common = (h, td, rank, world, local, peaks)
+    if args.workload in ("sample", "both"):
+        line = run_workload(args, "sample", *common, args.images, t_start, evals, first_index, api, capi, tables)
+    else:
+        line = run_workload(args, "train", *common, args.train_images, t_start, evals, first_index, api, capi, tables)
+    if args.workload == "both":
+        # secondary figure of BASELINE.json's metric: training images/s on the same GPUs, same JSON line
+        tl = run_workload(args, "train", *common, args.train_images, t_start, evals, first_index, api, capi, tables)
+        if rank == 0:
+            line["train"] = {k: tl[k] for k in ("metric", "value", "unit", "ms_per_step", "e2e", "gpu_launches", "config")}
+            line["train"]["tflops"] = tl["roofline"]["whole_step_tflops"]
+            line["train"]["frac_of_sustained_peak"] = tl["roofline"]["whole_step_frac_of_sustained"]
+    if rank == 0:
+        print(json.dumps(line), flush=True)
+    if td is not None:
+        td.barrier()
+        td.destroy_process_group()
+
+
+def run_workload(args, workload, h, td, rank, world, local, peaks, N, t_start, evals, first_index, api, capi, tables):
+    if workload == "sample":
         # ---- device-resident timing (value)
         for w in range(args.warmup):
             h.sample_device(N, seed=args.seed, first_index=first_index(w), t_start=t_start)
@@ -235,7 +256,7 @@ def run_ours(args):
         e2e = {"value": e2e_steps * N * world / e2e_s, "unit": "img/s", "h2d_bytes_per_step": int(xin.nbytes),
                "d2h_bytes_per_step": int(oout.nbytes), "steps": e2e_steps}
         metric = "sampled img/s (500-step DDPM, 32x32)"
-        workload = (f"generate_image: {evals}-evaluation reverse loop (t={t_start}..2), 32x32, trained_model.bson weights, "
+        workload_desc = (f"generate_image: {evals}-evaluation reverse loop (t={t_start}..2), 32x32, trained_model.bson weights, "
                     f"device Philox noise; BASELINE config 4 (65,536 images) == 16 steps of 4096")
         flop_per_unit = FLOP_PER_EVAL_FOLDED * evals
     else:
@@ -284,20 +305,20 @@ def run_ours(args):
         e2e = {"value": e2e_steps * N * world / e2e_s, "unit": "img/s",
                "h2d_bytes_per_step": int(2 * N * 4096 + 4 * N), "d2h_bytes_per_step": 4, "steps": e2e_steps}
         metric = "train img/s (U-Net fwd+bwd+Adam, 32x32)"
-        workload = (f"train_step: q_sample + U-Net fwd/bwd + MSE + Adam, 32x32 synthetic U(-1,1) data, per-GPU batch {N}, "
+        workload_desc = (f"train_step: q_sample + U-Net fwd/bwd + MSE + Adam, 32x32 synthetic U(-1,1) data, per-GPU batch {N}, "
                     f"global batch {N * world}, sync_bn={args.sync_bn}")
         flop_per_unit = FLOP_PER_TRAIN_IMG
 
     if rank != 0:
-        if td is not None:
-            td.destroy_process_group()
-        return
+        return None
 
     # ---- roofline of the dominant kernel: the 64->64 3x3 convolution at 32x32 (5 of the 10 convs,
     #      51% of the U-Net FLOPs), timed alone with CUDA events on the engine's stream
     chunk = min(args.chunk, N)
     kern = {}
     for name in ("conv_l2", "conv_l4", "conv_l9", "conv_l3", "reverse_update", "qsample", "mse", "adam"):
+        if workload == "train" and args.workload == "both":
+            break   # already measured in the sampling pass of this run
         try:
             kms, by, fl = h.time_kernel(name, chunk, 20)
             kern[name] = {"ms": kms, "tflops": fl / kms / 1e9 if fl else None, "gbs": by / kms / 1e6 if by else None}
@@ -311,7 +332,7 @@ def run_ours(args):
     else:
         peak_note = "kind::f16 tensor peak (cuBLAS bf16 burst)"
     roofline = {"bound": "tensor", "kernel": "conv3x3 64->64 @32x32 (layer 2)", "achieved": dom.get("tflops"),
-                "peak": peak_tf, "unit": "TFLOP/s", "frac": (dom.get("tflops") or 0.0) / peak_tf, "traffic": None,
+                "peak": peak_tf, "unit": "TFLOP/s", "frac": (dom.get("tflops") or 0.0) / peak_tf, "traffic": NCU_TRAFFIC_CONV_L2.get(chunk),
                 "peak_source": peaks["source"], "note": peak_note,
                 "whole_step_tflops": value * flop_per_unit / 1e12 / world,
                 "whole_step_frac_of_sustained": value * flop_per_unit / 1e12 / world / peaks["bf16_tflops_sustained"]}
@@ -321,7 +342,7 @@ def run_ours(args):
 
     # ---- CPU baseline on the box's host cores, bounded sample
     cpu = None
-    if world == 1 and not args.no_cpu:
+    if world == 1 and not args.no_cpu and workload == "sample":
         v, dt, threads = cpu_reference_sampling(args.ref_images, args.ref_steps)
         cpu = {"value": v, "unit": "img/s", "cores": threads, "kind": "port",
                "sample": f"{args.ref_images} images x {args.ref_steps} of 499 reverse steps ({dt:.1f} s), extrapolated to 499; "
@@ -331,38 +352,35 @@ def run_ours(args):
         "metric": metric, "value": value, "unit": "img/s", "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
         "ms_per_step": ms / args.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
         "dtype": {"fp32": "f32", "fp16": "f16", "bf16": "bf16"}[args.precision], "data": "synthetic",
-        "config": {"workload": workload, "images_per_step_per_gpu": N, "T": T_STEPS, "chunk": args.chunk,
+        "config": {"workload": workload_desc, "images_per_step_per_gpu": N, "T": T_STEPS, "chunk": args.chunk,
                    "precision": args.precision, "tensor_cores": bool(uses_tc),
                    "l2_policy": "per-step activation working set exceeds the 126 MB L2" if N * 0.4 > 126 else
                                 "activations of one chunk are L2-resident by design (chunked sampler); inputs regenerated per step"},
         "roofline": roofline, "roofline_hbm": roofline_hbm, "kernels": kern,
         "cpu_baseline": cpu, "e2e": e2e, "gpu_launches": int(launches), "clocks": clk,
     }
-    print(json.dumps(line), flush=True)
-    if td is not None:
-        td.destroy_process_group()
+    return line
 
 
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
-    ap.add_argument("--steps", type=int, default=4)
+    ap.add_argument("--steps", type=int, default=3)
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
-    ap.add_argument("--workload", default="sample", choices=["sample", "train"])
-    ap.add_argument("--images", type=int, default=0, help="images per step per GPU (default 4096 sample / 512 train)")
-    ap.add_argument("--chunk", type=int, default=256, help="images per captured reverse-loop graph")
+    ap.add_argument("--workload", default="both", choices=["sample", "train", "both"])
+    ap.add_argument("--images", type=int, default=4096, help="sampled images per step per GPU")
+    ap.add_argument("--train-images", type=int, default=4096, help="training batch per step per GPU")
+    ap.add_argument("--chunk", type=int, default=512, help="images per captured reverse-loop graph")
     ap.add_argument("--precision", default="fp16", choices=["fp32", "fp16", "bf16"])
     ap.add_argument("--t-start", type=int, default=T_STEPS)
     ap.add_argument("--seed", type=int, default=1234)
     ap.add_argument("--sync-bn", type=int, default=1)
     ap.add_argument("--e2e-steps", type=int, default=2)
-    ap.add_argument("--ref-images", type=int, default=16)
-    ap.add_argument("--ref-steps", type=int, default=12)
+    ap.add_argument("--ref-images", type=int, default=128)
+    ap.add_argument("--ref-steps", type=int, default=100)
     ap.add_argument("--no-cpu", action="store_true")
     args = ap.parse_args()
-    if args.images <= 0:
-        args.images = 4096 if args.workload == "sample" else 512
     if args.impl == "reference":
         run_reference(args)
     else:

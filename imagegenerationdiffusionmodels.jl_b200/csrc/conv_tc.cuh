@@ -162,7 +162,7 @@ __host__ __device__ constexpr uint32_t make_idesc(uint32_t fmt, uint32_t M, uint
 }
 
 // ------------------------------------------------------------------------------------ kernel
-constexpr int TC_THREADS = 192;
+constexpr int TC_THREADS = 224;   // warp 0 TMA, warps 1 and 6 MMA issuers (even / odd tiles), warps 2..5 epilogue
 constexpr int TC_BM = 128;
 
 template <typename TOut>
@@ -216,11 +216,20 @@ struct TcParams {
     int num_m_tiles;
     int chunk1_src1;      // 1: K-chunk 1 comes from the second tensor map (channel concat), 0: channels 64.. of the first
     long long* dbg;       // optional [gridDim.x*gridDim.y][8] cycle counters (role wait/busy breakdown), nullptr = off
+    // EPI == 2: final Conv((1,1), 64=>1) + reverse-diffusion update fused into this conv's epilogue
+    float* x;             // [N][H*W] current sample, updated in place
+    const float* z;       // [N][H*W] noise of this step
+    const float* wf;      // [64] final conv weight, bf[1] bias
+    const float* bf;
+    float sig, sqa, sqp, sqv;   // sigma_t, sqrt(a_t), sqrt(a_prev), sqrt(post_var)
+    int final_clamp;
 };
 
 // TAPS: 9 (3x3 conv, halo'ed slab) or 1 (plain GEMM rows); CHUNKS: 64-channel K chunks (1|2);
 // NOUT: output channels handled by this CTA (64|128); WP: padded row width (W+2) for TAPS==9
-// EPI: 0 = conv store on the same geometry, 1 = ConvTranspose 2x2 pixel shuffle (blockIdx.y = q)
+// EPI: 0 = conv store on the same geometry, 1 = ConvTranspose 2x2 pixel shuffle (blockIdx.y = q),
+//      2 = no activation store: eps_hat = <relu(acc+shift), wf> + bf per pixel, then the reverse-diffusion update
+//          x <- sqrt(a_prev)*clamp((x - sigma*eps_hat)/sqrt(a_t)) + sqrt(pv)*z   (generate_images.jl:196-208)
 // TMAST: 1 = epilogue stages the tile in swizzled shared memory and writes it with a TMA store
 // (halo rows are written as zeros, which is what they must hold), 0 = predicated 16-byte stores.
 template <int TAPS, int CHUNKS, int NOUT, int WP, int STAGES, int EPI, int TMAST, typename TIn, typename TOut>
@@ -232,7 +241,8 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constant__
     constexpr uint32_t A_STAGE_BYTES = R * 128;
     constexpr uint32_t W_TILE_BYTES = NOUT * 128;              // one (tap, chunk) weight tile [NOUT][64]
     constexpr uint32_t W_BYTES = TAPS * CHUNKS * W_TILE_BYTES;
-    constexpr int TMEM_COLS = (2 * NOUT <= 128) ? 128 : 256;
+    constexpr int ACC_BUFS = 4;                                // accumulator ring in TMEM (decouples MMA and epilogue)
+    constexpr int TMEM_COLS = (ACC_BUFS * NOUT <= 256) ? 256 : 512;
     constexpr uint32_t IDESC = make_idesc(IsBf16<TIn>::v, TC_BM, NOUT);
 
     extern __shared__ uint8_t smem_raw[];
@@ -242,15 +252,16 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constant__
     const uint32_t s_a = s_w + W_BYTES;
     const uint32_t s_o = s_a + STAGES * A_STAGE_BYTES;
     const uint32_t s_bar = s_o + O_BYTES;
-    // barrier slots (8 B each): [0] w_full, [1..S] a_full, [1+S..2S] a_empty, [1+2S, 2+2S] acc_full, [3+2S, 4+2S] acc_empty
+    // barrier slots (8 B each): [0] w_full, [1..S] a_full, [1+S..2S] a_empty, then ACC_BUFS acc_full, ACC_BUFS acc_empty
     auto bar_w = [&]() { return s_bar; };
     auto bar_afull = [&](int s) { return s_bar + 8u * (1 + s); };
     auto bar_aempty = [&](int s) { return s_bar + 8u * (1 + STAGES + s); };
     auto bar_accfull = [&](int b) { return s_bar + 8u * (1 + 2 * STAGES + b); };
-    auto bar_accempty = [&](int b) { return s_bar + 8u * (3 + 2 * STAGES + b); };
+    auto bar_accempty = [&](int b) { return s_bar + 8u * (1 + 2 * STAGES + ACC_BUFS + b); };
     uint8_t* misc = smem + W_BYTES + STAGES * A_STAGE_BYTES + O_BYTES;
-    uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(misc + 8 * (5 + 2 * STAGES));
+    uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(misc + 8 * (1 + 2 * STAGES + 2 * ACC_BUFS));
     float* s_shift = reinterpret_cast<float*>(misc + 256);               // [NOUT] per-channel shift of this CTA's N-slice
+    float* s_wf = s_shift + 128;                                         // [64] final-conv weights (EPI == 2)
 
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     long long dbg_acc[8] = {0, 0, 0, 0, 0, 0, 0, 0};
@@ -262,7 +273,7 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constant__
         if (p.chunk1_src1) prefetch_tmap(&tmA1);
         mbar_init(bar_w(), 1);
         for (int s = 0; s < STAGES; ++s) { mbar_init(bar_afull(s), 1); mbar_init(bar_aempty(s), 1); }
-        for (int b = 0; b < 2; ++b) { mbar_init(bar_accfull(b), 1); mbar_init(bar_accempty(b), 4); }
+        for (int b = 0; b < ACC_BUFS; ++b) { mbar_init(bar_accfull(b), 1); mbar_init(bar_accempty(b), 4); }
         fence_barrier_init();
     }
     if (warp == 2) tmem_alloc<TMEM_COLS>(smem_u32(tmem_slot));
@@ -270,6 +281,7 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constant__
         const int c = threadIdx.x - 64;
         const int co = (EPI == 1) ? c : (n_blk * NOUT + c);
         s_shift[c] = p.shift ? p.shift[co] : 0.f;
+        if (EPI == 2) s_wf[c] = p.wf[c];
     }
     if (warp == 0 && lane == 0 && TMAST) prefetch_tmap(&tmO);
     tc_fence_before();
@@ -304,26 +316,31 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constant__
                 if (++stage == STAGES) { stage = 0; phase ^= 1; }
             }
         }
-    } else if (warp == 1) {
-        // ================= MMA issuer (warp-uniform loop, one elected lane issues) =================
+    } else if (warp == 1 || warp == 6) {
+        // ================= MMA issuers (warp-uniform loops, one elected lane issues) =================
+        // Two issuer warps alternate tiles (warp 1: even, warp 6: odd tiles of this CTA).  The tensor pipe's
+        // instruction queue is shallow, so a single issuer drains it during every mbarrier wait (~150 cycles
+        // each); with two independent streams one warp's waits overlap the other's MMAs.  Tiles are
+        // independent (own TMEM accumulator, own slab), tcgen05.commit tracks the issuing thread's MMAs only.
+        const int parity = (warp == 1) ? 0 : 1;
         mbar_wait(bar_w(), 0);
         tc_fence_after();
         // matrix descriptor halves (see make_desc_sw128): lo = start>>4 | LBO<<16, hi = SBO | version | SWIZZLE_128B
         constexpr uint32_t DESC_HI = (1024u >> 4) | (1u << 14) | (2u << 29);
         const uint32_t a_lo_base = ((s_a & 0x3FFFFu) >> 4) | (1u << 16);
         const uint32_t b_lo_base = ((s_w & 0x3FFFFu) >> 4) | (1u << 16);
-        int stage = 0;
-        uint32_t phase = 0;
-        int buf = 0;
-        uint32_t acc_phase = 0;
-        for (int tile = blockIdx.x; tile < p.num_m_tiles; tile += gridDim.x) {
+        for (int seq = parity, tile = blockIdx.x + parity * gridDim.x; tile < p.num_m_tiles; seq += 2, tile += 2 * gridDim.x) {
+            const int buf = seq % ACC_BUFS;
+            const uint32_t acc_phase = (uint32_t)(seq / ACC_BUFS) & 1u;
             long long t0 = p.dbg ? clock64() : 0;
             mbar_wait(bar_accempty(buf), acc_phase ^ 1);
             if (p.dbg) dbg_acc[1] += clock64() - t0;
-            tc_fence_after();
             const uint32_t d_tmem = tmem_base + buf * NOUT;
 #pragma unroll
             for (int c = 0; c < CHUNKS; ++c) {
+                const int step = seq * CHUNKS + c;
+                const int stage = step % STAGES;
+                const uint32_t phase = (uint32_t)(step / STAGES) & 1u;
                 t0 = p.dbg ? clock64() : 0;
                 mbar_wait(bar_afull(stage), phase);
                 if (p.dbg) dbg_acc[2] += clock64() - t0;
@@ -333,7 +350,6 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constant__
                     const uint32_t a_lo = a_lo_base + stage * (A_STAGE_BYTES >> 4);
 #pragma unroll
                     for (int t = 0; t < TAPS; ++t) {
-                        constexpr int dummy = 0; (void)dummy;
                         const int shift = (TAPS == 9) ? (HALO + (t / 3 - 1) * WP + (t % 3 - 1)) : 0;
 #pragma unroll
                         for (int ks = 0; ks < 4; ++ks) {
@@ -347,15 +363,13 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constant__
                 }
                 __syncwarp();
                 if (p.dbg) dbg_acc[3] += clock64() - t0;
-                if (++stage == STAGES) { stage = 0; phase ^= 1; }
             }
-            if (++buf == 2) { buf = 0; acc_phase ^= 1; }
         }
     } else {
         // ================= epilogue warps (TMEM -> registers -> global) =================
         const int lane_grp = warp & 3;                       // TMEM lanes 32*lane_grp .. +31 are visible to this warp
         const int row = lane_grp * 32 + lane;
-        int buf = 0;
+        int buf = 0, obuf = 0;
         uint32_t acc_phase = 0;
         TOut* out = reinterpret_cast<TOut*>(p.out);
         for (int tile = blockIdx.x; tile < p.num_m_tiles; tile += gridDim.x) {
@@ -375,21 +389,27 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constant__
             tc_fence_after();
             const uint32_t taddr = tmem_base + ((uint32_t)(lane_grp * 32) << 16) + buf * NOUT;
             uint32_t stage_o = 0;
+            float dot = 0.f;
             if (TMAST) {
                 // the TMA store that last read this staging tile (two tiles ago) must have drained it
-                stage_o = s_o + (uint32_t)buf * (TC_BM * NOUT * 2);
+                stage_o = s_o + (uint32_t)obuf * (TC_BM * NOUT * 2);
                 if (threadIdx.x == 64) tma_store_wait_read<1>();
                 named_bar_sync(1, 128);
             }
+            // all accumulator columns of this row in one round trip (NOUT/16 loads in flight, one wait), then the
+            // TMEM buffer is handed back to the MMA warp BEFORE the arithmetic / stores of the epilogue
+            uint32_t racc[NOUT / 16][16];
+#pragma unroll
+            for (int q = 0; q < NOUT / 16; ++q) tmem_ld16(taddr + q * 16, racc[q]);
+            tmem_ld_wait();
+            tc_fence_before();
+            __syncwarp();
+            if (lane == 0) mbar_arrive(bar_accempty(buf));
 #pragma unroll
             for (int c0 = 0; c0 < NOUT; c0 += 32) {
-                uint32_t r0[16], r1[16];
-                tmem_ld16(taddr + c0, r0);
-                tmem_ld16(taddr + c0 + 16, r1);
-                tmem_ld_wait();
 #pragma unroll
                 for (int half = 0; half < 2; ++half) {
-                    const uint32_t* r = half ? r1 : r0;
+                    const uint32_t* r = racc[(c0 >> 4) + half];
                     const int cb = c0 + half * 16;
                     float v[16];
 #pragma unroll
@@ -404,7 +424,14 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constant__
 #pragma unroll
                         for (int j = 0; j < 16; ++j) v[j] = fmaxf(v[j], 0.f);
                     }
-                    if (TMAST) {
+                    if (EPI == 2) {
+#pragma unroll
+                        for (int j4 = 0; j4 < 4; ++j4) {
+                            const float4 w4 = *reinterpret_cast<const float4*>(s_wf + cb + 4 * j4);
+                            dot = fmaf(v[4 * j4 + 0], w4.x, dot); dot = fmaf(v[4 * j4 + 1], w4.y, dot);
+                            dot = fmaf(v[4 * j4 + 2], w4.z, dot); dot = fmaf(v[4 * j4 + 3], w4.w, dot);
+                        }
+                    } else if (TMAST) {
                         if (!valid) {
 #pragma unroll
                             for (int j = 0; j < 16; ++j) v[j] = 0.f;
@@ -425,6 +452,16 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constant__
                     }
                 }
             }
+            if (EPI == 2 && valid) {
+                const long long pix = (long long)n_img * (p.g.H * p.g.W) + hh * p.g.W + ww;
+                const float e = dot + __ldg(p.bf);
+                const float xv = p.x[pix];
+                float x0 = __fdiv_rn(__fsub_rn(xv, __fmul_rn(p.sig, e)), p.sqa);
+                x0 = fminf(fmaxf(x0, -1.f), 1.f);
+                float xn = __fadd_rn(__fmul_rn(p.sqp, x0), __fmul_rn(p.sqv, __ldg(p.z + pix)));
+                if (p.final_clamp) xn = fminf(fmaxf(xn, -1.f), 1.f);
+                p.x[pix] = xn;
+            }
             if (TMAST) {
                 fence_proxy_async();                 // generic-proxy smem writes -> visible to the TMA engine
                 named_bar_sync(1, 128);
@@ -435,11 +472,9 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constant__
                     tma_store_commit();
                 }
             }
-            tc_fence_before();
-            __syncwarp();
-            if (lane == 0) mbar_arrive(bar_accempty(buf));
             if (p.dbg) { dbg_acc[5] += clock64() - t1; dbg_acc[6] += 1; }
-            if (++buf == 2) { buf = 0; acc_phase ^= 1; }
+            obuf ^= 1;
+            if (++buf == ACC_BUFS) { buf = 0; acc_phase ^= 1; }
         }
     }
     if (TMAST && threadIdx.x == 64) tma_store_wait_all();
@@ -469,6 +504,7 @@ struct State {
     int num_sms = 148;
     int base_offset_mode = 0;
     bool enabled = true;
+    bool tma_store = true;      // epilogue of the 64->64 @32x32 conv: TMA store via swizzled smem (1) or direct stores (0)
 };
 inline State& state() {
     static State s;
@@ -575,7 +611,8 @@ bool conv3x3(cudaStream_t st, const TIn* s0, int C0, const TIn* s1, int C1, cons
     if (WP == 34 && Cin == 64 && Cout == 64 && !s1) {
         CUtensorMap w = make_map_2d<TIn>(Wt, 64, 9 * 64, 64);
         CUtensorMap o = make_map_2d<TOut>(out - (size_t)g.guard * Cout, rows, Cout, TC_BM);
-        launch<9, 1, 64, 34, 0, 1, TIn, TOut>(st, a0, a1, w, o, p, 1);
+        if (state().tma_store) launch<9, 1, 64, 34, 0, 1, TIn, TOut>(st, a0, a1, w, o, p, 1);
+        else launch<9, 1, 64, 34, 0, 0, TIn, TOut>(st, a0, a1, w, o, p, 1);
     } else if (WP == 34 && Cin == 128 && Cout == 64) {
         CUtensorMap w = make_map_2d<TIn>(Wt, 64, 9 * 128, 64);
         launch<9, 2, 64, 34, 0, 0, TIn, TOut>(st, a0, a1, w, a0, p, 1);
@@ -594,6 +631,31 @@ bool conv3x3(cudaStream_t st, const TIn* s0, int C0, const TIn* s1, int C1, cons
     } else {
         return false;
     }
+    return true;
+    }
+}
+
+// Last 3x3 conv (64=>64 @32x32) of the sampler with the final 1x1 conv and the reverse update fused in its epilogue
+template <typename TIn>
+bool conv3x3_final(cudaStream_t st, const TIn* s0, const TIn* Wt, const Geo& g, const float* shift, float* x, const float* z,
+                   const float* wf, const float* bf, const float scal[4], int final_clamp) {
+    if (!available()) return false;
+    if constexpr (sizeof(TIn) != 2) {
+        return false;
+    } else {
+    if (g.Wp != 34) return false;
+    TcParams p{};
+    p.out = nullptr; p.out_cs = 64; p.g = g; p.g_out = g; p.shift = shift; p.relu = 1;
+    p.num_m_tiles = cdiv(g.npos, TC_BM);
+    p.chunk1_src1 = 0;
+    p.dbg = nullptr;
+    p.x = x; p.z = z; p.wf = wf; p.bf = bf;
+    p.sig = scal[0]; p.sqa = scal[1]; p.sqp = scal[2]; p.sqv = scal[3];
+    p.final_clamp = final_clamp;
+    constexpr int R32 = ((TC_BM + 2 * 35 + 7) / 8) * 8;
+    CUtensorMap a0 = make_map_2d<TIn>(s0 - (size_t)g.guard * 64, (uint64_t)g.alloc_positions(), 64, R32);
+    CUtensorMap w = make_map_2d<TIn>(Wt, 64, 9 * 64, 64);
+    launch<9, 1, 64, 34, 2, 0, TIn, TIn>(st, a0, a0, w, a0, p, 1);
     return true;
     }
 }

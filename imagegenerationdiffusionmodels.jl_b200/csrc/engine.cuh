@@ -197,7 +197,7 @@ struct Engine {
     int rank = 0, world = 1, sync_bn = 0;
 
     // options / counters
-    long long opt_sample_chunk = 256, opt_use_graph = 1, opt_conv_impl = 0 /*0 auto, 1 simt, 2 tc*/;
+    long long opt_sample_chunk = 512, opt_use_graph = 1, opt_conv_impl = 0 /*0 auto, 1 simt, 2 tc*/, opt_fuse_final = 1;
     long long cnt_launches = 0;
 
     Engine(int T_, int D_, int H_, int W_, int prec_, int dev_);
@@ -234,9 +234,13 @@ struct Engine {
                double* stats);
     template <typename TA, typename TG>
     void dgrad3(const Tensor& dy, int l, Tensor& out, int out_c_total);
-    template <typename TA, typename TG> void forward_t(ActSet& s, const float* x_dev, const int* ts_dev, int t_fixed, Mode mode, bool update_running);
+    template <typename TA, typename TG> void forward_t(ActSet& s, const float* x_dev, const int* ts_dev, int t_fixed, Mode mode, bool update_running,
+                                                       bool skip_last = false);
     void forward(ActSet& s, const float* x_dev, const int* ts_dev, int t_fixed, Mode mode, bool update_running);
     template <typename TA, typename TG> void final_conv_t(ActSet& s, float* eps_hat_dev);
+    template <typename TA, typename TG> void layer10_fallback(ActSet& s) {
+        conv3<TA, TG>(s.a[9], nullptr, 10, s.a[10], Wfi[10], inf_shift[10], 1, nullptr);
+    }
     template <typename TA, typename TG> void backward_t(ActSet& s, const float* xt_dev, const int* ts_dev, const float* deps_dev, float alpha);
     void allreduce_sums(double* local, double* global, int n);
 
@@ -579,7 +583,8 @@ void Engine::dgrad3(const Tensor& dy, int l, Tensor& out, int out_c_total) {
 
 // ------------------------------------------------------------------------------------ forward
 template <typename TA, typename TG>
-void Engine::forward_t(ActSet& s, const float* x_dev, const int* ts_dev, int t_fixed, Mode mode, bool update_running) {
+void Engine::forward_t(ActSet& s, const float* x_dev, const int* ts_dev, int t_fixed, Mode mode, bool update_running,
+                       bool skip_last) {
     const int N = s.N;
     const bool train = mode == Mode::Train;
     prepare_ecls();
@@ -664,7 +669,7 @@ void Engine::forward_t(ActSet& s, const float* x_dev, const int* ts_dev, int t_f
     layer(7, s.u, nullptr);
     layer(8, s.a[7], nullptr);
     layer(9, s.a[8], &s.a[2]);  // cat(up_h3, h1; dims=3): upsampled first, skip second (train_brain.jl:175)
-    layer(10, s.a[9], nullptr);
+    if (!skip_last) layer(10, s.a[9], nullptr);   // the sampler fuses layer 10 with the final conv + reverse update
 }
 
 inline void Engine::forward(ActSet& s, const float* x_dev, const int* ts_dev, int t_fixed, Mode mode, bool update_running) {
@@ -898,8 +903,18 @@ void Engine::sample_steps_t(ActSet& s, float* x_dev, const float* z_dev, int N, 
             cnt_launches += 1;
             zstep = s.zstep.as<float>();
         }
-        forward_t<TA, TG>(s, x_dev, nullptr, t, Mode::Infer, false);
         const float* sc = &h_samp[(size_t)(t - 1) * 4];
+        if (use_tc() && opt_fuse_final) {
+            forward_t<TA, TG>(s, x_dev, nullptr, t, Mode::Infer, false, true);
+            if (tc::conv3x3_final<TA>(stream, s.a[9].pos0<TA>(), (const TA*)Wfi[10], s.a[9].g, inf_shift[10], x_dev, zstep,
+                                      arr(kFinalW), arr(kFinalB), sc, t == 2 ? 1 : 0)) {
+                cnt_launches += 1;
+                continue;
+            }
+            layer10_fallback<TA, TG>(s);
+        } else {
+            forward_t<TA, TG>(s, x_dev, nullptr, t, Mode::Infer, false);
+        }
         long long work = (long long)N * HW * 8;
         final_conv_kernel<TA><<<cdiv(work, 256), 256, 0, stream>>>(
             s.a[10].cview<TA>(), s.a[10].g, arr(kFinalW), arr(kFinalB), nullptr, 1, x_dev,

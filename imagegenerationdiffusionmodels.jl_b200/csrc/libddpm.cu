@@ -366,6 +366,8 @@ int ddpm_set_option(ddpm_handle* h, const char* key, int64_t value) {
     else if (k == "use_graph") e.opt_use_graph = value;
     else if (k == "conv_impl") { e.opt_conv_impl = value; for (auto& kv : e.infer_sets) kv.second->drop_graphs(); }
     else if (k == "sync_bn") e.sync_bn = (int)value;
+    else if (k == "tc_tma_store") { tc::state().tma_store = value != 0; for (auto& kv : e.infer_sets) kv.second->drop_graphs(); }
+    else if (k == "fuse_final") { e.opt_fuse_final = value; for (auto& kv : e.infer_sets) kv.second->drop_graphs(); }
     else if (k == "tc_role_profile") {
         // per-CTA cycle breakdown of the tcgen05 kernel roles, read back with ddpm_debug_fetch("tc_roles")
         if (value && !tc::state().dbg) DDPM_CUDA(cudaMalloc(&tc::state().dbg, 512 * 8 * sizeof(long long)));

@@ -15,6 +15,8 @@ h = capi.Handle(T=500, precision=capi.PREC_FP16)
 beta, _, acum = tables.beta_schedule(500)
 h.set_tables(beta, acum, tables.embedding_table(500))
 h.set_weights(api.SimpleUNet.load().arrays)
+if len(sys.argv) > 2:
+    h.set_option("tc_tma_store", int(sys.argv[2]))
 for name in ("conv_l2", "conv_l9", "conv_l4", "conv_l3"):
     ms, by, fl = h.time_kernel(name, n, 10)
     h.set_option("tc_role_profile", 1)

@@ -60,3 +60,22 @@ def test_tc_is_the_default_path(gpu_handles):
     h = gpu_handles["fp16"]
     assert h.counter("uses_tc") == 1
     assert gpu_handles["fp32"].counter("uses_tc") == 0
+
+
+def test_fused_final_epilogue_matches_unfused(gpu_handles, model_arrays):
+    """Sampler: last conv + final 1x1 conv + reverse update in one tcgen05 epilogue vs separate kernels.
+    The fused path feeds the un-rounded FP32 activations of layer 10 into the 1x1 conv, so they agree to
+    FP16 rounding of a10 only."""
+    h = gpu_handles["fp16"]
+    h.set_weights(model_arrays)
+    xT = np.random.default_rng(0).standard_normal((5, 1, 32, 32)).astype(np.float32)
+    z = np.random.default_rng(1).standard_normal((9, 5, 1, 32, 32)).astype(np.float32)
+    try:
+        h.set_option("fuse_final", 0)
+        a = h.sample(5, x_T=xT, z=z, t_start=10)
+        h.set_option("fuse_final", 1)
+        b = h.sample(5, x_T=xT, z=z, t_start=10)
+    finally:
+        h.set_option("fuse_final", 1)
+    assert np.abs(a - b).max() < 5e-3 and np.abs(a - b).mean() < 2e-4
+    assert np.abs(b).max() <= 1.0
