@@ -175,7 +175,7 @@ def run_reference(args):
         "e2e": {"value": value, "unit": "img/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
         "gpu_launches": 0,
     }
-    print(json.dumps(line), flush=True)
+    emit(line)
 
 
 # ------------------------------------------------------------------------------------ our arm
@@ -213,7 +213,7 @@ def run_ours(args):
             line["train"]["tflops"] = tl["roofline"]["whole_step_tflops"]
             line["train"]["frac_of_sustained_peak"] = tl["roofline"]["whole_step_frac_of_sustained"]
     if rank == 0:
-        print(json.dumps(line), flush=True)
+        emit(line)
     if td is not None:
         td.barrier()
         td.destroy_process_group()
@@ -362,7 +362,25 @@ def run_workload(args, workload, h, td, rank, world, local, peaks, N, t_start, e
     return line
 
 
+_REAL_STDOUT = None
+
+
+def emit(line: dict):
+    """The ONE JSON line goes to the real stdout; everything else (NCCL banners, warnings) was diverted to stderr."""
+    data = (json.dumps(line) + "\n").encode()
+    if _REAL_STDOUT is not None:
+        os.write(_REAL_STDOUT, data)
+    else:
+        sys.stdout.write(data.decode())
+        sys.stdout.flush()
+
+
 def main():
+    global _REAL_STDOUT
+    # libraries (NCCL prints its version banner on stdout) must not pollute the one-line contract
+    sys.stdout.flush()
+    _REAL_STDOUT = os.dup(1)
+    os.dup2(2, 1)
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
     ap.add_argument("--steps", type=int, default=3)
