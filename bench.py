@@ -200,6 +200,8 @@ def run_ours(args):
     def first_index(step_no):
         return (step_no * world + rank) * args.images
 
+    if args.train_images <= 0:
+        args.train_images = max(2, 4096 // world)
     common = (h, td, rank, world, local, peaks)
     if args.workload in ("sample", "both"):
         line = run_workload(args, "sample", *common, args.images, t_start, evals, first_index, api, capi, tables)
@@ -210,6 +212,7 @@ def run_ours(args):
         tl = run_workload(args, "train", *common, args.train_images, t_start, evals, first_index, api, capi, tables)
         if rank == 0:
             line["train"] = {k: tl[k] for k in ("metric", "value", "unit", "ms_per_step", "e2e", "gpu_launches", "config")}
+            line["train"]["scaling"] = "strong (global batch fixed at %d)" % (args.train_images * world)
             line["train"]["tflops"] = tl["roofline"]["whole_step_tflops"]
             line["train"]["frac_of_sustained_peak"] = tl["roofline"]["whole_step_frac_of_sustained"]
     if rank == 0:
@@ -388,7 +391,8 @@ def main():
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--workload", default="both", choices=["sample", "train", "both"])
     ap.add_argument("--images", type=int, default=4096, help="sampled images per step per GPU")
-    ap.add_argument("--train-images", type=int, default=4096, help="training batch per step per GPU")
+    ap.add_argument("--train-images", type=int, default=0,
+                    help="training batch per step per GPU (default: BASELINE config 5, global batch 4096 => 4096/n_gpus)")
     ap.add_argument("--chunk", type=int, default=512, help="images per captured reverse-loop graph")
     ap.add_argument("--precision", default="fp16", choices=["fp32", "fp16", "bf16"])
     ap.add_argument("--t-start", type=int, default=T_STEPS)
