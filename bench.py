@@ -194,6 +194,8 @@ def run_ours(args):
     model = api.SimpleUNet.load()
     h.set_weights(model.arrays)
     h.set_option("sample_chunk", args.chunk)
+    if args.streams > 0:
+        h.set_option("sample_streams", args.streams)
     t_start = args.t_start
     evals = t_start - 1
 
@@ -394,6 +396,7 @@ def main():
     ap.add_argument("--train-images", type=int, default=0,
                     help="training batch per step per GPU (default: BASELINE config 5, global batch 4096 => 4096/n_gpus)")
     ap.add_argument("--chunk", type=int, default=512, help="images per captured reverse-loop graph")
+    ap.add_argument("--streams", type=int, default=0, help="concurrent chunk streams of the sampler (0: library default)")
     ap.add_argument("--precision", default="fp16", choices=["fp32", "fp16", "bf16"])
     ap.add_argument("--t-start", type=int, default=T_STEPS)
     ap.add_argument("--seed", type=int, default=1234)

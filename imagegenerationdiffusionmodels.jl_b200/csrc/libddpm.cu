@@ -247,9 +247,21 @@ static void sample_impl(Engine& e, const float* x_T, const float* z, uint64_t se
     const int steps = t_start - 1;
     long long chunk = std::max<long long>(1, std::min<long long>(e.opt_sample_chunk, N));
     if (keep_on_device) e.d_sample_out.ensure((size_t)N * HW * 4);
-    for (long long c0 = 0; c0 < N; c0 += chunk) {
+    // derived weights / tables are refreshed once on the main stream; the chunk streams wait for that
+    e.prepare_ecls();
+    e.prepare_infer_affine();
+    const long long n_chunks = (N + chunk - 1) / chunk;
+    int n_streams = (int)std::max<long long>(1, std::min<long long>({e.opt_sample_streams, (long long)Engine::MAX_SAMPLE_STREAMS, n_chunks}));
+    DDPM_CUDA(cudaEventRecord(e.ev_fork, e.stream));
+    for (int i = 1; i < n_streams; ++i) DDPM_CUDA(cudaStreamWaitEvent(e.sample_streams[i], e.ev_fork, 0));
+    cudaStream_t main_stream = e.stream;
+    long long ci = 0;
+    try {
+    for (long long c0 = 0; c0 < N; c0 += chunk, ++ci) {
+        const int slot = (int)(ci % n_streams);
         int nb = (int)std::min<long long>(chunk, N - c0);
-        ActSet& s = e.get_set(nb, false);
+        ActSet& s = e.get_set(nb, false, slot);
+        e.stream = e.sample_streams[slot];       // every launch of this chunk goes to its stream
         float* xd = s.x.as<float>();
         if (x_T) {
             DDPM_CUDA(cudaMemcpyAsync(xd, x_T + c0 * HW, (size_t)nb * HW * 4, cudaMemcpyHostToDevice, e.stream));
@@ -265,7 +277,6 @@ static void sample_impl(Engine& e, const float* x_T, const float* z, uint64_t se
             // z[k] is an [N][HW] slab; take columns c0..c0+nb of every slab
             DDPM_CUDA(cudaMemcpy2DAsync(s.z.p, (size_t)nb * HW * 4, z + c0 * HW, (size_t)N * HW * 4, (size_t)nb * HW * 4,
                                         steps, cudaMemcpyHostToDevice, e.stream));
-            // a re-grown z buffer invalidates graphs that captured the old pointer
         }
         e.sample_chunk(s, z != nullptr, seed, first_index + c0, t_start);
         if (steps == 0) {
@@ -278,6 +289,16 @@ static void sample_impl(Engine& e, const float* x_T, const float* z, uint64_t se
         if (keep_on_device)
             DDPM_CUDA(cudaMemcpyAsync(e.d_sample_out.as<float>() + c0 * HW, xd, (size_t)nb * HW * 4, cudaMemcpyDeviceToDevice,
                                       e.stream));
+    }
+    } catch (...) {
+        e.stream = main_stream;
+        throw;
+    }
+    e.stream = main_stream;
+    // join: the main stream (and the caller's timer events on it) waits for every chunk stream
+    for (int i = 1; i < n_streams; ++i) {
+        DDPM_CUDA(cudaEventRecord(e.ev_join[i], e.sample_streams[i]));
+        DDPM_CUDA(cudaStreamWaitEvent(e.stream, e.ev_join[i], 0));
     }
     DDPM_CUDA(cudaStreamSynchronize(e.stream));
 }
@@ -363,6 +384,7 @@ int ddpm_set_option(ddpm_handle* h, const char* key, int64_t value) {
     Engine& e = E(h);
     std::string k = key ? key : "";
     if (k == "sample_chunk") { DDPM_CHECK(value >= 1, "sample_chunk must be >= 1"); e.opt_sample_chunk = value; }
+    else if (k == "sample_streams") { DDPM_CHECK(value >= 1 && value <= Engine::MAX_SAMPLE_STREAMS, "sample_streams must be 1..2"); e.opt_sample_streams = value; }
     else if (k == "use_graph") e.opt_use_graph = value;
     else if (k == "conv_impl") { e.opt_conv_impl = value; for (auto& kv : e.infer_sets) kv.second->drop_graphs(); }
     else if (k == "sync_bn") e.sync_bn = (int)value;
