@@ -196,6 +196,9 @@ def run_ours(args):
     h.set_option("sample_chunk", args.chunk)
     if args.streams > 0:
         h.set_option("sample_streams", args.streams)
+    for kv in filter(None, os.environ.get("DDPM_OPTS", "").split(",")):   # e.g. DDPM_OPTS=conv_v2=0,fuse_final=0
+        k, v = kv.split("=")
+        h.set_option(k, int(v))
     t_start = args.t_start
     evals = t_start - 1
 

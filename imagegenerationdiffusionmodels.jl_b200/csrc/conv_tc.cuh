@@ -39,7 +39,10 @@ __device__ __forceinline__ void mbar_expect_tx(uint32_t bar, uint32_t bytes) {
 __device__ __forceinline__ void mbar_arrive(uint32_t bar) {
     asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(bar) : "memory");
 }
-__device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t parity) {
+// Host-mapped diagnostics: a wait that never completes records where it was stuck before it traps.
+__device__ int* g_trap_info = nullptr;     // [8] in pinned, mapped host memory (set by tc::init)
+
+__device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t parity, int site = 0) {
     uint32_t done = 0;
     unsigned long long spins = 0;
     do {
@@ -50,7 +53,15 @@ __device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t parity) {
             : "=r"(done)
             : "r"(bar), "r"(parity)
             : "memory");
-        if (!done && ++spins > (1ull << 26)) __trap();  // a lost arrival must fault, never hang the GPU
+        if (!done && ++spins > (1ull << 24)) {          // a lost arrival must fault, never hang the GPU
+            if (g_trap_info) {
+                g_trap_info[0] = 1 + site; g_trap_info[1] = blockIdx.x; g_trap_info[2] = blockIdx.y;
+                g_trap_info[3] = threadIdx.x; g_trap_info[4] = (int)parity; g_trap_info[5] = (int)bar;
+                g_trap_info[6] = gridDim.x;
+                __threadfence_system();
+            }
+            __trap();
+        }
     } while (!done);
 }
 // one lane of a fully converged warp (keeps the surrounding control flow warp-uniform, so descriptors
@@ -242,6 +253,7 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constant__
     constexpr uint32_t W_TILE_BYTES = NOUT * 128;              // one (tap, chunk) weight tile [NOUT][64]
     constexpr uint32_t W_BYTES = TAPS * CHUNKS * W_TILE_BYTES;
     constexpr int ACC_BUFS = 4;                                // accumulator ring in TMEM (decouples MMA and epilogue)
+    constexpr bool DUAL = (STAGES % (2 * CHUNKS)) == 0;        // two MMA issuer warps only if stages stay warp-private
     constexpr int TMEM_COLS = (ACC_BUFS * NOUT <= 256) ? 256 : 512;
     constexpr uint32_t IDESC = make_idesc(IsBf16<TIn>::v, TC_BM, NOUT);
 
@@ -316,20 +328,22 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constant__
                 if (++stage == STAGES) { stage = 0; phase ^= 1; }
             }
         }
-    } else if (warp == 1 || warp == 6) {
+    } else if (warp == 1 || (warp == 6 && DUAL)) {
         // ================= MMA issuers (warp-uniform loops, one elected lane issues) =================
         // Two issuer warps alternate tiles (warp 1: even, warp 6: odd tiles of this CTA).  The tensor pipe's
         // instruction queue is shallow, so a single issuer drains it during every mbarrier wait (~150 cycles
         // each); with two independent streams one warp's waits overlap the other's MMAs.  Tiles are
         // independent (own TMEM accumulator, own slab), tcgen05.commit tracks the issuing thread's MMAs only.
+        // Dual issue is only legal when each pipeline stage is always consumed by the same warp (see conv3_tc.cuh).
         const int parity = (warp == 1) ? 0 : 1;
+        constexpr int NISS = DUAL ? 2 : 1;
         mbar_wait(bar_w(), 0);
         tc_fence_after();
         // matrix descriptor halves (see make_desc_sw128): lo = start>>4 | LBO<<16, hi = SBO | version | SWIZZLE_128B
         constexpr uint32_t DESC_HI = (1024u >> 4) | (1u << 14) | (2u << 29);
         const uint32_t a_lo_base = ((s_a & 0x3FFFFu) >> 4) | (1u << 16);
         const uint32_t b_lo_base = ((s_w & 0x3FFFFu) >> 4) | (1u << 16);
-        for (int seq = parity, tile = blockIdx.x + parity * gridDim.x; tile < p.num_m_tiles; seq += 2, tile += 2 * gridDim.x) {
+        for (int seq = parity, tile = blockIdx.x + parity * gridDim.x; tile < p.num_m_tiles; seq += NISS, tile += NISS * gridDim.x) {
             const int buf = seq % ACC_BUFS;
             const uint32_t acc_phase = (uint32_t)(seq / ACC_BUFS) & 1u;
             long long t0 = p.dbg ? clock64() : 0;
@@ -365,6 +379,8 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constant__
                 if (p.dbg) dbg_acc[3] += clock64() - t0;
             }
         }
+    } else if (warp == 6) {
+        // second issuer warp unused in this configuration (single-issuer mode)
     } else {
         // ================= epilogue warps (TMEM -> registers -> global) =================
         const int lane_grp = warp & 3;                       // TMEM lanes 32*lane_grp .. +31 are visible to this warp
@@ -498,6 +514,7 @@ typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t,
                                   CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
 
 struct State {
+    int* trap_host = nullptr;   // pinned + mapped [8]: filled by a kernel right before it traps on a stuck barrier
     long long* dbg = nullptr;   // device buffer [512][8] when role profiling is on
     EncodeTiledFn encode = nullptr;
     bool ok = false;
@@ -523,6 +540,15 @@ inline void init() {
         return;
     }
     s.encode = reinterpret_cast<EncodeTiledFn>(fn);
+    if (cudaHostAlloc(&s.trap_host, 8 * sizeof(int), cudaHostAllocMapped) == cudaSuccess) {
+        for (int i = 0; i < 8; ++i) s.trap_host[i] = 0;
+        int* dptr = nullptr;
+        if (cudaHostGetDevicePointer(&dptr, s.trap_host, 0) == cudaSuccess)
+            cudaMemcpyToSymbol(g_trap_info, &dptr, sizeof dptr);
+    } else {
+        cudaGetLastError();
+        s.trap_host = nullptr;
+    }
     int dev = 0;
     cudaGetDevice(&dev);
     cudaDeviceGetAttribute(&s.num_sms, cudaDevAttrMultiProcessorCount, dev);

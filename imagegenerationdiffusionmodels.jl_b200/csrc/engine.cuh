@@ -15,6 +15,7 @@
 #include "kernels.cuh"
 #include "igemm_simt.cuh"
 #include "conv_tc.cuh"
+#include "conv3_tc.cuh"
 
 namespace ddpm {
 
@@ -179,6 +180,9 @@ struct Engine {
     void* Wf[NUM_CONV + 1] = {};   // [cout][9][cin]  (TA)  -- L1 unused
     void* Wd[NUM_CONV + 1] = {};   // [cin][9][cout]  (TG)  -- L1 unused
     void* Wfi[NUM_CONV + 1] = {};  // Wf with the inference BatchNorm scale folded in (TA)
+    void* W3f[NUM_CONV + 1] = {};  // row-packed variants for conv3_tc.cuh: forward (TA), inference-folded (TA), dgrad (TG)
+    void* W3fi[NUM_CONV + 1] = {};
+    void* W3d[NUM_CONV + 1] = {};
     void *Wt = nullptr, *Wtd = nullptr;  // convT fwd (TA) [256][128], dgrad (TG) [128][256]
     float *Wimg = nullptr, *Wemb = nullptr;  // first conv, FP32
     float *Ptab = nullptr, *Ecls = nullptr;  // [T][9][64] embedding contributions
@@ -205,6 +209,10 @@ struct Engine {
 
     // options / counters
     long long opt_sample_streams = 1;
+    // 1 = row-packed tcgen05 conv (conv3_tc.cuh): MMAs at the tensor floor (96 cyc per M128 N192 K16) but its
+    // shuffle/exchange epilogue costs ~2300 cycles per tile, so the first formulation (conv_tc.cuh, ~2500 cycles per
+    // tile, smem-operand bound) is still faster end to end (B200, round 1: 1612 vs 1791 img/s) and stays the default.
+    long long opt_conv_v2 = 0;
     long long opt_sample_chunk = 512, opt_use_graph = 1, opt_conv_impl = 0 /*0 auto, 1 simt, 2 tc*/, opt_fuse_final = 1;
     long long cnt_launches = 0;
 
@@ -238,7 +246,7 @@ struct Engine {
     void prepare_infer_affine();
 
     template <typename TA, typename TG>
-    void conv3(const Tensor& s0, const Tensor* s1, int l, Tensor& out, const void* weights, const float* shift, int relu,
+    void conv3(const Tensor& s0, const Tensor* s1, int l, Tensor& out, bool infer_weights, const float* shift, int relu,
                double* stats);
     template <typename TA, typename TG>
     void dgrad3(const Tensor& dy, int l, Tensor& out, int out_c_total);
@@ -247,7 +255,7 @@ struct Engine {
     void forward(ActSet& s, const float* x_dev, const int* ts_dev, int t_fixed, Mode mode, bool update_running);
     template <typename TA, typename TG> void final_conv_t(ActSet& s, float* eps_hat_dev);
     template <typename TA, typename TG> void layer10_fallback(ActSet& s) {
-        conv3<TA, TG>(s.a[9], nullptr, 10, s.a[10], Wfi[10], inf_shift[10], 1, nullptr);
+        conv3<TA, TG>(s.a[9], nullptr, 10, s.a[10], true, inf_shift[10], 1, nullptr);
     }
     template <typename TA, typename TG> void backward_t(ActSet& s, const float* xt_dev, const int* ts_dev, const float* deps_dev, float alpha);
     void allreduce_sums(double* local, double* global, int n);
@@ -316,6 +324,9 @@ inline Engine::Engine(int T_, int D_, int H_, int W_, int prec_, int dev_)
             DDPM_CUDA(cudaMalloc(&Wf[l], n * esz_a()));
             DDPM_CUDA(cudaMalloc(&Wd[l], n * esz_g()));
             DDPM_CUDA(cudaMalloc(&Wfi[l], n * esz_a()));
+            DDPM_CUDA(cudaMalloc(&W3f[l], n * esz_a()));
+            DDPM_CUDA(cudaMalloc(&W3fi[l], n * esz_a()));
+            DDPM_CUDA(cudaMalloc(&W3d[l], n * esz_g()));
         }
     }
     DDPM_CUDA(cudaMalloc(&Wt, (size_t)4 * 128 * 64 * esz_a()));
@@ -349,7 +360,7 @@ inline Engine::~Engine() {
     for (int l = 1; l <= NUM_CONV; ++l) {
         float* v[] = {inf_scale[l], inf_shift[l], tr_mean[l], tr_istd[l], tr_scale[l], tr_shift[l], bw_mg[l], bw_mgx[l]};
         for (float* p : v) cudaFree(p);
-        cudaFree(Wf[l]); cudaFree(Wd[l]); cudaFree(Wfi[l]);
+        cudaFree(Wf[l]); cudaFree(Wd[l]); cudaFree(Wfi[l]); cudaFree(W3f[l]); cudaFree(W3fi[l]); cudaFree(W3d[l]);
     }
     cudaFree(Wt); cudaFree(Wtd); cudaFree(sums); cudaFree(sums_g); cudaFree(misc_sums); cudaFree(d_rng);
     DevBuf* bufs[] = {&d_x0, &d_eps, &d_xt, &d_deps, &d_ts, &d_idx, &d_Tw, &d_Ccls, &d_S, &d_z, &d_dataset, &d_sample_out};
@@ -495,6 +506,8 @@ void Engine::pack_weights_t() {
         long long n = 9LL * c.cin * c.cout;
         pack_conv3_kernel<TA><<<cdiv(n, 256), 256, 0, stream>>>(arr(c.w), c.cin, 0, c.cin, c.cout, 0, nullptr, (TA*)Wf[l]);
         pack_conv3_kernel<TG><<<cdiv(n, 256), 256, 0, stream>>>(arr(c.w), c.cin, 0, c.cin, c.cout, 1, nullptr, (TG*)Wd[l]);
+        pack_conv3_rows_kernel<TA><<<cdiv(n, 256), 256, 0, stream>>>(arr(c.w), c.cin, c.cout, 0, nullptr, (TA*)W3f[l]);
+        pack_conv3_rows_kernel<TG><<<cdiv(n, 256), 256, 0, stream>>>(arr(c.w), c.cin, c.cout, 1, nullptr, (TG*)W3d[l]);
     }
     long long nt = 4LL * 128 * 64;
     pack_up2_kernel<TA><<<cdiv(nt, 256), 256, 0, stream>>>(arr(kUpW), 128, 64, 0, (TA*)Wt);
@@ -502,7 +515,7 @@ void Engine::pack_weights_t() {
     long long n1 = 9LL * 64 * (D + 1);
     pack_l1_kernel<<<cdiv(n1, 256), 256, 0, stream>>>(arr(0), D, 64, Wimg, Wemb);
     DDPM_LAUNCH_CHECK();
-    cnt_launches += 2 * (NUM_CONV - 1) + 3;
+    cnt_launches += 4 * (NUM_CONV - 1) + 3;
 }
 
 inline void Engine::pack_weights() {
@@ -529,9 +542,10 @@ void Engine::pack_infer_weights_t() {
         const ConvSpec& c = kConv[l];
         long long n = 9LL * c.cin * c.cout;
         pack_conv3_kernel<TA><<<cdiv(n, 256), 256, 0, stream>>>(arr(c.w), c.cin, 0, c.cin, c.cout, 0, inf_scale[l], (TA*)Wfi[l]);
+        pack_conv3_rows_kernel<TA><<<cdiv(n, 256), 256, 0, stream>>>(arr(c.w), c.cin, c.cout, 0, inf_scale[l], (TA*)W3fi[l]);
     }
     DDPM_LAUNCH_CHECK();
-    cnt_launches += NUM_CONV - 1;
+    cnt_launches += 2 * (NUM_CONV - 1);
 }
 
 // Inference: BatchNorm with running statistics is a per-channel affine map; its scale is folded into
@@ -552,15 +566,23 @@ inline void Engine::prepare_infer_affine() {
 // ------------------------------------------------------------------------------------ convolutions
 // Conv((3,3), cin=>cout, pad=1) of layer l on s0 (and s1 concatenated along channels)
 template <typename TA, typename TG>
-void Engine::conv3(const Tensor& s0, const Tensor* s1, int l, Tensor& out, const void* weights, const float* shift,
+void Engine::conv3(const Tensor& s0, const Tensor* s1, int l, Tensor& out, bool infer_weights, const float* shift,
                    int relu, double* stats) {
+    const void* weights = infer_weights ? Wfi[l] : Wf[l];
+    const void* weights3 = infer_weights ? W3fi[l] : W3f[l];
     const ConvSpec& c = kConv[l];
     const Geo& g = out.g;
     int C0 = s0.C, C1 = s1 ? s1->C : 0;
     DDPM_CHECK(C0 + C1 == c.cin && out.C == c.cout, "conv3: channel mismatch");
     if (use_tc()) {
-        if (tc::conv3x3<TA, TA>(stream, s0.pos0<TA>(), C0, s1 ? s1->pos0<TA>() : nullptr, C1, (const TA*)weights, c.cout,
-                                out.pos0<TA>(), g, shift, relu)) {
+        bool ok = false;
+        if (opt_conv_v2)
+            ok = tc::conv3x3_v2<TA, TA>(stream, s0.pos0<TA>(), C0, s1 ? s1->pos0<TA>() : nullptr, C1, (const TA*)weights3, c.cout,
+                                        out.pos0<TA>(), g, shift, relu);
+        if (!ok)
+            ok = tc::conv3x3<TA, TA>(stream, s0.pos0<TA>(), C0, s1 ? s1->pos0<TA>() : nullptr, C1, (const TA*)weights, c.cout,
+                                     out.pos0<TA>(), g, shift, relu);
+        if (ok) {
             cnt_launches += 1;
             if (stats) {  // train-mode BatchNorm statistics of the stored (rounded) y
                 long long pixels = (long long)g.N * g.H * g.W;
@@ -585,8 +607,14 @@ void Engine::dgrad3(const Tensor& dy, int l, Tensor& out, int out_c_total) {
     const Geo& g = out.g;
     DDPM_CHECK(dy.C == c.cout && out.C == out_c_total && out_c_total == c.cin, "dgrad3: channel mismatch");
     if (use_tc()) {
-        if (tc::conv3x3<TG, TG>(stream, dy.pos0<TG>(), c.cout, nullptr, 0, (const TG*)Wd[l], c.cin, out.pos0<TG>(), g,
-                                nullptr, 0)) {
+        bool ok = false;
+        if (opt_conv_v2)
+            ok = tc::conv3x3_v2<TG, TG>(stream, dy.pos0<TG>(), c.cout, nullptr, 0, (const TG*)W3d[l], c.cin, out.pos0<TG>(), g,
+                                        nullptr, 0);
+        if (!ok)
+            ok = tc::conv3x3<TG, TG>(stream, dy.pos0<TG>(), c.cout, nullptr, 0, (const TG*)Wd[l], c.cin, out.pos0<TG>(), g,
+                                     nullptr, 0);
+        if (ok) {
             cnt_launches += 1;
             return;
         }
@@ -638,10 +666,10 @@ void Engine::forward_t(ActSet& s, const float* x_dev, const int* ts_dev, int t_f
     auto layer = [&](int l, const Tensor& in0, const Tensor* in1) {
         const ConvSpec& c = kConv[l];
         if (train) {
-            conv3<TA, TG>(in0, in1, l, s.y[l], Wf[l], arr(c.b), 0, lsum(l));
+            conv3<TA, TG>(in0, in1, l, s.y[l], false, arr(c.b), 0, lsum(l));
             bn(l, l == 2);
         } else {
-            conv3<TA, TG>(in0, in1, l, s.a[l], Wfi[l], inf_shift[l], 1, nullptr);
+            conv3<TA, TG>(in0, in1, l, s.a[l], true, inf_shift[l], 1, nullptr);
         }
     };
 
@@ -924,8 +952,21 @@ void Engine::sample_steps_t(ActSet& s, float* x_dev, const float* z_dev, int N, 
         const float* sc = &h_samp[(size_t)(t - 1) * 4];
         if (use_tc() && opt_fuse_final) {
             forward_t<TA, TG>(s, x_dev, nullptr, t, Mode::Infer, false, true);
-            if (tc::conv3x3_final<TA>(stream, s.a[9].pos0<TA>(), (const TA*)Wfi[10], s.a[9].g, inf_shift[10], x_dev, zstep,
-                                      arr(kFinalW), arr(kFinalB), sc, t == 2 ? 1 : 0)) {
+            bool fused = false;
+            if (opt_conv_v2) {
+                if constexpr (sizeof(TA) == 2) {
+                    tc::C3Params fp{};
+                    fp.x = x_dev; fp.z = zstep; fp.wf = arr(kFinalW); fp.bf = arr(kFinalB);
+                    fp.sig = sc[0]; fp.sqa = sc[1]; fp.sqp = sc[2]; fp.sqv = sc[3];
+                    fp.final_clamp = t == 2 ? 1 : 0;
+                    fused = tc::conv3x3_v2<TA, TA>(stream, s.a[9].pos0<TA>(), 64, nullptr, 0, (const TA*)W3fi[10], 64, nullptr,
+                                                   s.a[9].g, inf_shift[10], 1, &fp);
+                }
+            }
+            if (!fused)
+                fused = tc::conv3x3_final<TA>(stream, s.a[9].pos0<TA>(), (const TA*)Wfi[10], s.a[9].g, inf_shift[10], x_dev, zstep,
+                                              arr(kFinalW), arr(kFinalB), sc, t == 2 ? 1 : 0);
+            if (fused) {
                 cnt_launches += 1;
                 continue;
             }

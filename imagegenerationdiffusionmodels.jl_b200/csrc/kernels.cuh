@@ -809,6 +809,32 @@ __global__ void pack_conv3_kernel(const float* __restrict__ w, int Cin_total, in
         out[i] = from_f<TW>(w[(1 + dx) + 3 * (1 + dy) + 9LL * (ci + ci_off) + 9LL * Cin_total * co]);
     }
 }
+// Row-packed layout of conv3_tc.cuh: rows = (out-channel block of 64) x (dx, channel) = 192 per block, cols = (dy, k).
+//   forward : out channel = Flux co, k = Flux ci :  w[1-dx, 1-dy, ci, co] * row_scale[co]
+//   dgrad   : out channel = Flux ci, k = Flux co :  w[1+dx, 1+dy, ci, co]
+template <typename TW>
+__global__ void pack_conv3_rows_kernel(const float* __restrict__ w, int CinFlux, int CoutFlux, int dgrad,
+                                       const float* __restrict__ row_scale, TW* __restrict__ out) {
+    const int K = dgrad ? CoutFlux : CinFlux;        // contraction channels of this conv
+    const int OC = dgrad ? CinFlux : CoutFlux;       // output channels of this conv
+    long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    const long long total = 9LL * K * OC;
+    if (i >= total) return;
+    const int col = (int)(i % (3 * K));
+    const int row = (int)(i / (3 * K));
+    const int nblk = row / 192, rr = row % 192, dxi = rr / 64, oc = nblk * 64 + (rr % 64);
+    const int dyi = col / K, kc = col % K;
+    const int dx = dxi - 1, dy = dyi - 1;
+    float v;
+    if (!dgrad) {
+        v = w[(1 - dx) + 3 * (1 - dy) + 9LL * kc + 9LL * CinFlux * oc];
+        if (row_scale) v *= row_scale[oc];
+    } else {
+        v = w[(1 + dx) + 3 * (1 + dy) + 9LL * oc + 9LL * CinFlux * kc];
+    }
+    out[i] = from_f<TW>(v);
+}
+
 // ConvTranspose weight w[a,b,co,ci]:  Wt[q*Cout+co][ci] (fwd, K = ci)  /  Wtd[ci][q*Cout+co] (dgrad, K = q,co)
 template <typename TW>
 __global__ void pack_up2_kernel(const float* __restrict__ w, int Cin, int Cout, int dgrad, TW* __restrict__ out) {

@@ -18,6 +18,7 @@ static thread_local std::string g_last_error;
     }                                             \
     catch (const std::exception& e) {             \
         g_last_error = e.what();                  \
+        append_trap_info();                       \
         cudaGetLastError();                       \
         return 1;                                 \
     }                                             \
@@ -26,6 +27,16 @@ static thread_local std::string g_last_error;
         return 1;                                 \
     }                                             \
     return 0;
+
+static void append_trap_info() {
+    int* t = tc::state().trap_host;
+    if (t && t[0] != 0) {
+        char buf[200];
+        snprintf(buf, sizeof buf, " [stuck mbarrier: site=%d block=(%d,%d) of %d thread=%d parity=%d bar=0x%x]", t[0] - 1, t[1], t[2],
+                 t[6], t[3], t[4], t[5]);
+        g_last_error += buf;
+    }
+}
 
 static Engine& E(ddpm_handle* h) {
     if (!h || !h->eng) throw Error("null handle");
@@ -389,6 +400,7 @@ int ddpm_set_option(ddpm_handle* h, const char* key, int64_t value) {
     else if (k == "conv_impl") { e.opt_conv_impl = value; for (auto& kv : e.infer_sets) kv.second->drop_graphs(); }
     else if (k == "sync_bn") e.sync_bn = (int)value;
     else if (k == "tc_tma_store") { tc::state().tma_store = value != 0; for (auto& kv : e.infer_sets) kv.second->drop_graphs(); }
+    else if (k == "conv_v2") { e.opt_conv_v2 = value; for (auto& kv : e.infer_sets) kv.second->drop_graphs(); }
     else if (k == "fuse_final") { e.opt_fuse_final = value; for (auto& kv : e.infer_sets) kv.second->drop_graphs(); }
     else if (k == "tc_role_profile") {
         // per-CTA cycle breakdown of the tcgen05 kernel roles, read back with ddpm_debug_fetch("tc_roles")
@@ -517,7 +529,7 @@ int ddpm_time_kernel(ddpm_handle* h, const char* name, int64_t n_images, int ite
             }
             // inference aliasing: a[l] may alias an input two layers back, never in0/in1
             DDPM_DISPATCH(e.prec, time_it([&] {
-                e.conv3<TA, TG>(*in0, in1, l, s.a[l], e.Wfi[l], e.inf_shift[l], 1, nullptr);
+                e.conv3<TA, TG>(*in0, in1, l, s.a[l], true, e.inf_shift[l], 1, nullptr);
             }));
             double px = (double)N * c.hw * c.hw;
             fl = 2.0 * px * c.cout * 9.0 * c.cin;
