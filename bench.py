@@ -324,7 +324,7 @@ def run_workload(args, workload, h, td, rank, world, local, peaks, N, t_start, e
     #      51% of the U-Net FLOPs), timed alone with CUDA events on the engine's stream
     chunk = min(args.chunk, N)
     kern = {}
-    for name in ("conv_l2", "conv_l4", "conv_l9", "conv_l3", "reverse_update", "qsample", "mse", "adam"):
+    for name in ("conv_l2", "conv_l4", "conv_l9", "conv_l3", "conv1", "pool", "up2", "reverse_update", "qsample", "mse", "adam"):
         if workload == "train" and args.workload == "both":
             break   # already measured in the sampling pass of this run
         try:

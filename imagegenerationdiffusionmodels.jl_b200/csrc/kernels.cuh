@@ -166,74 +166,95 @@ __global__ void apply_noise_f64_kernel(const double* __restrict__ img, const dou
 // image); only the image channel is convolved (K = 9), in FP32 on CUDA cores.
 //   y = (sum_tap x[h+dy,w+dx]*Wimg[tap][co] + Ecls[t][cls][co]) * scale[co] + shift[co]
 // x is the unpadded boundary layout [N][H][W].
-constexpr int CONV1_PIX_PER_BLOCK = 512;
+constexpr int CONV1_PIX_PER_BLOCK = 256;
 
-// Thread layout: 8 lanes per pixel, 8 output channels per lane.  The 72 image-channel weights, scale and
-// shift of a lane's 8 channels live in registers for the whole block (no shared-memory traffic in the
-// pixel loop); H = W = 32 is a compile-time constant (the engine rejects other sizes).
+// Thread layout: 16 lanes per pixel, 4 output channels per lane (16 pixels per 256-thread pass).  The 36
+// image-channel weights, scale and shift of a lane's 4 channels live in registers for the whole block; keeping the
+// per-thread state small (vs 8 channels = 146 registers, 1 block/SM) triples the resident warps of this
+// latency-bound kernel.  H = W = 32 is a compile-time constant (the engine rejects other sizes).
+template <typename T> __device__ __forceinline__ void st4(T* p, const float o[4]);
+template <> __device__ __forceinline__ void st4<float>(float* p, const float o[4]) {
+    *reinterpret_cast<float4*>(p) = make_float4(o[0], o[1], o[2], o[3]);
+}
+template <> __device__ __forceinline__ void st4<__half>(__half* p, const float o[4]) {
+    uint2 v;
+    __half2* h = reinterpret_cast<__half2*>(&v);
+    h[0] = __floats2half2_rn(o[0], o[1]); h[1] = __floats2half2_rn(o[2], o[3]);
+    *reinterpret_cast<uint2*>(p) = v;
+}
+template <> __device__ __forceinline__ void st4<__nv_bfloat16>(__nv_bfloat16* p, const float o[4]) {
+    uint2 v;
+    __nv_bfloat162* h = reinterpret_cast<__nv_bfloat162*>(&v);
+    h[0] = __floats2bfloat162_rn(o[0], o[1]); h[1] = __floats2bfloat162_rn(o[2], o[3]);
+    *reinterpret_cast<uint2*>(p) = v;
+}
+
+// One block = 8 full rows (256 pixels) of one image.  The block first stages the zero-padded 10 x 34 input
+// window in shared memory, so the nine taps are unconditional broadcast LDS (the kernel was issue-bound on
+// per-tap bounds checks: 175 instructions per pixel-thread, profiles/README.md).  Thread layout: 16 lanes per
+// pixel, 4 output channels per lane, weights/scale/shift of the lane's channels in registers.
 template <typename TA>
 __global__ void __launch_bounds__(256)
 conv1_kernel(const float* __restrict__ x, const int* __restrict__ ts, int t_fixed, const float* __restrict__ Wimg,
              const float* __restrict__ Ecls, const float* __restrict__ scale, const float* __restrict__ shift, int relu,
              View<TA> out, Geo g, double* __restrict__ stats) {
-    constexpr int H = 32, W = 32, HW = H * W;
+    constexpr int H = 32, W = 32, HW = H * W, ROWS = CONV1_PIX_PER_BLOCK / W, TW = W + 2;
+    __shared__ float tile[(ROWS + 2) * TW];
     __shared__ float red[2][64];
     const int t = threadIdx.x;
-    const int cg = (t & 7) * 8;
-    float wr[9][8], sc[8], sh[8];
+    const long long pbeg = (long long)blockIdx.x * CONV1_PIX_PER_BLOCK;
+    const int n = (int)(pbeg >> 10);
+    const int h0 = (int)((pbeg & (HW - 1)) >> 5);
+    if (n >= g.N) return;
+    const float* xi = x + (long long)n * HW;
+    for (int i = t; i < (ROWS + 2) * TW; i += 256) {
+        const int rr = i / TW, cc = i - rr * TW;
+        const int hh = h0 + rr - 1, ww = cc - 1;
+        tile[i] = (hh >= 0 && hh < H && ww >= 0 && ww < W) ? __ldg(xi + hh * W + ww) : 0.f;
+    }
+    if (t < 64) { red[0][t] = 0.f; red[1][t] = 0.f; }
+    const int cg = (t & 15) * 4;
+    float wr[9][4], sc[4], sh[4];
 #pragma unroll
     for (int tap = 0; tap < 9; ++tap) {
-        const float4 a = *reinterpret_cast<const float4*>(Wimg + tap * 64 + cg);
-        const float4 b = *reinterpret_cast<const float4*>(Wimg + tap * 64 + cg + 4);
+        const float4 a = __ldg(reinterpret_cast<const float4*>(Wimg + tap * 64 + cg));
         wr[tap][0] = a.x; wr[tap][1] = a.y; wr[tap][2] = a.z; wr[tap][3] = a.w;
-        wr[tap][4] = b.x; wr[tap][5] = b.y; wr[tap][6] = b.z; wr[tap][7] = b.w;
     }
 #pragma unroll
-    for (int j = 0; j < 8; ++j) {
+    for (int j = 0; j < 4; ++j) {
         sc[j] = scale ? scale[cg + j] : 1.f;
         sh[j] = shift ? shift[cg + j] : 0.f;
     }
-    if (stats) {
-        if (t < 64) { red[0][t] = 0.f; red[1][t] = 0.f; }
-        __syncthreads();
-    }
-    const long long total = (long long)g.N * HW;
-    float s1[8], s2[8];
-#pragma unroll
-    for (int j = 0; j < 8; ++j) { s1[j] = 0.f; s2[j] = 0.f; }
-    const long long pbeg = (long long)blockIdx.x * CONV1_PIX_PER_BLOCK;
-    for (long long pix = pbeg + (t >> 3); pix < pbeg + CONV1_PIX_PER_BLOCK && pix < total; pix += 32) {
-        const int n = (int)(pix >> 10);
-        const int rem = (int)(pix & (HW - 1));
-        const int h = rem >> 5, w = rem & 31;
-        const float* xi = x + (long long)n * HW;
+    const int trow = ts ? (ts[n] - 1) : (t_fixed - 1);
+    const float* erow = Ecls + (long long)trow * 9 * 64 + cg;
+    __syncthreads();
+    float s1[4] = {0.f, 0.f, 0.f, 0.f}, s2[4] = {0.f, 0.f, 0.f, 0.f};
+    TA* obase = out.p + ((long long)(n * (H + 1) + 1 + h0) * (W + 2) + 1) * out.cs + cg;
+#pragma unroll 2
+    for (int lp = (t >> 4); lp < CONV1_PIX_PER_BLOCK; lp += 16) {
+        const int hl = lp >> 5, w = lp & 31, h = h0 + hl;
+        const float* tp = tile + hl * TW + w;
         float xv[9];
 #pragma unroll
-        for (int tap = 0; tap < 9; ++tap) {
-            const int hh = h + tap / 3 - 1, ww = w + tap % 3 - 1;
-            xv[tap] = (hh >= 0 && hh < H && ww >= 0 && ww < W) ? __ldg(xi + hh * W + ww) : 0.f;
-        }
+        for (int tap = 0; tap < 9; ++tap) xv[tap] = tp[(tap / 3) * TW + (tap % 3)];
         const int cls = (h == 0 ? 0 : (h == H - 1 ? 2 : 1)) * 3 + (w == 0 ? 0 : (w == W - 1 ? 2 : 1));
-        const int trow = ts ? (ts[n] - 1) : (t_fixed - 1);
-        const float* e = Ecls + ((long long)trow * 9 + cls) * 64 + cg;
-        const float4 e0 = __ldg(reinterpret_cast<const float4*>(e));
-        const float4 e1 = __ldg(reinterpret_cast<const float4*>(e + 4));
-        const float ev[8] = {e0.x, e0.y, e0.z, e0.w, e1.x, e1.y, e1.z, e1.w};
-        float o[8];
+        const float4 e4 = __ldg(reinterpret_cast<const float4*>(erow + cls * 64));
+        const float ev[4] = {e4.x, e4.y, e4.z, e4.w};
+        float o[4];
 #pragma unroll
-        for (int j = 0; j < 8; ++j) {
-            float acc = 0.f;
+        for (int j = 0; j < 4; ++j) {
+            float acc = ev[j];
 #pragma unroll
             for (int tap = 0; tap < 9; ++tap) acc = fmaf(xv[tap], wr[tap][j], acc);
-            const float v = (acc + ev[j]) * sc[j] + sh[j];
+            const float v = acc * sc[j] + sh[j];
             s1[j] += v; s2[j] = fmaf(v, v, s2[j]);
             o[j] = relu ? fmaxf(v, 0.f) : v;
         }
-        V8<TA>::st(out.p + ((long long)(n * (H + 1) + 1 + h) * (W + 2) + (w + 1)) * out.cs + cg, o);
+        st4<TA>(obase + (long long)(hl * (W + 2) + w) * out.cs, o);
     }
     if (stats) {
 #pragma unroll
-        for (int j = 0; j < 8; ++j) { atomicAdd(&red[0][cg + j], s1[j]); atomicAdd(&red[1][cg + j], s2[j]); }
+        for (int j = 0; j < 4; ++j) { atomicAdd(&red[0][cg + j], s1[j]); atomicAdd(&red[1][cg + j], s2[j]); }
         __syncthreads();
         if (t < 64) { atomicAdd(&stats[t], (double)red[0][t]); atomicAdd(&stats[64 + t], (double)red[1][t]); }
     }
@@ -658,6 +679,25 @@ pool_bwd_merge_kernel(View<const TA> a, View<const TG> dskip, View<const TG> dpo
 // ------------------------------------------------------------------------------------ backward of the first conv
 // One block per image.  For the image channel:  Tw[n][tap][co] = sum_p dy[p][co]*x[p+shift(tap)]
 // For the folded embedding channels: class sums Ccls[n][cls][co] = sum_{p in border class} dy[p][co]
+template <typename T> __device__ __forceinline__ void ld4(const T* p, float o[4]);
+template <> __device__ __forceinline__ void ld4<float>(const float* p, float o[4]) {
+    const float4 v = *reinterpret_cast<const float4*>(p);
+    o[0] = v.x; o[1] = v.y; o[2] = v.z; o[3] = v.w;
+}
+template <> __device__ __forceinline__ void ld4<__half>(const __half* p, float o[4]) {
+    const uint2 v = *reinterpret_cast<const uint2*>(p);
+    const __half2* h = reinterpret_cast<const __half2*>(&v);
+    const float2 a = __half22float2(h[0]), b = __half22float2(h[1]);
+    o[0] = a.x; o[1] = a.y; o[2] = b.x; o[3] = b.y;
+}
+template <> __device__ __forceinline__ void ld4<__nv_bfloat16>(const __nv_bfloat16* p, float o[4]) {
+    const uint2 v = *reinterpret_cast<const uint2*>(p);
+    const __nv_bfloat162* h = reinterpret_cast<const __nv_bfloat162*>(&v);
+    const float2 a = __bfloat1622float2(h[0]), b = __bfloat1622float2(h[1]);
+    o[0] = a.x; o[1] = a.y; o[2] = b.x; o[3] = b.y;
+}
+
+// 16 lanes x 4 channels per pixel, 16 pixels per pass (72 accumulators per thread instead of 144)
 template <typename TG>
 __global__ void __launch_bounds__(256)
 l1_bwd_kernel(View<const TG> dy, Geo g, const float* __restrict__ x, float* __restrict__ Tw, float* __restrict__ Ccls) {
@@ -665,37 +705,45 @@ l1_bwd_kernel(View<const TG> dy, Geo g, const float* __restrict__ x, float* __re
     const int t = threadIdx.x, n = blockIdx.x;
     for (int i = t; i < 576; i += 256) { tw_s[i] = 0.f; cl_s[i] = 0.f; }
     __syncthreads();
-    const int H = g.H, W = g.W;
-    const int c0 = (t & 7) * 8, pl = t >> 3;
+    const int H = g.H, W = g.W, TW = W + 2;
+    const int c0 = (t & 15) * 4, pl = t >> 4;
     const float* xi = x + (long long)n * H * W;
-    float tw[9][8], cl[9][8];
+    // zero-padded image window in shared memory: taps become unconditional broadcast loads
+    __shared__ float tile[34 * 34];
+    for (int i = t; i < (H + 2) * TW; i += 256) {
+        const int rr = i / TW, cc = i - rr * TW;
+        const int hh = rr - 1, ww = cc - 1;
+        tile[i] = (hh >= 0 && hh < H && ww >= 0 && ww < W) ? xi[hh * W + ww] : 0.f;
+    }
+    __syncthreads();
+    float tw[9][4], cl[9][4];
 #pragma unroll
     for (int a = 0; a < 9; ++a)
 #pragma unroll
-        for (int j = 0; j < 8; ++j) { tw[a][j] = 0.f; cl[a][j] = 0.f; }
-    for (int pix = pl; pix < H * W; pix += 32) {
+        for (int j = 0; j < 4; ++j) { tw[a][j] = 0.f; cl[a][j] = 0.f; }
+    for (int pix = pl; pix < H * W; pix += 16) {
         int h = pix / W, w = pix - h * W;
-        float d[8];
-        V8<TG>::ld(dy.p + g.pos(n, h, w) * dy.cs + c0, d);
+        float d[4];
+        ld4<TG>(dy.p + g.pos(n, h, w) * dy.cs + c0, d);
         int cls = (h == 0 ? 0 : (h == H - 1 ? 2 : 1)) * 3 + (w == 0 ? 0 : (w == W - 1 ? 2 : 1));
 #pragma unroll
         for (int a = 0; a < 9; ++a) {
             const float m = (a == cls) ? 1.f : 0.f;
 #pragma unroll
-            for (int j = 0; j < 8; ++j) cl[a][j] = fmaf(m, d[j], cl[a][j]);
+            for (int j = 0; j < 4; ++j) cl[a][j] = fmaf(m, d[j], cl[a][j]);
         }
+        const float* tp = tile + h * TW + w;
 #pragma unroll
         for (int tap = 0; tap < 9; ++tap) {
-            int hh = h + tap / 3 - 1, ww = w + tap % 3 - 1;
-            float xv = (hh >= 0 && hh < H && ww >= 0 && ww < W) ? xi[hh * W + ww] : 0.f;
+            const float xv = tp[(tap / 3) * TW + (tap % 3)];
 #pragma unroll
-            for (int j = 0; j < 8; ++j) tw[tap][j] = fmaf(d[j], xv, tw[tap][j]);
+            for (int j = 0; j < 4; ++j) tw[tap][j] = fmaf(d[j], xv, tw[tap][j]);
         }
     }
 #pragma unroll
     for (int tap = 0; tap < 9; ++tap)
 #pragma unroll
-        for (int j = 0; j < 8; ++j) {
+        for (int j = 0; j < 4; ++j) {
             atomicAdd(&tw_s[tap * 64 + c0 + j], tw[tap][j]);
             atomicAdd(&cl_s[tap * 64 + c0 + j], cl[tap][j]);
         }

@@ -515,6 +515,23 @@ int ddpm_time_kernel(ddpm_handle* h, const char* name, int64_t n_images, int ite
             }));
             // reads a10 (64 ch) + x, writes x; z is generated in registers
             by = (double)N * HW * (64.0 * e.esz_a() + 8.0);
+        } else if (k == "conv1" || k == "pool" || k == "up2") {
+            DDPM_DISPATCH(e.prec, time_it([&] {
+                if (k == "conv1") {
+                    long long pixels = (long long)N * HW;
+                    conv1_kernel<TA><<<cdiv(pixels, CONV1_PIX_PER_BLOCK), 256, 0, e.stream>>>(
+                        s.x.as<float>(), nullptr, e.T / 2, e.Wimg, e.Ecls, e.inf_scale[1], e.inf_shift[1], 1, s.a[1].view<TA>(),
+                        s.a[1].g, nullptr);
+                } else if (k == "pool") {
+                    long long work = (long long)N * 16 * 16 * 8;
+                    bn_apply_pool_kernel<TA><<<cdiv(work, 256), 256, 0, e.stream>>>(s.a[2].cview<TA>(), s.a[2].view<TA>(),
+                                                                                  s.p1.view<TA>(), s.a[2].g, s.p1.g, 64, nullptr,
+                                                                                  nullptr);
+                } else {
+                    tc::up2<TA>(e.stream, s.a[6].pos0<TA>(), (const TA*)e.Wt, s.u.pos0<TA>(), s.a[6].g, s.u.g, e.arr(kUpB));
+                }
+            }));
+            by = (double)N * HW * 64.0 * e.esz_a();
         } else if (k.rfind("conv_l", 0) == 0) {
             int l = std::atoi(k.c_str() + 6);
             DDPM_CHECK(l >= 2 && l <= NUM_CONV, "conv layer index must be 2..10");
