@@ -103,16 +103,54 @@ __device__ __forceinline__ void prefetch_tmap(const CUtensorMap* map) {
     asm volatile("prefetch.tensormap [%0];" ::"l"(map) : "memory");
 }
 
-template <int COLS>
+// ---- CTA-pair (cta_group::2) plumbing: the two CTAs of a cluster run one M=256 MMA stream issued by rank 0
+__device__ __forceinline__ uint32_t cluster_ctarank() {
+    uint32_t r;
+    asm volatile("mov.u32 %0, %%cluster_ctarank;" : "=r"(r));
+    return r;
+}
+__device__ __forceinline__ void cluster_sync_all() {
+    asm volatile("barrier.cluster.arrive.release.aligned;" ::: "memory");
+    asm volatile("barrier.cluster.wait.acquire.aligned;" ::: "memory");
+}
+// shared::cluster address of the same shared-memory offset in CTA `rank` of this cluster
+__device__ __forceinline__ uint32_t map_to_cta(uint32_t saddr, uint32_t rank) {
+    uint32_t r;
+    asm volatile("mapa.shared::cluster.u32 %0, %1, %2;" : "=r"(r) : "r"(saddr), "r"(rank));
+    return r;
+}
+__device__ __forceinline__ void mbar_arrive_cluster(uint32_t bar_cluster_addr) {
+    // default semantics (.release.cta) on purpose: a cluster-scope release would first drain this thread's outstanding
+    // global stores of the previous tile (~1.5k cycles per tile measured); the TMEM hand-over it guards is ordered by
+    // tcgen05.wait::ld + tcgen05.fence::before_thread_sync, not by the memory model
+    asm volatile("mbarrier.arrive.shared::cluster.b64 _, [%0];" ::"r"(bar_cluster_addr) : "memory");
+}
+// TMA load into THIS CTA's shared memory whose byte count is credited to an mbarrier that may live in the peer CTA
+__device__ __forceinline__ void tma_load_2d_pair(uint32_t dst, const CUtensorMap* map, int c0, int c1, uint32_t bar_cluster_addr) {
+    asm volatile(
+        "cp.async.bulk.tensor.2d.cta_group::2.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4}], [%2];"
+        ::"r"(dst), "l"(map), "r"(bar_cluster_addr), "r"(c0), "r"(c1)
+        : "memory");
+}
+
+template <int COLS, int CG = 1>
 __device__ __forceinline__ void tmem_alloc(uint32_t dst_smem) {
     uint32_t ncols = COLS;
-    asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(dst_smem), "r"(ncols) : "memory");
-    asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+    if constexpr (CG == 1) {
+        asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(dst_smem), "r"(ncols) : "memory");
+        asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+    } else {
+        asm volatile("tcgen05.alloc.cta_group::2.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(dst_smem), "r"(ncols) : "memory");
+        asm volatile("tcgen05.relinquish_alloc_permit.cta_group::2.sync.aligned;" ::: "memory");
+    }
 }
-template <int COLS>
+template <int COLS, int CG = 1>
 __device__ __forceinline__ void tmem_dealloc(uint32_t taddr) {
     uint32_t ncols = COLS;
-    asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(taddr), "r"(ncols) : "memory");
+    if constexpr (CG == 1)
+        asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(taddr), "r"(ncols) : "memory");
+    else
+        asm volatile("tcgen05.dealloc.cta_group::2.sync.aligned.b32 %0, %1;" ::"r"(taddr), "r"(ncols) : "memory");
 }
 // D[tmem] (+)= A[smem] * B[smem], single-CTA, kind::f16 (FP16/BF16 inputs, FP32 accumulate)
 __device__ __forceinline__ void umma_f16(uint32_t d_tmem, uint64_t a_desc, uint64_t b_desc, uint32_t idesc, uint32_t accumulate) {
@@ -124,20 +162,41 @@ __device__ __forceinline__ void umma_f16(uint32_t d_tmem, uint64_t a_desc, uint6
         : "memory");
 }
 // same, descriptors passed as (lo, hi) halves so that advancing the start address is one 32-bit add
+template <int CG = 1>
 __device__ __forceinline__ void umma_f16_lh(uint32_t d_tmem, uint32_t a_lo, uint32_t b_lo, uint32_t desc_hi, uint32_t idesc,
                                             uint32_t accumulate) {
-    asm volatile(
-        "{\n\t.reg .pred p;\n\t.reg .b64 da, db;\n\t"
-        "mov.b64 da, {%1, %3};\n\t"
-        "mov.b64 db, {%2, %3};\n\t"
-        "setp.ne.b32 p, %5, 0;\n\t"
-        "tcgen05.mma.cta_group::1.kind::f16 [%0], da, db, %4, p;\n\t}"
-        ::"r"(d_tmem), "r"(a_lo), "r"(b_lo), "r"(desc_hi), "r"(idesc), "r"(accumulate)
-        : "memory");
+    if constexpr (CG == 1) {
+        asm volatile(
+            "{\n\t.reg .pred p;\n\t.reg .b64 da, db;\n\t"
+            "mov.b64 da, {%1, %3};\n\t"
+            "mov.b64 db, {%2, %3};\n\t"
+            "setp.ne.b32 p, %5, 0;\n\t"
+            "tcgen05.mma.cta_group::1.kind::f16 [%0], da, db, %4, p;\n\t}"
+            ::"r"(d_tmem), "r"(a_lo), "r"(b_lo), "r"(desc_hi), "r"(idesc), "r"(accumulate)
+            : "memory");
+    } else {
+        // M = 256 over the CTA pair: each CTA supplies its own 128 A rows and half of the B rows (same smem offsets)
+        asm volatile(
+            "{\n\t.reg .pred p;\n\t.reg .b64 da, db;\n\t"
+            "mov.b64 da, {%1, %3};\n\t"
+            "mov.b64 db, {%2, %3};\n\t"
+            "setp.ne.b32 p, %5, 0;\n\t"
+            "tcgen05.mma.cta_group::2.kind::f16 [%0], da, db, %4, p;\n\t}"
+            ::"r"(d_tmem), "r"(a_lo), "r"(b_lo), "r"(desc_hi), "r"(idesc), "r"(accumulate)
+            : "memory");
+    }
 }
 // arrive on an mbarrier when all previously issued tcgen05.mma of this thread have completed
+// (CG == 2: the arrival is multicast to the barrier at the same offset in both CTAs of the pair)
+template <int CG = 1>
 __device__ __forceinline__ void umma_commit(uint32_t bar) {
-    asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(bar) : "memory");
+    if constexpr (CG == 1) {
+        asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(bar) : "memory");
+    } else {
+        const uint16_t mask = 3;
+        asm volatile("tcgen05.commit.cta_group::2.mbarrier::arrive::one.shared::cluster.multicast::cluster.b64 [%0], %1;"
+                     ::"r"(bar), "h"(mask) : "memory");
+    }
 }
 // 32 lanes x 16 consecutive 32-bit columns -> 16 registers per thread (thread i <-> lane base+i)
 __device__ __forceinline__ void tmem_ld16(uint32_t taddr, uint32_t r[16]) {
@@ -173,7 +232,8 @@ __host__ __device__ constexpr uint32_t make_idesc(uint32_t fmt, uint32_t M, uint
 }
 
 // ------------------------------------------------------------------------------------ kernel
-constexpr int TC_THREADS = 224;   // warp 0 TMA, warps 1 and 6 MMA issuers (even / odd tiles), warps 2..5 epilogue
+// warp 0 TMA, warps 1 and 6 MMA issuers (even / odd tiles), warps 2..5 and 7..10 epilogue sets (even / odd tiles)
+constexpr int TC_THREADS = 352;
 constexpr int TC_BM = 128;
 
 template <typename TOut>
@@ -243,23 +303,66 @@ struct TcParams {
 //          x <- sqrt(a_prev)*clamp((x - sigma*eps_hat)/sqrt(a_t)) + sqrt(pv)*z   (generate_images.jl:196-208)
 // TMAST: 1 = epilogue stages the tile in swizzled shared memory and writes it with a TMA store
 // (halo rows are written as zeros, which is what they must hold), 0 = predicated 16-byte stores.
-template <int TAPS, int CHUNKS, int NOUT, int WP, int STAGES, int EPI, int TMAST, typename TIn, typename TOut>
+// ---- shared-memory plan (shared by the kernel and its launcher)
+// slab stages that fit next to the resident weights and `extra` bytes of epilogue staging
+template <int TAPS, int CHUNKS, int NOUT, int WP, int CG>
+constexpr int stages_for(int extra) {
+    constexpr int HALO = (TAPS == 9) ? (WP + 1) : 0;
+    constexpr int R = ((TC_BM + 2 * HALO + 7) / 8) * 8;
+    const int budget = 227 * 1024 - 1024 /*align*/ - 1024 /*barriers, shift*/ - TAPS * CHUNKS * (NOUT / CG) * 128 - extra;
+    if (budget <= 0) return 0;
+    int s = budget / (R * 128);
+    if (s > 8) s = 8;
+    // CTA pairs: prefer a ring the two issuer warps can split (see DUAL in the kernel) over one more stage
+    if (CG == 2 && s >= 2 * CHUNKS) s = (s / (2 * CHUNKS)) * (2 * CHUNKS);
+    return s;
+}
+// channels per pass of the per-warp store staging (direct-store epilogues): every epilogue warp transposes its
+// 32 rows x STC channels through a private shared-memory patch so that a store instruction writes whole 128-byte
+// (STC=64) or 64-byte (STC=32) row segments instead of 32 scattered 16-byte pieces.  0 = no room, direct stores.
+template <int TAPS, int CHUNKS, int NOUT, int WP, int EPI, int TMAST, int CG>
+constexpr int stage_cols() {
+    if (TMAST || EPI == 2) return 0;
+    const int full = stages_for<TAPS, CHUNKS, NOUT, WP, CG>(0);
+    const int want = full < 4 ? full : 4;
+    if (stages_for<TAPS, CHUNKS, NOUT, WP, CG>(8 * 32 * 64 * 2) >= want) return 64;
+    if (stages_for<TAPS, CHUNKS, NOUT, WP, CG>(8 * 32 * 32 * 2) >= want) return 32;
+    return 0;
+}
+template <int TAPS, int CHUNKS, int NOUT, int WP, int EPI, int TMAST, int CG>
+constexpr int epi_smem_bytes() {
+    return TMAST ? 2 * TC_BM * NOUT * 2 : 8 * 32 * stage_cols<TAPS, CHUNKS, NOUT, WP, EPI, TMAST, CG>() * 2;
+}
+template <int TAPS, int CHUNKS, int NOUT, int WP, int EPI, int TMAST, int CG = 1>
+constexpr int pick_stages() {
+    return stages_for<TAPS, CHUNKS, NOUT, WP, CG>(epi_smem_bytes<TAPS, CHUNKS, NOUT, WP, EPI, TMAST, CG>());
+}
+
+// CG: 1 = one CTA per 128-position tile; 2 = CTA pair (cluster of 2, tcgen05 cta_group::2): the pair works on 256
+// consecutive positions, each CTA stages its own 128-position slab and HALF of the weight rows (NOUT/2 output
+// channels); rank 0 issues M=256 MMAs that read both CTAs' shared memory, each CTA's TMEM receives all NOUT columns
+// of its own 128 positions.  Per SM and MMA the shared-memory operand traffic drops from 4 KB + NOUT*32 B to
+// 4 KB + NOUT*16 B, and 128 => 128 layers no longer need the Cout split that re-read every slab twice.
+template <int TAPS, int CHUNKS, int NOUT, int WP, int STAGES, int EPI, int TMAST, int CG, typename TIn, typename TOut>
 __global__ void __launch_bounds__(TC_THREADS, 1)
 conv_tc_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constant__ CUtensorMap tmA1,
                const __grid_constant__ CUtensorMap tmW, const __grid_constant__ CUtensorMap tmO, const TcParams p) {
     constexpr int HALO = (TAPS == 9) ? (WP + 1) : 0;
     constexpr int R = ((TC_BM + 2 * HALO + 7) / 8) * 8;       // slab rows (multiple of 8 -> 1024 B multiple)
     constexpr uint32_t A_STAGE_BYTES = R * 128;
-    constexpr uint32_t W_TILE_BYTES = NOUT * 128;              // one (tap, chunk) weight tile [NOUT][64]
+    constexpr int NB = NOUT / CG;                              // weight rows (output channels) staged by this CTA
+    constexpr uint32_t W_TILE_BYTES = NB * 128;                // one (tap, chunk) weight tile [NB][64]
     constexpr uint32_t W_BYTES = TAPS * CHUNKS * W_TILE_BYTES;
     constexpr int ACC_BUFS = 4;                                // accumulator ring in TMEM (decouples MMA and epilogue)
     constexpr bool DUAL = (STAGES % (2 * CHUNKS)) == 0;        // two MMA issuer warps only if stages stay warp-private
     constexpr int TMEM_COLS = (ACC_BUFS * NOUT <= 256) ? 256 : 512;
-    constexpr uint32_t IDESC = make_idesc(IsBf16<TIn>::v, TC_BM, NOUT);
+    constexpr uint32_t IDESC = make_idesc(IsBf16<TIn>::v, TC_BM * CG, NOUT);
 
     extern __shared__ uint8_t smem_raw[];
     uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
-    constexpr uint32_t O_BYTES = TMAST ? 2u * TC_BM * NOUT * 2u : 0u;   // two staging tiles [128][NOUT] (16-bit)
+    // epilogue staging: TMAST -> two tiles [128][NOUT] (one per epilogue set); else 8 per-warp patches [32][STC]
+    constexpr int STC = stage_cols<TAPS, CHUNKS, NOUT, WP, EPI, TMAST, CG>();
+    constexpr uint32_t O_BYTES = (uint32_t)epi_smem_bytes<TAPS, CHUNKS, NOUT, WP, EPI, TMAST, CG>();
     const uint32_t s_w = smem_u32(smem);
     const uint32_t s_a = s_w + W_BYTES;
     const uint32_t s_o = s_a + STAGES * A_STAGE_BYTES;
@@ -279,16 +382,20 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constant__
     long long dbg_acc[8] = {0, 0, 0, 0, 0, 0, 0, 0};
     const long long t_kernel0 = p.dbg ? clock64() : 0;
     const int n_blk = blockIdx.y;                 // N-slice (conv: half of Cout; up2: sub-position q)
+    const uint32_t rank = (CG == 2) ? cluster_ctarank() : 0u;     // position half / weight-row half inside the CTA pair
+    const bool leader = (rank == 0);
+    const int unit = blockIdx.x / CG, n_units = gridDim.x / CG;   // persistent work unit = CTA (CG 1) or CTA pair (CG 2)
+    const int num_units_tiles = (p.num_m_tiles + CG - 1) / CG;    // tiles of CG*128 positions
 
     if (warp == 0 && lane == 0) {
         prefetch_tmap(&tmA0); prefetch_tmap(&tmW);
         if (p.chunk1_src1) prefetch_tmap(&tmA1);
         mbar_init(bar_w(), 1);
         for (int s = 0; s < STAGES; ++s) { mbar_init(bar_afull(s), 1); mbar_init(bar_aempty(s), 1); }
-        for (int b = 0; b < ACC_BUFS; ++b) { mbar_init(bar_accfull(b), 1); mbar_init(bar_accempty(b), 4); }
+        for (int b = 0; b < ACC_BUFS; ++b) { mbar_init(bar_accfull(b), 1); mbar_init(bar_accempty(b), 4 * CG); }
         fence_barrier_init();
     }
-    if (warp == 2) tmem_alloc<TMEM_COLS>(smem_u32(tmem_slot));
+    if (warp == 2) tmem_alloc<TMEM_COLS, CG>(smem_u32(tmem_slot));
     if (threadIdx.x >= 64 && threadIdx.x < 64 + NOUT) {
         const int c = threadIdx.x - 64;
         const int co = (EPI == 1) ? c : (n_blk * NOUT + c);
@@ -297,22 +404,32 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constant__
     }
     if (warp == 0 && lane == 0 && TMAST) prefetch_tmap(&tmO);
     tc_fence_before();
-    __syncthreads();
+    if (CG == 2) cluster_sync_all();          // the peer's barriers must be initialised before anything signals them
+    else __syncthreads();
     tc_fence_after();
     const uint32_t tmem_base = *tmem_slot;
+    // barriers that collect contributions of both CTAs live in the leader (rank 0)
+    auto lead = [&](uint32_t bar) { return (CG == 2) ? map_to_cta(bar, 0) : bar; };
 
     if (warp == 0) {
         // ================= TMA producer (warp-uniform loop, one elected lane issues) =================
         if (elect_one()) {
-            mbar_expect_tx(bar_w(), W_BYTES);
+            if (leader) mbar_expect_tx(bar_w(), W_BYTES * CG);
+            const uint32_t bw = lead(bar_w());
             for (int t = 0; t < TAPS; ++t)
-                for (int c = 0; c < CHUNKS; ++c)
-                    tma_load_2d(s_w + (t * CHUNKS + c) * W_TILE_BYTES, &tmW, (t * CHUNKS + c) * 64, n_blk * NOUT, bar_w());
+                for (int c = 0; c < CHUNKS; ++c) {
+                    if (CG == 2)
+                        tma_load_2d_pair(s_w + (t * CHUNKS + c) * W_TILE_BYTES, &tmW, (t * CHUNKS + c) * 64,
+                                         n_blk * NOUT + (int)rank * NB, bw);
+                    else
+                        tma_load_2d(s_w + (t * CHUNKS + c) * W_TILE_BYTES, &tmW, (t * CHUNKS + c) * 64, n_blk * NOUT, bw);
+                }
         }
         __syncwarp();
         int stage = 0;
         uint32_t phase = 0;
-        for (int tile = blockIdx.x; tile < p.num_m_tiles; tile += gridDim.x) {
+        for (int ut = unit; ut < num_units_tiles; ut += n_units) {
+            const int tile = ut * CG + (int)rank;
             const int row0 = tile * TC_BM - HALO + p.g.guard;   // row coordinate in the tensor map (base = allocation start)
 #pragma unroll
             for (int c = 0; c < CHUNKS; ++c) {
@@ -320,15 +437,19 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constant__
                 mbar_wait(bar_aempty(stage), phase ^ 1);
                 if (p.dbg) dbg_acc[0] += clock64() - t0;
                 if (elect_one()) {
-                    mbar_expect_tx(bar_afull(stage), A_STAGE_BYTES);
+                    if (leader) mbar_expect_tx(bar_afull(stage), A_STAGE_BYTES * CG);
                     const bool second = (c == 1) && p.chunk1_src1;
-                    tma_load_2d(s_a + stage * A_STAGE_BYTES, second ? &tmA1 : &tmA0, second ? 0 : c * 64, row0, bar_afull(stage));
+                    if (CG == 2)
+                        tma_load_2d_pair(s_a + stage * A_STAGE_BYTES, second ? &tmA1 : &tmA0, second ? 0 : c * 64, row0,
+                                         lead(bar_afull(stage)));
+                    else
+                        tma_load_2d(s_a + stage * A_STAGE_BYTES, second ? &tmA1 : &tmA0, second ? 0 : c * 64, row0, bar_afull(stage));
                 }
                 __syncwarp();
                 if (++stage == STAGES) { stage = 0; phase ^= 1; }
             }
         }
-    } else if (warp == 1 || (warp == 6 && DUAL)) {
+    } else if ((warp == 1 || (warp == 6 && DUAL)) && leader) {
         // ================= MMA issuers (warp-uniform loops, one elected lane issues) =================
         // Two issuer warps alternate tiles (warp 1: even, warp 6: odd tiles of this CTA).  The tensor pipe's
         // instruction queue is shallow, so a single issuer drains it during every mbarrier wait (~150 cycles
@@ -343,7 +464,7 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constant__
         constexpr uint32_t DESC_HI = (1024u >> 4) | (1u << 14) | (2u << 29);
         const uint32_t a_lo_base = ((s_a & 0x3FFFFu) >> 4) | (1u << 16);
         const uint32_t b_lo_base = ((s_w & 0x3FFFFu) >> 4) | (1u << 16);
-        for (int seq = parity, tile = blockIdx.x + parity * gridDim.x; tile < p.num_m_tiles; seq += NISS, tile += NISS * gridDim.x) {
+        for (int seq = parity, ut = unit + parity * n_units; ut < num_units_tiles; seq += NISS, ut += NISS * n_units) {
             const int buf = seq % ACC_BUFS;
             const uint32_t acc_phase = (uint32_t)(seq / ACC_BUFS) & 1u;
             long long t0 = p.dbg ? clock64() : 0;
@@ -367,66 +488,84 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constant__
                         const int shift = (TAPS == 9) ? (HALO + (t / 3 - 1) * WP + (t % 3 - 1)) : 0;
 #pragma unroll
                         for (int ks = 0; ks < 4; ++ks) {
-                            umma_f16_lh(d_tmem, a_lo + ((shift * 128 + ks * 32) >> 4),
-                                        b_lo_base + (((t * CHUNKS + c) * W_TILE_BYTES + ks * 32) >> 4), DESC_HI, IDESC,
-                                        (c | t | ks) ? 1u : 0u);
+                            umma_f16_lh<CG>(d_tmem, a_lo + ((shift * 128 + ks * 32) >> 4),
+                                            b_lo_base + (((t * CHUNKS + c) * W_TILE_BYTES + ks * 32) >> 4), DESC_HI, IDESC,
+                                            (c | t | ks) ? 1u : 0u);
                         }
                     }
-                    umma_commit(bar_aempty(stage));                       // slab reusable once these MMAs retire
-                    if (c == CHUNKS - 1) umma_commit(bar_accfull(buf));   // accumulator ready for the epilogue
+                    umma_commit<CG>(bar_aempty(stage));                       // slab reusable once these MMAs retire
+                    if (c == CHUNKS - 1) umma_commit<CG>(bar_accfull(buf));   // accumulator ready for the epilogue
                 }
                 __syncwarp();
                 if (p.dbg) dbg_acc[3] += clock64() - t0;
             }
+            dbg_acc[7] += 1;
         }
-    } else if (warp == 6) {
-        // second issuer warp unused in this configuration (single-issuer mode)
+    } else if (warp == 1 || warp == 6) {
+        // issuer warps without work: second issuer in single-issuer mode, both issuers of the non-leader CTA of a pair
     } else {
         // ================= epilogue warps (TMEM -> registers -> global) =================
+        // Two sets of four warps (2..5 and 7..10) take alternate tiles: one tile's epilogue is a ~2.5k-cycle latency
+        // chain (accumulator wait, tcgen05.ld round trips, staging-tile hand-over to the TMA store), so a single set
+        // caps the CTA at one tile per chain; two sets overlap the chains of consecutive tiles.
+        const int eset = (warp >= 7) ? 1 : 0;
         const int lane_grp = warp & 3;                       // TMEM lanes 32*lane_grp .. +31 are visible to this warp
         const int row = lane_grp * 32 + lane;
-        int buf = 0, obuf = 0;
-        uint32_t acc_phase = 0;
+        const bool store_thread = (threadIdx.x == (eset ? 224 : 64));     // first lane of the set: issues its TMA stores
         TOut* out = reinterpret_cast<TOut*>(p.out);
-        for (int tile = blockIdx.x; tile < p.num_m_tiles; tile += gridDim.x) {
-            const long long pos = (long long)tile * TC_BM + row;
-            int n_img, hh, ww;
-            const bool valid = p.g.decode(pos, n_img, hh, ww);
+        const uint32_t accempty_base = lead(bar_accempty(0));
+        const uint32_t stage_o = s_o + (uint32_t)eset * (TC_BM * NOUT * 2);     // this set's staging tile (TMAST)
+        const uint32_t wst = s_o + (uint32_t)(eset * 4 + lane_grp) * (32 * STC * 2);   // this warp's store patch (STC > 0)
+        const int npos = (int)p.g.npos;
+        for (int seq = eset, ut = unit + eset * n_units; ut < num_units_tiles; seq += 2, ut += 2 * n_units) {
+            const int buf = seq % ACC_BUFS;
+            const uint32_t acc_phase = (uint32_t)(seq / ACC_BUFS) & 1u;
+            const int tile = ut * CG + (int)rank;
+            // position -> (image, row, column) with compile-time divisors (square images: Hs = WP - 1)
+            const int pos = tile * TC_BM + row;
+            const int pr = pos / WP, pc = pos - pr * WP;
+            const int n_img = pr / (WP - 1), prr = pr - n_img * (WP - 1);
+            const int hh = prr - 1, ww = pc - 1;
+            const bool valid = pos < npos && prr != 0 && pc >= 1 && pc <= WP - 2 && n_img < p.g.N;
             long long opos = pos;
             int ch_off = n_blk * NOUT;
             if (EPI == 1) {
                 if (valid) opos = p.g_out.pos(n_img, 2 * hh + (n_blk >> 1), 2 * ww + (n_blk & 1));
                 ch_off = 0;
             }
+            const int oidx = valid ? (int)opos : -1;          // output row of this thread's position (staged stores)
             long long t0 = p.dbg ? clock64() : 0;
             mbar_wait(bar_accfull(buf), acc_phase);
             long long t1 = p.dbg ? clock64() : 0;
             if (p.dbg) dbg_acc[4] += t1 - t0;
             tc_fence_after();
             const uint32_t taddr = tmem_base + ((uint32_t)(lane_grp * 32) << 16) + buf * NOUT;
-            uint32_t stage_o = 0;
             float dot = 0.f;
             if (TMAST) {
-                // the TMA store that last read this staging tile (two tiles ago) must have drained it
-                stage_o = s_o + (uint32_t)obuf * (TC_BM * NOUT * 2);
-                if (threadIdx.x == 64) tma_store_wait_read<1>();
-                named_bar_sync(1, 128);
+                // the TMA store that last read this set's staging tile (two tiles ago) must have drained it
+                if (store_thread) tma_store_wait_read<0>();
+                named_bar_sync(1 + eset, 128);
             }
-            // all accumulator columns of this row in one round trip (NOUT/16 loads in flight, one wait), then the
-            // TMEM buffer is handed back to the MMA warp BEFORE the arithmetic / stores of the epilogue
-            uint32_t racc[NOUT / 16][16];
+            // 64 accumulator columns of this row per round trip (4 loads in flight, one wait); the TMEM buffer is handed
+            // back to the MMA warp right after the last load, BEFORE the arithmetic / stores of the epilogue
 #pragma unroll
-            for (int q = 0; q < NOUT / 16; ++q) tmem_ld16(taddr + q * 16, racc[q]);
-            tmem_ld_wait();
-            tc_fence_before();
-            __syncwarp();
-            if (lane == 0) mbar_arrive(bar_accempty(buf));
+            for (int cq = 0; cq < NOUT; cq += 64) {
+                uint32_t racc[4][16];
 #pragma unroll
-            for (int c0 = 0; c0 < NOUT; c0 += 32) {
+                for (int q = 0; q < 4; ++q) tmem_ld16(taddr + cq + q * 16, racc[q]);
+                tmem_ld_wait();
+                if (cq + 64 == NOUT) {
+                    tc_fence_before();
+                    __syncwarp();
+                    if (lane == 0) {
+                        if (CG == 2) mbar_arrive_cluster(accempty_base + 8u * buf);
+                        else mbar_arrive(bar_accempty(buf));
+                    }
+                }
 #pragma unroll
-                for (int half = 0; half < 2; ++half) {
-                    const uint32_t* r = racc[(c0 >> 4) + half];
-                    const int cb = c0 + half * 16;
+                for (int q = 0; q < 4; ++q) {
+                    const uint32_t* r = racc[q];
+                    const int cb = cq + q * 16;
                     float v[16];
 #pragma unroll
                     for (int j4 = 0; j4 < 4; ++j4) {
@@ -463,6 +602,38 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constant__
                                      "r"(qa.y), "r"(qa.z), "r"(qa.w) : "memory");
                         asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(rbase + (((ch + 1) ^ sw) << 4)), "r"(qb.x),
                                      "r"(qb.y), "r"(qb.z), "r"(qb.w) : "memory");
+                    } else if (STC > 0) {
+                        constexpr int STCX = STC > 0 ? STC : 64;               // (dead branch when STC == 0)
+                        // transpose through the warp's patch: row = lane, 16-byte chunks XOR-swizzled by row
+                        uint4 qa, qb;
+                        pack16<TOut>(v, qa, qb);
+                        constexpr int CPR = STCX / 8;                           // 16-byte chunks per patch row
+                        const uint32_t ch = (uint32_t)(cb % STCX) >> 3;          // even chunk index of these 16 channels
+                        const uint32_t sw = (STCX == 64) ? ((uint32_t)lane & 7u) : (((uint32_t)lane >> 1) & 3u);
+                        const uint32_t rbase = wst + (uint32_t)lane * (STCX * 2);
+                        asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(rbase + ((ch ^ sw) << 4)), "r"(qa.x),
+                                     "r"(qa.y), "r"(qa.z), "r"(qa.w) : "memory");
+                        asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(rbase + (((ch + 1) ^ sw) << 4)), "r"(qb.x),
+                                     "r"(qb.y), "r"(qb.z), "r"(qb.w) : "memory");
+                        if ((cb + 16) % STCX == 0) {
+                            // patch complete: CPR lanes per row write one contiguous row segment each
+                            __syncwarp();
+                            const int c_lo = cb + 16 - STCX;                      // first channel held by the patch
+                            const uint32_t cj = (uint32_t)lane % CPR;
+#pragma unroll
+                            for (int it = 0; it < CPR; ++it) {
+                                const int srow = it * (32 / CPR) + lane / CPR;
+                                const uint32_t ssw = (STCX == 64) ? ((uint32_t)srow & 7u) : (((uint32_t)srow >> 1) & 3u);
+                                uint4 val;
+                                asm volatile("ld.shared.v4.b32 {%0, %1, %2, %3}, [%4];"
+                                             : "=r"(val.x), "=r"(val.y), "=r"(val.z), "=r"(val.w)
+                                             : "r"(wst + (uint32_t)srow * (STCX * 2) + ((cj ^ ssw) << 4)));
+                                const int o = __shfl_sync(0xffffffffu, oidx, srow);
+                                if (o >= 0)
+                                    *reinterpret_cast<uint4*>(out + (long long)o * p.out_cs + ch_off + c_lo + cj * 8) = val;
+                            }
+                            __syncwarp();
+                        }
                     } else if (valid) {
                         store16<TOut>(out + opos * p.out_cs + ch_off + cb, v);
                     }
@@ -480,8 +651,8 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constant__
             }
             if (TMAST) {
                 fence_proxy_async();                 // generic-proxy smem writes -> visible to the TMA engine
-                named_bar_sync(1, 128);
-                if (threadIdx.x == 64) {
+                named_bar_sync(1 + eset, 128);
+                if (store_thread) {
 #pragma unroll
                     for (int hsel = 0; hsel < NOUT / 64; ++hsel)
                         tma_store_2d(&tmO, stage_o + hsel * (TC_BM * 128), n_blk * NOUT + hsel * 64, tile * TC_BM + p.g.guard);
@@ -489,22 +660,20 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constant__
                 }
             }
             if (p.dbg) { dbg_acc[5] += clock64() - t1; dbg_acc[6] += 1; }
-            obuf ^= 1;
-            if (++buf == ACC_BUFS) { buf = 0; acc_phase ^= 1; }
         }
     }
-    if (TMAST && threadIdx.x == 64) tma_store_wait_all();
+    if (TMAST && (threadIdx.x == 64 || threadIdx.x == 224)) tma_store_wait_all();
     if (p.dbg && lane == 0 && warp <= 2) {
         long long* d = p.dbg + (size_t)(blockIdx.y * gridDim.x + blockIdx.x) * 8;
-        if (warp == 0) d[0] = dbg_acc[0];
-        if (warp == 1) { d[1] = dbg_acc[1]; d[2] = dbg_acc[2]; d[3] = dbg_acc[3]; }
+        if (warp == 1) { d[0] = dbg_acc[7]; d[1] = dbg_acc[1]; d[2] = dbg_acc[2]; d[3] = dbg_acc[3]; }
         if (warp == 2) { d[4] = dbg_acc[4]; d[5] = dbg_acc[5]; d[6] = dbg_acc[6]; d[7] = clock64() - t_kernel0; }
     }
     tc_fence_before();
-    __syncthreads();
+    if (CG == 2) cluster_sync_all();          // neither CTA may retire (or free TMEM) while the pair's MMAs can still touch it
+    else __syncthreads();
     if (warp == 2) {
         tc_fence_after();
-        tmem_dealloc<TMEM_COLS>(tmem_base);
+        tmem_dealloc<TMEM_COLS, CG>(tmem_base);
     }
 }
 
@@ -522,6 +691,10 @@ struct State {
     int base_offset_mode = 0;
     bool enabled = true;
     bool tma_store = true;      // epilogue of the 64->64 @32x32 conv: TMA store via swizzled smem (1) or direct stores (0)
+    // bit set -> that layer shape runs as CTA pairs (cta_group::2):
+    // 1 = 128=>128 @16x16, 2 = 64=>64 @32x32 (incl. the fused sampler epilogue), 4 = 128=>64 @32x32 (concat),
+    // 8 = 64=>128 @16x16, 16 = the two data-gradient-only shapes (128=>64 @16x16, 64=>128 @32x32)
+    int pair_mask = 31;
 };
 inline State& state() {
     static State s;
@@ -579,26 +752,18 @@ CUtensorMap make_map_2d(const void* base, uint64_t rows, uint64_t cols, uint32_t
     return m;
 }
 
-template <int TAPS, int CHUNKS, int NOUT, int WP, int TMAST>
-constexpr int pick_stages() {
-    constexpr int HALO = (TAPS == 9) ? (WP + 1) : 0;
-    constexpr int R = ((TC_BM + 2 * HALO + 7) / 8) * 8;
-    constexpr int budget = 227 * 1024 - 1024 /*align*/ - 1024 /*barriers, shift*/ - TAPS * CHUNKS * NOUT * 128 -
-                           (TMAST ? 2 * TC_BM * NOUT * 2 : 0);
-    constexpr int s = budget / (R * 128);
-    return s > 8 ? 8 : s;
-}
-
-template <int TAPS, int CHUNKS, int NOUT, int WP, int EPI, int TMAST, typename TIn, typename TOut>
+template <int TAPS, int CHUNKS, int NOUT, int WP, int EPI, int TMAST, typename TIn, typename TOut, int CG = 1>
 void launch(cudaStream_t st, const CUtensorMap& a0, const CUtensorMap& a1, const CUtensorMap& w, const CUtensorMap& o,
             const TcParams& p, int n_blocks_y) {
-    constexpr int STAGES = pick_stages<TAPS, CHUNKS, NOUT, WP, TMAST>();
+    constexpr int STAGES = pick_stages<TAPS, CHUNKS, NOUT, WP, EPI, TMAST, CG>();
     static_assert(STAGES >= 2, "not enough shared memory for a 2-stage pipeline");
     constexpr int HALO = (TAPS == 9) ? (WP + 1) : 0;
     constexpr int R = ((TC_BM + 2 * HALO + 7) / 8) * 8;
-    constexpr size_t smem = 1024 + (size_t)TAPS * CHUNKS * NOUT * 128 + (size_t)STAGES * R * 128 +
-                            (TMAST ? 2 * TC_BM * NOUT * 2 : 0) + 1024;
-    auto kern = conv_tc_kernel<TAPS, CHUNKS, NOUT, WP, STAGES, EPI, TMAST, TIn, TOut>;
+    constexpr size_t smem = 1024 + (size_t)TAPS * CHUNKS * (NOUT / CG) * 128 + (size_t)STAGES * R * 128 +
+                            (size_t)epi_smem_bytes<TAPS, CHUNKS, NOUT, WP, EPI, TMAST, CG>() + 1024;
+    DDPM_CHECK(p.g.Wp == WP && p.g.Hs == WP - 1 && p.g.npos + 2 * TC_BM < (1ll << 31),
+               "conv_tc: geometry does not match the kernel's compile-time row width");
+    auto kern = conv_tc_kernel<TAPS, CHUNKS, NOUT, WP, STAGES, EPI, TMAST, CG, TIn, TOut>;
     static bool attr_set = false;
     if (!attr_set) {
         DDPM_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
@@ -607,8 +772,26 @@ void launch(cudaStream_t st, const CUtensorMap& a0, const CUtensorMap& a1, const
     int ctas_x = state().num_sms / n_blocks_y;
     if (ctas_x > p.num_m_tiles) ctas_x = p.num_m_tiles;
     if (ctas_x < 1) ctas_x = 1;
-    dim3 grid(ctas_x, n_blocks_y);
-    kern<<<grid, TC_THREADS, smem, st>>>(a0, a1, w, o, p);
+    if constexpr (CG == 1) {
+        dim3 grid(ctas_x, n_blocks_y);
+        kern<<<grid, TC_THREADS, smem, st>>>(a0, a1, w, o, p);
+    } else {
+        // CTA pairs: clusters of two along x (the hardware co-schedules them on the two SMs of a TPC)
+        ctas_x = ((ctas_x + 1) / 2) * 2;
+        if (ctas_x > state().num_sms / n_blocks_y) ctas_x -= 2;
+        if (ctas_x < 2) ctas_x = 2;
+        cudaLaunchConfig_t cfg{};
+        cfg.gridDim = dim3(ctas_x, n_blocks_y);
+        cfg.blockDim = dim3(TC_THREADS);
+        cfg.dynamicSmemBytes = smem;
+        cfg.stream = st;
+        cudaLaunchAttribute attr[1];
+        attr[0].id = cudaLaunchAttributeClusterDimension;
+        attr[0].val.clusterDim.x = 2; attr[0].val.clusterDim.y = 1; attr[0].val.clusterDim.z = 1;
+        cfg.attrs = attr;
+        cfg.numAttrs = 1;
+        DDPM_CUDA(cudaLaunchKernelEx(&cfg, kern, a0, a1, w, o, p));
+    }
     DDPM_LAUNCH_CHECK();
 }
 
@@ -635,25 +818,38 @@ bool conv3x3(cudaStream_t st, const TIn* s0, int C0, const TIn* s1, int C1, cons
     CUtensorMap a1 = a0;
     if (s1) a1 = make_map_2d<TIn>(s1 - (size_t)g.guard * C1, rows, C1, WP == 34 ? R32 : R16);
     if (WP == 34 && Cin == 64 && Cout == 64 && !s1) {
-        CUtensorMap w = make_map_2d<TIn>(Wt, 64, 9 * 64, 64);
+        const bool pair = (state().pair_mask & 2) != 0;
+        CUtensorMap w = make_map_2d<TIn>(Wt, 64, 9 * 64, pair ? 32 : 64);
         CUtensorMap o = make_map_2d<TOut>(out - (size_t)g.guard * Cout, rows, Cout, TC_BM);
-        if (state().tma_store) launch<9, 1, 64, 34, 0, 1, TIn, TOut>(st, a0, a1, w, o, p, 1);
+        if (pair) launch<9, 1, 64, 34, 0, 1, TIn, TOut, 2>(st, a0, a1, w, o, p, 1);
+        else if (state().tma_store) launch<9, 1, 64, 34, 0, 1, TIn, TOut>(st, a0, a1, w, o, p, 1);
         else launch<9, 1, 64, 34, 0, 0, TIn, TOut>(st, a0, a1, w, o, p, 1);
     } else if (WP == 34 && Cin == 128 && Cout == 64) {
-        CUtensorMap w = make_map_2d<TIn>(Wt, 64, 9 * 128, 64);
-        launch<9, 2, 64, 34, 0, 0, TIn, TOut>(st, a0, a1, w, a0, p, 1);
+        const bool pair = (state().pair_mask & 4) != 0;
+        CUtensorMap w = make_map_2d<TIn>(Wt, 64, 9 * 128, pair ? 32 : 64);
+        if (pair) launch<9, 2, 64, 34, 0, 0, TIn, TOut, 2>(st, a0, a1, w, a0, p, 1);
+        else launch<9, 2, 64, 34, 0, 0, TIn, TOut>(st, a0, a1, w, a0, p, 1);
     } else if (WP == 18 && Cin == 64 && Cout == 128 && !s1) {
-        CUtensorMap w = make_map_2d<TIn>(Wt, 128, 9 * 64, 128);
-        launch<9, 1, 128, 18, 0, 0, TIn, TOut>(st, a0, a1, w, a0, p, 1);
+        const bool pair = (state().pair_mask & 8) != 0;
+        CUtensorMap w = make_map_2d<TIn>(Wt, 128, 9 * 64, pair ? 64 : 128);
+        if (pair) launch<9, 1, 128, 18, 0, 0, TIn, TOut, 2>(st, a0, a1, w, a0, p, 1);
+        else launch<9, 1, 128, 18, 0, 0, TIn, TOut>(st, a0, a1, w, a0, p, 1);
     } else if (WP == 18 && Cin == 128 && Cout == 128 && !s1) {
         CUtensorMap w = make_map_2d<TIn>(Wt, 128, 9 * 128, 64);
-        launch<9, 2, 64, 18, 0, 0, TIn, TOut>(st, a0, a1, w, a0, p, 2);      // Cout split over blockIdx.y so the weights fit
+        if (state().pair_mask & 1)
+            launch<9, 2, 128, 18, 0, 0, TIn, TOut, 2>(st, a0, a1, w, a0, p, 1);  // CTA pair: each CTA stages 64 of the 128 weight rows
+        else
+            launch<9, 2, 64, 18, 0, 0, TIn, TOut>(st, a0, a1, w, a0, p, 2);      // Cout split over blockIdx.y so the weights fit
     } else if (WP == 18 && Cin == 128 && Cout == 64 && !s1) {
-        CUtensorMap w = make_map_2d<TIn>(Wt, 64, 9 * 128, 64);         // dgrad of down2.conv1
-        launch<9, 2, 64, 18, 0, 0, TIn, TOut>(st, a0, a1, w, a0, p, 1);
+        const bool pair = (state().pair_mask & 16) != 0;
+        CUtensorMap w = make_map_2d<TIn>(Wt, 64, 9 * 128, pair ? 32 : 64);         // dgrad of down2.conv1
+        if (pair) launch<9, 2, 64, 18, 0, 0, TIn, TOut, 2>(st, a0, a1, w, a0, p, 1);
+        else launch<9, 2, 64, 18, 0, 0, TIn, TOut>(st, a0, a1, w, a0, p, 1);
     } else if (WP == 34 && Cin == 64 && Cout == 128 && !s1) {
-        CUtensorMap w = make_map_2d<TIn>(Wt, 128, 9 * 64, 128);        // dgrad of up1.conv1 (d cat)
-        launch<9, 1, 128, 34, 0, 0, TIn, TOut>(st, a0, a1, w, a0, p, 1);
+        const bool pair = (state().pair_mask & 16) != 0;
+        CUtensorMap w = make_map_2d<TIn>(Wt, 128, 9 * 64, pair ? 64 : 128);        // dgrad of up1.conv1 (d cat)
+        if (pair) launch<9, 1, 128, 34, 0, 0, TIn, TOut, 2>(st, a0, a1, w, a0, p, 1);
+        else launch<9, 1, 128, 34, 0, 0, TIn, TOut>(st, a0, a1, w, a0, p, 1);
     } else {
         return false;
     }
@@ -680,8 +876,10 @@ bool conv3x3_final(cudaStream_t st, const TIn* s0, const TIn* Wt, const Geo& g, 
     p.final_clamp = final_clamp;
     constexpr int R32 = ((TC_BM + 2 * 35 + 7) / 8) * 8;
     CUtensorMap a0 = make_map_2d<TIn>(s0 - (size_t)g.guard * 64, (uint64_t)g.alloc_positions(), 64, R32);
-    CUtensorMap w = make_map_2d<TIn>(Wt, 64, 9 * 64, 64);
-    launch<9, 1, 64, 34, 2, 0, TIn, TIn>(st, a0, a0, w, a0, p, 1);
+    const bool pair = (state().pair_mask & 2) != 0;
+    CUtensorMap w = make_map_2d<TIn>(Wt, 64, 9 * 64, pair ? 32 : 64);
+    if (pair) launch<9, 1, 64, 34, 2, 0, TIn, TIn, 2>(st, a0, a0, w, a0, p, 1);
+    else launch<9, 1, 64, 34, 2, 0, TIn, TIn>(st, a0, a0, w, a0, p, 1);
     return true;
     }
 }

@@ -400,6 +400,7 @@ int ddpm_set_option(ddpm_handle* h, const char* key, int64_t value) {
     else if (k == "conv_impl") { e.opt_conv_impl = value; for (auto& kv : e.infer_sets) kv.second->drop_graphs(); }
     else if (k == "sync_bn") e.sync_bn = (int)value;
     else if (k == "tc_tma_store") { tc::state().tma_store = value != 0; for (auto& kv : e.infer_sets) kv.second->drop_graphs(); }
+    else if (k == "tc_pair") { tc::state().pair_mask = value; for (auto& kv : e.infer_sets) kv.second->drop_graphs(); }
     else if (k == "conv_v2") { e.opt_conv_v2 = value; for (auto& kv : e.infer_sets) kv.second->drop_graphs(); }
     else if (k == "fuse_final") { e.opt_fuse_final = value; for (auto& kv : e.infer_sets) kv.second->drop_graphs(); }
     else if (k == "tc_role_profile") {

@@ -109,3 +109,35 @@ def test_row_packed_conv_matches_first_formulation(gpu_handles, oracle, model_ar
     for k in (6, 12, 18, 36, 50, 56):
         assert rel_l2(gb[k], ga[k]) < 3e-2
     assert np.abs(sa - sb).max() < 5e-3
+
+
+def test_cta_pair_convs_match_single_cta_convs(gpu_handles, oracle, model_arrays, dataset, tabs):
+    """cta_group::2 kernels (two CTAs share one M=256 MMA stream, each staging half of the weight rows) against the
+    single-CTA kernels: same K order per output element, so test-mode outputs and the sampler are bit-identical;
+    train mode differs only through the atomically accumulated BatchNorm statistics (last-ulp noise)."""
+    h = gpu_handles["fp16"]
+    h.set_weights(model_arrays)
+    rng = np.random.default_rng(3)
+    xT = rng.standard_normal((5, 1, 32, 32)).astype(np.float32)
+    z = rng.standard_normal((9, 5, 1, 32, 32)).astype(np.float32)
+    try:
+        for B in (2, 9, 37):          # 2 and 9: the last pair-tile of every layer is ragged / half empty
+            x0, ts, eps = config2_batch(dataset, B)
+            xt = oracle.q_sample(x0, ts, eps, tabs["acum"])
+            h.set_option("tc_pair", 0)
+            e0 = h.predict_eps(xt, ts, train_mode=False)
+            l0, g0 = h.loss_and_grad(x0, ts, eps)
+            h.set_option("tc_pair", 31)
+            e1 = h.predict_eps(xt, ts, train_mode=False)
+            l1, g1 = h.loss_and_grad(x0, ts, eps)
+            assert np.array_equal(e0, e1), B
+            assert abs(l0 - l1) <= 1e-4 * abs(l0)
+            for k in (6, 12, 18, 24, 30, 36, 50, 56):
+                assert rel_l2(g1[k], g0[k]) < 3e-2, (B, k)
+        h.set_option("tc_pair", 0)
+        a = h.sample(5, x_T=xT, z=z, t_start=10)
+        h.set_option("tc_pair", 31)
+        b = h.sample(5, x_T=xT, z=z, t_start=10)
+        assert np.array_equal(a, b)
+    finally:
+        h.set_option("tc_pair", 31)
