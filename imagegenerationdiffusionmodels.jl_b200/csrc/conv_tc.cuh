@@ -309,7 +309,7 @@ template <int TAPS, int CHUNKS, int NOUT, int WP, int CG>
 constexpr int stages_for(int extra) {
     constexpr int HALO = (TAPS == 9) ? (WP + 1) : 0;
     constexpr int R = ((TC_BM + 2 * HALO + 7) / 8) * 8;
-    const int budget = 227 * 1024 - 1024 /*align*/ - 1024 /*barriers, shift*/ - TAPS * CHUNKS * (NOUT / CG) * 128 - extra;
+    const int budget = 227 * 1024 - 1024 /*align*/ - 1280 /*barriers, shift*/ - TAPS * CHUNKS * (NOUT / CG) * 128 - extra;
     if (budget <= 0) return 0;
     int s = budget / (R * 128);
     if (s > 8) s = 8;
@@ -367,15 +367,19 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constant__
     const uint32_t s_a = s_w + W_BYTES;
     const uint32_t s_o = s_a + STAGES * A_STAGE_BYTES;
     const uint32_t s_bar = s_o + O_BYTES;
-    // barrier slots (8 B each): [0] w_full, [1..S] a_full, [1+S..2S] a_empty, then ACC_BUFS acc_full, ACC_BUFS acc_empty
-    auto bar_w = [&]() { return s_bar; };
-    auto bar_afull = [&](int s) { return s_bar + 8u * (1 + s); };
-    auto bar_aempty = [&](int s) { return s_bar + 8u * (1 + STAGES + s); };
-    auto bar_accfull = [&](int b) { return s_bar + 8u * (1 + 2 * STAGES + b); };
-    auto bar_accempty = [&](int b) { return s_bar + 8u * (1 + 2 * STAGES + ACC_BUFS + b); };
+    // barrier slots (8 B each): [0..NWG) weight tiles (one per (chunk, tap), in the order the MMAs consume them, so the
+    // first tile starts while most of the weights are still in flight), then S a_full, S a_empty, ACC_BUFS acc_full,
+    // ACC_BUFS acc_empty
+    constexpr int NWG = TAPS * CHUNKS;
+    auto bar_w = [&](int g) { return s_bar + 8u * g; };
+    auto bar_afull = [&](int s) { return s_bar + 8u * (NWG + s); };
+    auto bar_aempty = [&](int s) { return s_bar + 8u * (NWG + STAGES + s); };
+    auto bar_accfull = [&](int b) { return s_bar + 8u * (NWG + 2 * STAGES + b); };
+    auto bar_accempty = [&](int b) { return s_bar + 8u * (NWG + 2 * STAGES + ACC_BUFS + b); };
     uint8_t* misc = smem + W_BYTES + STAGES * A_STAGE_BYTES + O_BYTES;
-    uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(misc + 8 * (1 + 2 * STAGES + 2 * ACC_BUFS));
-    float* s_shift = reinterpret_cast<float*>(misc + 256);               // [NOUT] per-channel shift of this CTA's N-slice
+    uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(misc + 8 * (NWG + 2 * STAGES + 2 * ACC_BUFS));
+    static_assert(8 * (NWG + 2 * STAGES + 2 * ACC_BUFS) + 4 <= 384, "barrier area overflows into the shift vector");
+    float* s_shift = reinterpret_cast<float*>(misc + 384);               // [NOUT] per-channel shift of this CTA's N-slice
     float* s_wf = s_shift + 128;                                         // [64] final-conv weights (EPI == 2)
 
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
@@ -390,7 +394,7 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constant__
     if (warp == 0 && lane == 0) {
         prefetch_tmap(&tmA0); prefetch_tmap(&tmW);
         if (p.chunk1_src1) prefetch_tmap(&tmA1);
-        mbar_init(bar_w(), 1);
+        for (int g = 0; g < NWG; ++g) mbar_init(bar_w(g), 1);
         for (int s = 0; s < STAGES; ++s) { mbar_init(bar_afull(s), 1); mbar_init(bar_aempty(s), 1); }
         for (int b = 0; b < ACC_BUFS; ++b) { mbar_init(bar_accfull(b), 1); mbar_init(bar_accempty(b), 4 * CG); }
         fence_barrier_init();
@@ -414,10 +418,10 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constant__
     if (warp == 0) {
         // ================= TMA producer (warp-uniform loop, one elected lane issues) =================
         if (elect_one()) {
-            if (leader) mbar_expect_tx(bar_w(), W_BYTES * CG);
-            const uint32_t bw = lead(bar_w());
-            for (int t = 0; t < TAPS; ++t)
-                for (int c = 0; c < CHUNKS; ++c) {
+            for (int c = 0; c < CHUNKS; ++c)
+                for (int t = 0; t < TAPS; ++t) {
+                    if (leader) mbar_expect_tx(bar_w(c * TAPS + t), W_TILE_BYTES * CG);
+                    const uint32_t bw = lead(bar_w(c * TAPS + t));
                     if (CG == 2)
                         tma_load_2d_pair(s_w + (t * CHUNKS + c) * W_TILE_BYTES, &tmW, (t * CHUNKS + c) * 64,
                                          n_blk * NOUT + (int)rank * NB, bw);
@@ -458,8 +462,7 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constant__
         // Dual issue is only legal when each pipeline stage is always consumed by the same warp (see conv3_tc.cuh).
         const int parity = (warp == 1) ? 0 : 1;
         constexpr int NISS = DUAL ? 2 : 1;
-        mbar_wait(bar_w(), 0);
-        tc_fence_after();
+        bool w_pending = true;                   // first tile of this warp: wait for each weight tile right before its MMAs
         // matrix descriptor halves (see make_desc_sw128): lo = start>>4 | LBO<<16, hi = SBO | version | SWIZZLE_128B
         constexpr uint32_t DESC_HI = (1024u >> 4) | (1u << 14) | (2u << 29);
         const uint32_t a_lo_base = ((s_a & 0x3FFFFu) >> 4) | (1u << 16);
@@ -486,6 +489,10 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constant__
 #pragma unroll
                     for (int t = 0; t < TAPS; ++t) {
                         const int shift = (TAPS == 9) ? (HALO + (t / 3 - 1) * WP + (t % 3 - 1)) : 0;
+                        if (w_pending) {
+                            mbar_wait(bar_w(c * TAPS + t), 0);
+                            tc_fence_after();
+                        }
 #pragma unroll
                         for (int ks = 0; ks < 4; ++ks) {
                             umma_f16_lh<CG>(d_tmem, a_lo + ((shift * 128 + ks * 32) >> 4),
@@ -499,6 +506,7 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constant__
                 __syncwarp();
                 if (p.dbg) dbg_acc[3] += clock64() - t0;
             }
+            w_pending = false;
             dbg_acc[7] += 1;
         }
     } else if (warp == 1 || warp == 6) {
@@ -760,7 +768,7 @@ void launch(cudaStream_t st, const CUtensorMap& a0, const CUtensorMap& a1, const
     constexpr int HALO = (TAPS == 9) ? (WP + 1) : 0;
     constexpr int R = ((TC_BM + 2 * HALO + 7) / 8) * 8;
     constexpr size_t smem = 1024 + (size_t)TAPS * CHUNKS * (NOUT / CG) * 128 + (size_t)STAGES * R * 128 +
-                            (size_t)epi_smem_bytes<TAPS, CHUNKS, NOUT, WP, EPI, TMAST, CG>() + 1024;
+                            (size_t)epi_smem_bytes<TAPS, CHUNKS, NOUT, WP, EPI, TMAST, CG>() + 1280;
     DDPM_CHECK(p.g.Wp == WP && p.g.Hs == WP - 1 && p.g.npos + 2 * TC_BM < (1ll << 31),
                "conv_tc: geometry does not match the kernel's compile-time row width");
     auto kern = conv_tc_kernel<TAPS, CHUNKS, NOUT, WP, STAGES, EPI, TMAST, CG, TIn, TOut>;

@@ -120,6 +120,7 @@ def test_cta_pair_convs_match_single_cta_convs(gpu_handles, oracle, model_arrays
     rng = np.random.default_rng(3)
     xT = rng.standard_normal((5, 1, 32, 32)).astype(np.float32)
     z = rng.standard_normal((9, 5, 1, 32, 32)).astype(np.float32)
+    rep = {}
     try:
         for B in (2, 9, 37):          # 2 and 9: the last pair-tile of every layer is ragged / half empty
             x0, ts, eps = config2_batch(dataset, B)
@@ -127,17 +128,28 @@ def test_cta_pair_convs_match_single_cta_convs(gpu_handles, oracle, model_arrays
             h.set_option("tc_pair", 0)
             e0 = h.predict_eps(xt, ts, train_mode=False)
             l0, g0 = h.loss_and_grad(x0, ts, eps)
+            _, g0b = h.loss_and_grad(x0, ts, eps)     # same kernels again: run-to-run noise floor of train mode
             h.set_option("tc_pair", 31)
             e1 = h.predict_eps(xt, ts, train_mode=False)
             l1, g1 = h.loss_and_grad(x0, ts, eps)
-            assert np.array_equal(e0, e1), B
-            assert abs(l0 - l1) <= 1e-4 * abs(l0)
-            for k in (6, 12, 18, 24, 30, 36, 50, 56):
-                assert rel_l2(g1[k], g0[k]) < 3e-2, (B, k)
+            ks = (6, 12, 18, 24, 30, 36, 50, 56)
+            rep[f"B{B}"] = {"eps_max_abs_diff": float(np.abs(e0 - e1).max()), "loss": [l0, l1],
+                            "grad_rel": {k: rel_l2(g1[k], g0[k]) for k in ks},
+                            "grad_rel_same_kernels_twice": {k: rel_l2(g0b[k], g0[k]) for k in ks}}
         h.set_option("tc_pair", 0)
         a = h.sample(5, x_T=xT, z=z, t_start=10)
         h.set_option("tc_pair", 31)
         b = h.sample(5, x_T=xT, z=z, t_start=10)
-        assert np.array_equal(a, b)
+        rep["sampler_max_abs_diff"] = float(np.abs(a - b).max())
     finally:
         h.set_option("tc_pair", 31)
+        _dump("pair_vs_single.json", rep)
+    for B in (2, 9, 37):
+        r = rep[f"B{B}"]
+        assert r["eps_max_abs_diff"] == 0.0, rep
+        assert abs(r["loss"][0] - r["loss"][1]) <= 1e-4 * abs(r["loss"][0]), rep
+        # train mode is not run-to-run reproducible (atomically accumulated BatchNorm statistics flip FP16 roundings
+        # and ReLU masks); the pair kernels must stay within a small multiple of that noise floor
+        floor = max(r["grad_rel_same_kernels_twice"].values())
+        assert max(r["grad_rel"].values()) < max(3.0 * floor, 1e-2), rep
+    assert rep["sampler_max_abs_diff"] == 0.0, rep
