@@ -1,0 +1,271 @@
+// First convolution of the sampler on tensor cores (sm_100a).
+//
+// down1.conv1 = Conv((3,3), 1+128 => 64, pad=1) on cat(x, tile(t_emb)) (/root/reference/src/train_brain.jl:111,164-168)
+// with the embedding channels folded into per-border-class constants (kernels.cuh, conv1_kernel).  What is left is a
+// K = 9 contraction per output -- far too thin for an implicit GEMM on FP16 inputs alone, and the CUDA-core kernel
+// spends ~125 instructions per (pixel, 4 channels).  Here the contraction runs on tcgen05 with both FP32 operands
+// split into two BF16 parts (BF16 keeps the FP32 exponent range, so the low parts never go subnormal -- an FP16
+// split lost the low weight parts that way and was only FP16-accurate on B200):
+//     x*w  ~=  x_hi*w_hi + x_lo*w_hi + x_hi*w_lo          (16 significand bits per operand; the dropped
+//                                                           x_lo*w_lo term and the residuals are ~2^-17 relative,
+//                                                           60x below the FP16 rounding of the stored activation)
+// so one output row is a K = 27 (padded to 32) dot product:  A row = [x_hi(9) | x_lo(9) | x_hi(9) | 0(5)],
+// B row(co) = [w_hi(9) | w_hi(9) | w_lo(9) | 0(5)], FP32 accumulation in TMEM, w = scale[co] * Wimg[tap][co].
+// Four builder warps write the A tile (128 positions x 64 B used of a 128-byte swizzled row) straight into shared
+// memory from the FP32 image -- no im2col buffer in HBM --, one thread issues two M128 N64 K16 MMAs per tile, and
+// two sets of four epilogue warps add the (timestep, border class) constant and the BatchNorm shift in FP32, apply
+// ReLU and write the tile, halo rows as zeros, with a TMA store.
+// Used when one timestep is shared by the whole batch (the reverse-diffusion loop, generate_images.jl:196-208);
+// per-image timesteps and training keep the CUDA-core kernel.
+#pragma once
+#include "conv_tc.cuh"
+
+namespace ddpm {
+namespace tc {
+
+constexpr int C1_THREADS = 32 * 13;   // warps 0..3 A-tile builders, warp 4 MMA issuer / TMEM owner, warps 5..8 and 9..12 epilogue sets
+constexpr int C1_STAGES = 4;
+
+struct C1Params {
+    const float* x;        // [N][32][32] FP32 sample
+    const float* Wimg;     // [9][64] image-channel weights, tap-major
+    const float* Ecls_t;   // [9][64] embedding constants of this timestep per border class
+    const float* scale;    // [64] inference BatchNorm scale (nullptr = 1)
+    const float* shift;    // [64] inference BatchNorm shift / bias (nullptr = 0)
+    int relu;
+    Geo g;                 // 32x32 output geometry
+    int num_tiles;
+};
+
+__device__ __forceinline__ uint32_t pack_h2(float a, float b) {      // both values are already BF16-representable
+    __nv_bfloat162 h = __floats2bfloat162_rn(a, b);
+    return *reinterpret_cast<uint32_t*>(&h);
+}
+__device__ __forceinline__ void split2(float v, float& hi, float& lo) {
+    hi = __bfloat162float(__float2bfloat16_rn(v));
+    lo = __bfloat162float(__float2bfloat16_rn(v - hi));
+}
+
+template <typename TOut>
+__global__ void __launch_bounds__(C1_THREADS, 1)
+conv1_tc_kernel(const __grid_constant__ CUtensorMap tmO, const C1Params p) {
+    constexpr int WP = 34, HS = 33, H = 32, W = 32;
+    constexpr int ACC_BUFS = 4, NOUT = 64;
+    constexpr uint32_t A_STAGE_BYTES = TC_BM * 128;
+    constexpr uint32_t B_BYTES = NOUT * 128;
+    constexpr uint32_t O_TILE = TC_BM * NOUT * 2;
+    constexpr uint32_t IDESC = make_idesc(1u, TC_BM, NOUT);          // BF16 operands
+
+    extern __shared__ uint8_t smem_raw[];
+    uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
+    const uint32_t s_b = smem_u32(smem);
+    const uint32_t s_a = s_b + B_BYTES;
+    const uint32_t s_o = s_a + C1_STAGES * A_STAGE_BYTES;
+    const uint32_t s_bar = s_o + 2 * O_TILE;
+    auto bar_afull = [&](int s) { return s_bar + 8u * s; };
+    auto bar_aempty = [&](int s) { return s_bar + 8u * (C1_STAGES + s); };
+    auto bar_accfull = [&](int b) { return s_bar + 8u * (2 * C1_STAGES + b); };
+    auto bar_accempty = [&](int b) { return s_bar + 8u * (2 * C1_STAGES + ACC_BUFS + b); };
+    uint8_t* misc = smem + B_BYTES + C1_STAGES * A_STAGE_BYTES + 2 * O_TILE;
+    uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(misc + 8 * (2 * C1_STAGES + 2 * ACC_BUFS));
+    float* s_E = reinterpret_cast<float*>(misc + 256);                // [9][64]: Ecls*scale + shift per border class
+
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    if (threadIdx.x == 0) {
+        prefetch_tmap(&tmO);
+        for (int s = 0; s < C1_STAGES; ++s) { mbar_init(bar_afull(s), 4); mbar_init(bar_aempty(s), 1); }
+        for (int b = 0; b < ACC_BUFS; ++b) { mbar_init(bar_accfull(b), 1); mbar_init(bar_accempty(b), 4); }
+        fence_barrier_init();
+    }
+    if (warp == 4) tmem_alloc<256>(smem_u32(tmem_slot));
+    for (int i = threadIdx.x; i < 9 * 64; i += C1_THREADS) {
+        const int c = i & 63;
+        s_E[i] = p.Ecls_t[i] * (p.scale ? p.scale[c] : 1.f) + (p.shift ? p.shift[c] : 0.f);
+    }
+    if (threadIdx.x < NOUT) {
+        // B row of output channel c: [w_hi | w_hi | w_lo | 0], 16-byte chunks XOR-swizzled by the row index
+        const int c = threadIdx.x;
+        const float sc = p.scale ? p.scale[c] : 1.f;
+        float hi[9], lo[9];
+#pragma unroll
+        for (int k = 0; k < 9; ++k) {
+            split2(p.Wimg[k * 64 + c] * sc, hi[k], lo[k]);
+        }
+        const float col[32] = {hi[0], hi[1], hi[2], hi[3], hi[4], hi[5], hi[6], hi[7], hi[8], hi[0], hi[1], hi[2], hi[3],
+                               hi[4], hi[5], hi[6], hi[7], hi[8], lo[0], lo[1], lo[2], lo[3], lo[4], lo[5], lo[6], lo[7],
+                               lo[8], 0.f,   0.f,   0.f,   0.f,   0.f};
+        const uint32_t rbase = s_b + (uint32_t)c * 128;
+#pragma unroll
+        for (int j = 0; j < 4; ++j) {
+            asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(rbase + (((uint32_t)j ^ ((uint32_t)c & 7u)) << 4)),
+                         "r"(pack_h2(col[8 * j + 0], col[8 * j + 1])), "r"(pack_h2(col[8 * j + 2], col[8 * j + 3])),
+                         "r"(pack_h2(col[8 * j + 4], col[8 * j + 5])), "r"(pack_h2(col[8 * j + 6], col[8 * j + 7]))
+                         : "memory");
+        }
+        fence_proxy_async();
+    }
+    tc_fence_before();
+    __syncthreads();
+    tc_fence_after();
+    const uint32_t tmem_base = *tmem_slot;
+    const int npos = (int)p.g.npos;
+
+    if (warp < 4) {
+        // ================= A-tile builders: thread r writes row r of every tile this CTA owns =================
+        const int r = threadIdx.x;
+        int it = 0;
+        for (int tile = blockIdx.x; tile < p.num_tiles; tile += gridDim.x, ++it) {
+            const int stage = it % C1_STAGES;
+            const uint32_t phase = (uint32_t)(it / C1_STAGES) & 1u;
+            const int pos = tile * TC_BM + r;
+            const int pr = pos / WP, pc = pos - pr * WP;
+            const int n = pr / HS, prr = pr - n * HS;
+            const int h = prr - 1, w = pc - 1;
+            const bool valid = pos < npos && prr != 0 && pc >= 1 && pc <= W && n < p.g.N;
+            float v[9];
+#pragma unroll
+            for (int k = 0; k < 9; ++k) {
+                const int hh = h + k / 3 - 1, ww = w + k % 3 - 1;
+                const bool in = valid && hh >= 0 && hh < H && ww >= 0 && ww < W;
+                v[k] = in ? __ldg(p.x + ((long long)n * H + hh) * W + ww) : 0.f;
+            }
+            float hi[9], lo[9];
+#pragma unroll
+            for (int k = 0; k < 9; ++k) split2(v[k], hi[k], lo[k]);
+            const float col[32] = {hi[0], hi[1], hi[2], hi[3], hi[4], hi[5], hi[6], hi[7], hi[8], lo[0], lo[1], lo[2], lo[3],
+                                   lo[4], lo[5], lo[6], lo[7], lo[8], hi[0], hi[1], hi[2], hi[3], hi[4], hi[5], hi[6], hi[7],
+                                   hi[8], 0.f,   0.f,   0.f,   0.f,   0.f};
+            mbar_wait(bar_aempty(stage), phase ^ 1u);
+            const uint32_t rbase = s_a + (uint32_t)stage * A_STAGE_BYTES + (uint32_t)r * 128;
+#pragma unroll
+            for (int j = 0; j < 4; ++j) {
+                asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(rbase + (((uint32_t)j ^ ((uint32_t)r & 7u)) << 4)),
+                             "r"(pack_h2(col[8 * j + 0], col[8 * j + 1])), "r"(pack_h2(col[8 * j + 2], col[8 * j + 3])),
+                             "r"(pack_h2(col[8 * j + 4], col[8 * j + 5])), "r"(pack_h2(col[8 * j + 6], col[8 * j + 7]))
+                             : "memory");
+            }
+            fence_proxy_async();               // generic-proxy writes -> visible to the tensor core's async-proxy reads
+            __syncwarp();
+            if (lane == 0) mbar_arrive(bar_afull(stage));
+        }
+    } else if (warp == 4) {
+        // ================= MMA issuer =================
+        constexpr uint32_t DESC_HI = (1024u >> 4) | (1u << 14) | (2u << 29);
+        const uint32_t a_lo_base = ((s_a & 0x3FFFFu) >> 4) | (1u << 16);
+        const uint32_t b_lo_base = ((s_b & 0x3FFFFu) >> 4) | (1u << 16);
+        int it = 0;
+        for (int tile = blockIdx.x; tile < p.num_tiles; tile += gridDim.x, ++it) {
+            const int stage = it % C1_STAGES, buf = it % ACC_BUFS;
+            const uint32_t phase = (uint32_t)(it / C1_STAGES) & 1u, acc_phase = (uint32_t)(it / ACC_BUFS) & 1u;
+            mbar_wait(bar_accempty(buf), acc_phase ^ 1u);
+            mbar_wait(bar_afull(stage), phase);
+            tc_fence_after();
+            if (elect_one()) {
+                const uint32_t a_lo = a_lo_base + stage * (A_STAGE_BYTES >> 4);
+                const uint32_t d_tmem = tmem_base + buf * NOUT;
+                umma_f16_lh(d_tmem, a_lo, b_lo_base, DESC_HI, IDESC, 0u);
+                umma_f16_lh(d_tmem, a_lo + (32 >> 4), b_lo_base + (32 >> 4), DESC_HI, IDESC, 1u);
+                umma_commit(bar_aempty(stage));
+                umma_commit(bar_accfull(buf));
+            }
+            __syncwarp();
+        }
+    } else {
+        // ================= epilogue sets (alternate tiles): TMEM -> +E[cls] -> ReLU -> staging tile -> TMA store =================
+        const int eset = (warp >= 9) ? 1 : 0;
+        const int lane_grp = warp & 3;
+        const int row = lane_grp * 32 + lane;
+        const bool store_thread = (threadIdx.x == (eset ? 9 * 32 : 5 * 32));
+        const uint32_t stage_o = s_o + (uint32_t)eset * O_TILE;
+        for (int it = eset, tile = blockIdx.x + eset * gridDim.x; tile < p.num_tiles; it += 2, tile += 2 * gridDim.x) {
+            const int buf = it % ACC_BUFS;
+            const uint32_t acc_phase = (uint32_t)(it / ACC_BUFS) & 1u;
+            const int pos = tile * TC_BM + row;
+            const int pr = pos / WP, pc = pos - pr * WP;
+            const int n = pr / HS, prr = pr - n * HS;
+            const int h = prr - 1, w = pc - 1;
+            const bool valid = pos < npos && prr != 0 && pc >= 1 && pc <= W && n < p.g.N;
+            const int cls = (h == 0 ? 0 : (h == H - 1 ? 2 : 1)) * 3 + (w == 0 ? 0 : (w == W - 1 ? 2 : 1));
+            const float* erow = s_E + (valid ? cls : 4) * 64;
+            mbar_wait(bar_accfull(buf), acc_phase);
+            tc_fence_after();
+            if (store_thread) tma_store_wait_read<0>();       // this set's previous TMA store has drained the staging tile
+            named_bar_sync(1 + eset, 128);
+            const uint32_t taddr = tmem_base + ((uint32_t)(lane_grp * 32) << 16) + buf * NOUT;
+            uint32_t racc[4][16];
+#pragma unroll
+            for (int q = 0; q < 4; ++q) tmem_ld16(taddr + q * 16, racc[q]);
+            tmem_ld_wait();
+            tc_fence_before();
+            __syncwarp();
+            if (lane == 0) mbar_arrive(bar_accempty(buf));
+#pragma unroll
+            for (int q = 0; q < 4; ++q) {
+                float v[16];
+#pragma unroll
+                for (int j4 = 0; j4 < 4; ++j4) {
+                    const float4 e = *reinterpret_cast<const float4*>(erow + q * 16 + 4 * j4);
+                    v[4 * j4 + 0] = __uint_as_float(racc[q][4 * j4 + 0]) + e.x;
+                    v[4 * j4 + 1] = __uint_as_float(racc[q][4 * j4 + 1]) + e.y;
+                    v[4 * j4 + 2] = __uint_as_float(racc[q][4 * j4 + 2]) + e.z;
+                    v[4 * j4 + 3] = __uint_as_float(racc[q][4 * j4 + 3]) + e.w;
+                }
+#pragma unroll
+                for (int j = 0; j < 16; ++j) v[j] = valid ? (p.relu ? fmaxf(v[j], 0.f) : v[j]) : 0.f;
+                uint4 qa, qb;
+                pack16<TOut>(v, qa, qb);
+                const uint32_t rbase = stage_o + (uint32_t)row * 128;
+                const uint32_t ch = (uint32_t)(q * 2);
+                const uint32_t sw = (uint32_t)row & 7u;
+                asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(rbase + ((ch ^ sw) << 4)), "r"(qa.x), "r"(qa.y),
+                             "r"(qa.z), "r"(qa.w) : "memory");
+                asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(rbase + (((ch + 1) ^ sw) << 4)), "r"(qb.x), "r"(qb.y),
+                             "r"(qb.z), "r"(qb.w) : "memory");
+            }
+            fence_proxy_async();
+            named_bar_sync(1 + eset, 128);
+            if (store_thread) {
+                tma_store_2d(&tmO, stage_o, 0, tile * TC_BM + p.g.guard);
+                tma_store_commit();
+            }
+        }
+        if (store_thread) tma_store_wait_all();
+    }
+    tc_fence_before();
+    __syncthreads();
+    if (warp == 4) {
+        tc_fence_after();
+        tmem_dealloc<256>(tmem_base);
+    }
+}
+
+// Launch: a1 = relu((x (*) Wimg + Ecls[t]) * scale + shift) on the padded 32x32 layout, one shared timestep
+template <typename TOut>
+bool conv1_shared_t(cudaStream_t st, const float* x, const float* Wimg, const float* Ecls_t, const float* scale,
+                    const float* shift, int relu, TOut* out, const Geo& g) {
+    if (!available()) return false;
+    if constexpr (sizeof(TOut) != 2) {
+        return false;
+    } else {
+    if (g.Wp != 34 || g.Hs != 33 || g.npos + 2 * TC_BM >= (1ll << 31)) return false;
+    C1Params p{};
+    p.x = x; p.Wimg = Wimg; p.Ecls_t = Ecls_t; p.scale = scale; p.shift = shift; p.relu = relu; p.g = g;
+    p.num_tiles = cdiv(g.npos, TC_BM);
+    CUtensorMap o = make_map_2d<TOut>(out - (size_t)g.guard * 64, (uint64_t)g.alloc_positions(), 64, TC_BM);
+    constexpr size_t smem = 1024 + 64 * 128 + (size_t)C1_STAGES * TC_BM * 128 + 2 * TC_BM * 64 * 2 + 256 + 9 * 64 * 4 + 256;
+    auto kern = conv1_tc_kernel<TOut>;
+    static bool attr_set = false;
+    if (!attr_set) {
+        DDPM_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        attr_set = true;
+    }
+    int ctas = state().num_sms;
+    if (ctas > p.num_tiles) ctas = p.num_tiles;
+    kern<<<ctas, C1_THREADS, smem, st>>>(o, p);
+    DDPM_LAUNCH_CHECK();
+    return true;
+    }
+}
+
+}  // namespace tc
+}  // namespace ddpm

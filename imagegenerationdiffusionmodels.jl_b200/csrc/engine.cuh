@@ -16,6 +16,7 @@
 #include "igemm_simt.cuh"
 #include "conv_tc.cuh"
 #include "conv3_tc.cuh"
+#include "conv1_tc.cuh"
 
 namespace ddpm {
 
@@ -213,6 +214,7 @@ struct Engine {
     // shuffle/exchange epilogue costs ~2300 cycles per tile, so the first formulation (conv_tc.cuh, ~2500 cycles per
     // tile, smem-operand bound) is still faster end to end (B200, round 1: 1612 vs 1791 img/s) and stays the default.
     long long opt_conv_v2 = 0;
+    long long opt_conv1_tc = 1;    // sampler: first conv on tensor cores (hi/lo split operands) when the batch shares one timestep
     long long opt_sample_chunk = 512, opt_use_graph = 1, opt_conv_impl = 0 /*0 auto, 1 simt, 2 tc*/, opt_fuse_final = 1;
     long long cnt_launches = 0;
 
@@ -680,10 +682,16 @@ void Engine::forward_t(ActSet& s, const float* x_dev, const int* ts_dev, int t_f
         const ConvSpec& c = kConv[1];
         long long pixels = (long long)N * HW;
         Tensor& o = train ? s.y[1] : s.a[1];
-        conv1_kernel<TA><<<cdiv(pixels, CONV1_PIX_PER_BLOCK), 256, 0, stream>>>(x_dev, ts_dev, t_fixed, Wimg, Ecls,
+        bool done = false;
+        if (!train && !ts_dev && opt_conv1_tc && use_tc())
+            done = tc::conv1_shared_t<TA>(stream, x_dev, Wimg, Ecls + (long long)(t_fixed - 1) * 9 * 64, inf_scale[1],
+                                          inf_shift[1], 1, o.pos0<TA>(), o.g);
+        if (!done) {
+            conv1_kernel<TA><<<cdiv(pixels, CONV1_PIX_PER_BLOCK), 256, 0, stream>>>(x_dev, ts_dev, t_fixed, Wimg, Ecls,
                                                               train ? nullptr : inf_scale[1], train ? arr(c.b) : inf_shift[1],
                                                               train ? 0 : 1, o.view<TA>(), o.g, train ? lsum(1) : nullptr);
-        DDPM_LAUNCH_CHECK();
+            DDPM_LAUNCH_CHECK();
+        }
         cnt_launches += 1;
         if (train) bn(1, false);
     }

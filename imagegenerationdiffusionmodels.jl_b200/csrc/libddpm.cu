@@ -401,6 +401,7 @@ int ddpm_set_option(ddpm_handle* h, const char* key, int64_t value) {
     else if (k == "sync_bn") e.sync_bn = (int)value;
     else if (k == "tc_tma_store") { tc::state().tma_store = value != 0; for (auto& kv : e.infer_sets) kv.second->drop_graphs(); }
     else if (k == "tc_pair") { tc::state().pair_mask = value; for (auto& kv : e.infer_sets) kv.second->drop_graphs(); }
+    else if (k == "conv1_tc") { e.opt_conv1_tc = value; for (auto& kv : e.infer_sets) kv.second->drop_graphs(); }
     else if (k == "conv_v2") { e.opt_conv_v2 = value; for (auto& kv : e.infer_sets) kv.second->drop_graphs(); }
     else if (k == "fuse_final") { e.opt_fuse_final = value; for (auto& kv : e.infer_sets) kv.second->drop_graphs(); }
     else if (k == "tc_role_profile") {
@@ -520,9 +521,15 @@ int ddpm_time_kernel(ddpm_handle* h, const char* name, int64_t n_images, int ite
             DDPM_DISPATCH(e.prec, time_it([&] {
                 if (k == "conv1") {
                     long long pixels = (long long)N * HW;
-                    conv1_kernel<TA><<<cdiv(pixels, CONV1_PIX_PER_BLOCK), 256, 0, e.stream>>>(
-                        s.x.as<float>(), nullptr, e.T / 2, e.Wimg, e.Ecls, e.inf_scale[1], e.inf_shift[1], 1, s.a[1].view<TA>(),
-                        s.a[1].g, nullptr);
+                    bool done = false;
+                    if (e.opt_conv1_tc && e.use_tc())
+                        done = tc::conv1_shared_t<TA>(e.stream, s.x.as<float>(), e.Wimg,
+                                                      e.Ecls + (long long)(e.T / 2 - 1) * 9 * 64, e.inf_scale[1], e.inf_shift[1],
+                                                      1, s.a[1].pos0<TA>(), s.a[1].g);
+                    if (!done)
+                        conv1_kernel<TA><<<cdiv(pixels, CONV1_PIX_PER_BLOCK), 256, 0, e.stream>>>(
+                            s.x.as<float>(), nullptr, e.T / 2, e.Wimg, e.Ecls, e.inf_scale[1], e.inf_shift[1], 1,
+                            s.a[1].view<TA>(), s.a[1].g, nullptr);
                 } else if (k == "pool") {
                     long long work = (long long)N * 16 * 16 * 8;
                     bn_apply_pool_kernel<TA><<<cdiv(work, 256), 256, 0, e.stream>>>(s.a[2].cview<TA>(), s.a[2].view<TA>(),

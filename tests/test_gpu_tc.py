@@ -153,3 +153,37 @@ def test_cta_pair_convs_match_single_cta_convs(gpu_handles, oracle, model_arrays
         floor = max(r["grad_rel_same_kernels_twice"].values())
         assert max(r["grad_rel"].values()) < max(3.0 * floor, 1e-2), rep
     assert rep["sampler_max_abs_diff"] == 0.0, rep
+
+
+def test_first_conv_on_tensor_cores_matches_cuda_core_kernel(gpu_handles, model_arrays):
+    """conv1_tc.cuh (BF16 hi/lo split operands on tcgen05, FP32 accumulate) against the FP32 CUDA-core first conv on
+    the same device-resident input: the stored FP16 activation may differ by one rounding step in a few elements
+    (the split keeps 16 significand bits per operand), never by more; the sampler output moves by < 1e-3."""
+    h = gpu_handles["fp16"]
+    h.set_weights(model_arrays)
+    n = 37                                   # ragged last tile, images straddling tile boundaries
+    rng = np.random.default_rng(5)
+    xT = (2.0 * rng.standard_normal((n, 1, 32, 32))).astype(np.float32)
+    z = rng.standard_normal((5, n, 1, 32, 32)).astype(np.float32)
+    rep = {}
+    try:
+        out = {}
+        for m in (0, 1):
+            h.set_option("conv1_tc", m)
+            out[m] = h.sample(n, x_T=xT, z=z, t_start=6)
+        # the layer alone: ddpm_time_kernel("conv1") refills the set's x with the same Philox normals on every call and
+        # leaves the first conv's output in the (otherwise aliased) a1 buffer
+        h.set_option("conv1_tc", 0); h.time_kernel("conv1", n, 1); ref = h.debug_fetch("infer:a1")
+        h.set_option("conv1_tc", 1); h.time_kernel("conv1", n, 1); got = h.debug_fetch("infer:a1")
+        d = np.abs(got - ref)
+        # one FP16 rounding step of the reference value, floored at 2e-5 absolute (values that straddle the ReLU zero)
+        ulp = np.maximum(2.0 ** (np.floor(np.log2(np.maximum(np.abs(ref), 2.0 ** -14))) - 10), 2e-5)
+        rep = {"frac_mismatch": float(np.mean(d > 0)), "max_err_ulp": float((d / ulp).max()),
+               "max_abs_a1": float(np.abs(ref).max()), "frac_nonzero": float(np.mean(ref != 0)),
+               "sampler_max_abs_diff": float(np.abs(out[0] - out[1]).max())}
+    finally:
+        h.set_option("conv1_tc", 1)
+        _dump("conv1_tc_vs_simt.json", rep)
+    assert rep["max_abs_a1"] > 0.1 and rep["frac_nonzero"] > 0.2, rep     # the layer really ran on real data
+    assert rep["frac_mismatch"] < 0.03 and rep["max_err_ulp"] <= 1.0, rep
+    assert rep["sampler_max_abs_diff"] < 1e-3, rep
