@@ -6,8 +6,9 @@
   python bench.py --impl reference ...                     (CPU restatement of the Flux path)
 
 A "step" is one full pass of the hot path over one batch: `--images` images per GPU taken
-through all T-1 = 499 U-Net evaluations + reverse updates (BASELINE config 4 sharded: 16 steps of
-4096 images == the 65,536-image job on one GPU).  Weak scaling: every rank samples its own
+through all T-1 = 499 U-Net evaluations + reverse updates (BASELINE config 4 sharded: 12.6 steps of
+5200 images == the 65,536-image job on one GPU; 5200 = 4 graph chunks of 1300, the chunk size that fills the
+persistent kernels' tile rounds exactly).  Weak scaling: every rank samples its own
 `--images` images per step, global image indices are disjoint, no data-path collective.
 
 Prints ONE JSON line on rank 0 (see the contract in the task description / DESIGN.md).
@@ -32,8 +33,9 @@ FLOP_PER_EVAL_FOLDED = 735.31e6     # SURVEY.md Appendix A with the embedding fo
 FLOP_PER_EVAL_REFERENCE = 886.31e6  # the reference's 129-channel formulation
 FLOP_PER_TRAIN_IMG = 2204.76e6      # fwd + dgrad + wgrad with the fold
 # dram__bytes_read.sum + dram__bytes_write.sum of ONE conv3x3 64->64 @32x32 launch from `ncu --set full`
-# (profiles/conv_l2_r1_ncu.txt), keyed by images per launch
-NCU_TRAFFIC_CONV_L2 = {512: 98.6e6}
+# keyed by images per launch: 512 -> profiles/conv_l2_r1_ncu.txt (single-CTA kernel, earlier in round 1),
+# 1300 -> profiles/conv_l2_r1b_ncu.txt (CTA-pair kernel, the default)
+NCU_TRAFFIC_CONV_L2 = {512: 98.6e6, 1300: 325.8e6}
 
 
 def load_peaks():
@@ -265,7 +267,7 @@ def run_workload(args, workload, h, td, rank, world, local, peaks, N, t_start, e
                "d2h_bytes_per_step": int(oout.nbytes), "steps": e2e_steps}
         metric = "sampled img/s (500-step DDPM, 32x32)"
         workload_desc = (f"generate_image: {evals}-evaluation reverse loop (t={t_start}..2), 32x32, trained_model.bson weights, "
-                    f"device Philox noise; BASELINE config 4 (65,536 images) == 16 steps of 4096")
+                    f"device Philox noise; BASELINE config 4 (65,536 images) == {65536 / N:.1f} steps of {N}")
         flop_per_unit = FLOP_PER_EVAL_FOLDED * evals
     else:
         # ---- training throughput: data parallel, global batch = images * world
@@ -395,10 +397,10 @@ def main():
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--workload", default="both", choices=["sample", "train", "both"])
-    ap.add_argument("--images", type=int, default=4096, help="sampled images per step per GPU")
+    ap.add_argument("--images", type=int, default=5200, help="sampled images per step per GPU (4 chunks of 1300)")
     ap.add_argument("--train-images", type=int, default=0,
                     help="training batch per step per GPU (default: BASELINE config 5, global batch 4096 => 4096/n_gpus)")
-    ap.add_argument("--chunk", type=int, default=512, help="images per captured reverse-loop graph")
+    ap.add_argument("--chunk", type=int, default=1300, help="images per captured reverse-loop graph")
     ap.add_argument("--streams", type=int, default=0, help="concurrent chunk streams of the sampler (0: library default)")
     ap.add_argument("--precision", default="fp16", choices=["fp32", "fp16", "bf16"])
     ap.add_argument("--t-start", type=int, default=T_STEPS)

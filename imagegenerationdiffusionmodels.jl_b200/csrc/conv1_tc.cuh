@@ -78,6 +78,8 @@ conv1_tc_kernel(const __grid_constant__ CUtensorMap tmO, const C1Params p) {
         fence_barrier_init();
     }
     if (warp == 4) tmem_alloc<256>(smem_u32(tmem_slot));
+    pdl_launch_dependents();
+    pdl_wait();                               // nothing above reads global memory (programmatic dependent launch)
     for (int i = threadIdx.x; i < 9 * 64; i += C1_THREADS) {
         const int c = i & 63;
         s_E[i] = p.Ecls_t[i] * (p.scale ? p.scale[c] : 1.f) + (p.shift ? p.shift[c] : 0.f);
@@ -113,22 +115,30 @@ conv1_tc_kernel(const __grid_constant__ CUtensorMap tmO, const C1Params p) {
     if (warp < 4) {
         // ================= A-tile builders: thread r writes row r of every tile this CTA owns =================
         const int r = threadIdx.x;
-        int it = 0;
-        for (int tile = blockIdx.x; tile < p.num_tiles; tile += gridDim.x, ++it) {
-            const int stage = it % C1_STAGES;
-            const uint32_t phase = (uint32_t)(it / C1_STAGES) & 1u;
+        // the nine taps of position (tile, r); halo / out-of-image taps read as zero
+        auto load_taps = [&](int tile, float v[9]) {
             const int pos = tile * TC_BM + r;
             const int pr = pos / WP, pc = pos - pr * WP;
             const int n = pr / HS, prr = pr - n * HS;
             const int h = prr - 1, w = pc - 1;
-            const bool valid = pos < npos && prr != 0 && pc >= 1 && pc <= W && n < p.g.N;
-            float v[9];
+            const bool valid = tile < p.num_tiles && pos < npos && prr != 0 && pc >= 1 && pc <= W && n < p.g.N;
 #pragma unroll
             for (int k = 0; k < 9; ++k) {
                 const int hh = h + k / 3 - 1, ww = w + k % 3 - 1;
                 const bool in = valid && hh >= 0 && hh < H && ww >= 0 && ww < W;
                 v[k] = in ? __ldg(p.x + ((long long)n * H + hh) * W + ww) : 0.f;
             }
+        };
+        float vn[9];
+        load_taps(blockIdx.x, vn);
+        int it = 0;
+        for (int tile = blockIdx.x; tile < p.num_tiles; tile += gridDim.x, ++it) {
+            const int stage = it % C1_STAGES;
+            const uint32_t phase = (uint32_t)(it / C1_STAGES) & 1u;
+            float v[9];
+#pragma unroll
+            for (int k = 0; k < 9; ++k) v[k] = vn[k];
+            load_taps(tile + gridDim.x, vn);          // next tile's loads stay in flight while this tile is packed
             float hi[9], lo[9];
 #pragma unroll
             for (int k = 0; k < 9; ++k) split2(v[k], hi[k], lo[k]);
@@ -261,7 +271,17 @@ bool conv1_shared_t(cudaStream_t st, const float* x, const float* Wimg, const fl
     }
     int ctas = state().num_sms;
     if (ctas > p.num_tiles) ctas = p.num_tiles;
-    kern<<<ctas, C1_THREADS, smem, st>>>(o, p);
+    cudaLaunchConfig_t cfg{};
+    cfg.gridDim = dim3(ctas);
+    cfg.blockDim = dim3(C1_THREADS);
+    cfg.dynamicSmemBytes = smem;
+    cfg.stream = st;
+    cudaLaunchAttribute attr[1];
+    attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+    attr[0].val.programmaticStreamSerializationAllowed = 1;
+    cfg.attrs = attr;
+    cfg.numAttrs = state().pdl ? 1 : 0;
+    DDPM_CUDA(cudaLaunchKernelEx(&cfg, kern, o, p));
     DDPM_LAUNCH_CHECK();
     return true;
     }

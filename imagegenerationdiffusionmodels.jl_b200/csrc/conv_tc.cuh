@@ -103,6 +103,12 @@ __device__ __forceinline__ void prefetch_tmap(const CUtensorMap* map) {
     asm volatile("prefetch.tensormap [%0];" ::"l"(map) : "memory");
 }
 
+// ---- programmatic dependent launch: a kernel launched with the programmatic-serialization attribute may start while
+// its predecessor in the stream drains; everything before pdl_wait() must not touch global memory the predecessor
+// (or anything before it) writes.  Both are no-ops for ordinary launches.
+__device__ __forceinline__ void pdl_wait() { asm volatile("griddepcontrol.wait;" ::: "memory"); }
+__device__ __forceinline__ void pdl_launch_dependents() { asm volatile("griddepcontrol.launch_dependents;" ::: "memory"); }
+
 // ---- CTA-pair (cta_group::2) plumbing: the two CTAs of a cluster run one M=256 MMA stream issued by rank 0
 __device__ __forceinline__ uint32_t cluster_ctarank() {
     uint32_t r;
@@ -400,13 +406,16 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constant__
         fence_barrier_init();
     }
     if (warp == 2) tmem_alloc<TMEM_COLS, CG>(smem_u32(tmem_slot));
+    if (warp == 0 && lane == 0 && TMAST) prefetch_tmap(&tmO);
+    // everything above is private to this CTA: with a programmatic dependent launch it overlaps the predecessor's tail
+    pdl_launch_dependents();
+    pdl_wait();
     if (threadIdx.x >= 64 && threadIdx.x < 64 + NOUT) {
         const int c = threadIdx.x - 64;
         const int co = (EPI == 1) ? c : (n_blk * NOUT + c);
         s_shift[c] = p.shift ? p.shift[co] : 0.f;
         if (EPI == 2) s_wf[c] = p.wf[c];
     }
-    if (warp == 0 && lane == 0 && TMAST) prefetch_tmap(&tmO);
     tc_fence_before();
     if (CG == 2) cluster_sync_all();          // the peer's barriers must be initialised before anything signals them
     else __syncthreads();
@@ -703,6 +712,7 @@ struct State {
     // 1 = 128=>128 @16x16, 2 = 64=>64 @32x32 (incl. the fused sampler epilogue), 4 = 128=>64 @32x32 (concat),
     // 8 = 64=>128 @16x16, 16 = the two data-gradient-only shapes (128=>64 @16x16, 64=>128 @32x32)
     int pair_mask = 31;
+    bool pdl = true;            // launch the tcgen05 conv kernels as programmatic dependents of their stream predecessor
 };
 inline State& state() {
     static State s;
@@ -780,26 +790,32 @@ void launch(cudaStream_t st, const CUtensorMap& a0, const CUtensorMap& a1, const
     int ctas_x = state().num_sms / n_blocks_y;
     if (ctas_x > p.num_m_tiles) ctas_x = p.num_m_tiles;
     if (ctas_x < 1) ctas_x = 1;
-    if constexpr (CG == 1) {
-        dim3 grid(ctas_x, n_blocks_y);
-        kern<<<grid, TC_THREADS, smem, st>>>(a0, a1, w, o, p);
-    } else {
+    if (CG == 2) {
         // CTA pairs: clusters of two along x (the hardware co-schedules them on the two SMs of a TPC)
         ctas_x = ((ctas_x + 1) / 2) * 2;
         if (ctas_x > state().num_sms / n_blocks_y) ctas_x -= 2;
         if (ctas_x < 2) ctas_x = 2;
-        cudaLaunchConfig_t cfg{};
-        cfg.gridDim = dim3(ctas_x, n_blocks_y);
-        cfg.blockDim = dim3(TC_THREADS);
-        cfg.dynamicSmemBytes = smem;
-        cfg.stream = st;
-        cudaLaunchAttribute attr[1];
-        attr[0].id = cudaLaunchAttributeClusterDimension;
-        attr[0].val.clusterDim.x = 2; attr[0].val.clusterDim.y = 1; attr[0].val.clusterDim.z = 1;
-        cfg.attrs = attr;
-        cfg.numAttrs = 1;
-        DDPM_CUDA(cudaLaunchKernelEx(&cfg, kern, a0, a1, w, o, p));
     }
+    cudaLaunchConfig_t cfg{};
+    cfg.gridDim = dim3(ctas_x, n_blocks_y);
+    cfg.blockDim = dim3(TC_THREADS);
+    cfg.dynamicSmemBytes = smem;
+    cfg.stream = st;
+    cudaLaunchAttribute attr[2];
+    int na = 0;
+    if (CG == 2) {
+        attr[na].id = cudaLaunchAttributeClusterDimension;
+        attr[na].val.clusterDim.x = 2; attr[na].val.clusterDim.y = 1; attr[na].val.clusterDim.z = 1;
+        ++na;
+    }
+    if (state().pdl) {
+        attr[na].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+        attr[na].val.programmaticStreamSerializationAllowed = 1;
+        ++na;
+    }
+    cfg.attrs = attr;
+    cfg.numAttrs = na;
+    DDPM_CUDA(cudaLaunchKernelEx(&cfg, kern, a0, a1, w, o, p));
     DDPM_LAUNCH_CHECK();
 }
 

@@ -215,7 +215,9 @@ struct Engine {
     // tile, smem-operand bound) is still faster end to end (B200, round 1: 1612 vs 1791 img/s) and stays the default.
     long long opt_conv_v2 = 0;
     long long opt_conv1_tc = 1;    // sampler: first conv on tensor cores (hi/lo split operands) when the batch shares one timestep
-    long long opt_sample_chunk = 512, opt_use_graph = 1, opt_conv_impl = 0 /*0 auto, 1 simt, 2 tc*/, opt_fuse_final = 1;
+    // images per captured reverse-loop graph.  1300 images fill the persistent conv kernels' tile rounds exactly
+    // (32x32 layers: 77.0 rounds of 74 CTA-pair tiles, 16x16 layers: 21.0) -- 512 left the 16x16 layers at 92 %
+    long long opt_sample_chunk = 1300, opt_use_graph = 1, opt_conv_impl = 0 /*0 auto, 1 simt, 2 tc*/, opt_fuse_final = 1;
     long long cnt_launches = 0;
 
     Engine(int T_, int D_, int H_, int W_, int prec_, int dev_);

@@ -256,7 +256,14 @@ static void sample_impl(Engine& e, const float* x_T, const float* z, uint64_t se
     DDPM_CHECK(t_start >= 1 && t_start <= e.T, "t_start out of range 1..T");
     const int HW = e.HW;
     const int steps = t_start - 1;
+    // balanced chunks: ceil(N / ceil(N / sample_chunk)) images each, so a batch slightly over the chunk size does not
+    // leave a small, poorly filled last chunk (Philox noise is keyed by the global image index: chunking never
+    // changes the images)
     long long chunk = std::max<long long>(1, std::min<long long>(e.opt_sample_chunk, N));
+    {
+        const long long k = (N + chunk - 1) / chunk;
+        chunk = (N + k - 1) / k;
+    }
     if (keep_on_device) e.d_sample_out.ensure((size_t)N * HW * 4);
     // derived weights / tables are refreshed once on the main stream; the chunk streams wait for that
     e.prepare_ecls();
@@ -401,6 +408,7 @@ int ddpm_set_option(ddpm_handle* h, const char* key, int64_t value) {
     else if (k == "sync_bn") e.sync_bn = (int)value;
     else if (k == "tc_tma_store") { tc::state().tma_store = value != 0; for (auto& kv : e.infer_sets) kv.second->drop_graphs(); }
     else if (k == "tc_pair") { tc::state().pair_mask = value; for (auto& kv : e.infer_sets) kv.second->drop_graphs(); }
+    else if (k == "tc_pdl") { tc::state().pdl = value != 0; for (auto& kv : e.infer_sets) kv.second->drop_graphs(); }
     else if (k == "conv1_tc") { e.opt_conv1_tc = value; for (auto& kv : e.infer_sets) kv.second->drop_graphs(); }
     else if (k == "conv_v2") { e.opt_conv_v2 = value; for (auto& kv : e.infer_sets) kv.second->drop_graphs(); }
     else if (k == "fuse_final") { e.opt_fuse_final = value; for (auto& kv : e.infer_sets) kv.second->drop_graphs(); }
