@@ -807,6 +807,21 @@ void launch(cudaStream_t st, const CUtensorMap& a0, const CUtensorMap& a1, const
         attr[na].id = cudaLaunchAttributeClusterDimension;
         attr[na].val.clusterDim.x = 2; attr[na].val.clusterDim.y = 1; attr[na].val.clusterDim.z = 1;
         ++na;
+        // the kernel is persistent: never launch more pairs than the device can keep resident at once (a part with
+        // an unpaired SM would otherwise run the surplus pair as a second wave and double the kernel time)
+        static int max_pairs = -1;
+        if (max_pairs < 0) {
+            cfg.attrs = attr;
+            cfg.numAttrs = na;
+            int nc = 0;
+            if (cudaOccupancyMaxActiveClusters(&nc, kern, &cfg) == cudaSuccess && nc > 0) max_pairs = nc;
+            else { cudaGetLastError(); max_pairs = state().num_sms / 2; }
+        }
+        if (ctas_x * n_blocks_y > 2 * max_pairs) {
+            ctas_x = (2 * max_pairs / n_blocks_y) & ~1;
+            if (ctas_x < 2) ctas_x = 2;
+            cfg.gridDim = dim3(ctas_x, n_blocks_y);
+        }
     }
     if (state().pdl) {
         attr[na].id = cudaLaunchAttributeProgrammaticStreamSerialization;
