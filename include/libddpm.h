@@ -121,7 +121,14 @@ int ddpm_apply_noise_f64(const double* img, const double* eps, int64_t n, const 
 int ddpm_comm_unique_id(void* id_out /*128 bytes*/);
 int ddpm_comm_init(ddpm_handle*, const void* id, int rank, int world, int sync_bn);
 
-/* Instrumentation used by bench.py / tests (not needed by the Julia host). */
+/* Instrumentation used by bench.py / tests (not needed by the Julia host).  Option keys (value, default):
+ *   sample_chunk (images per captured reverse-loop graph, 1300; a batch is cut into equal chunks no larger than this),
+ *   sample_streams (1), use_graph (1), conv_impl (0 auto | 1 CUDA-core | 2 tcgen05), sync_bn (1),
+ *   fuse_final (1: last conv + final 1x1 conv + reverse update in one epilogue),
+ *   tc_pair (bit mask of layer shapes run as CTA pairs / cta_group::2, 31 = all), tc_pdl (1: programmatic dependent
+ *   launch of the tcgen05 kernels), conv1_tc (1: first conv of the sampler on tensor cores), tc_tma_store (1),
+ *   conv_v2 (0: second, row-packed conv formulation), tc_role_profile (0: in-kernel cycle counters).
+ * None of them changes results beyond the documented rounding of the selected kernels. */
 int ddpm_set_option(ddpm_handle*, const char* key, int64_t value);
 int64_t ddpm_get_counter(ddpm_handle*, const char* key);
 /* CUDA-event stopwatch on the engine's launch stream (device time of everything enqueued between
