@@ -591,7 +591,7 @@ void Engine::conv3(const Tensor& s0, const Tensor* s1, int l, Tensor& out, bool 
             if (stats) {  // train-mode BatchNorm statistics of the stored (rounded) y
                 long long pixels = (long long)g.N * g.H * g.W;
                 (void)pixels;
-                bn_reduce_linear_kernel<TA, TA, 0><<<cdiv(g.npos, LIN_POS_PER_BLOCK), 256, 0, stream>>>(
+                bn_reduce_linear_kernel<TA, TA, 0><<<lin_reduce_blocks(g.npos, tc::state().num_sms), 256, 0, stream>>>(
                     out.cview<TA>(), out.cview<TA>(), g.npos, c.cout, nullptr, nullptr, nullptr, nullptr, stats);
                 DDPM_LAUNCH_CHECK();
                 cnt_launches += 1;
@@ -762,7 +762,7 @@ void Engine::backward_t(ActSet& s, const float* xt_dev, const int* ts_dev, const
         long long pixels = (long long)N * c.hw * c.hw;
         int blocks = cdiv(pixels, BNB_PIX_PER_BLOCK);
         double m = count_local * c.hw * c.hw;
-        bn_reduce_linear_kernel<TA, TG, 1><<<cdiv(g.npos, LIN_POS_PER_BLOCK), 256, 0, stream>>>(
+        bn_reduce_linear_kernel<TA, TG, 1><<<lin_reduce_blocks(g.npos, tc::state().num_sms), 256, 0, stream>>>(
             s.y[l].cview<TA>(), da, g.npos, c.cout, tr_scale[l], tr_shift[l], tr_mean[l], tr_istd[l], lsum(l));
         if (sync_bn && comm) {
             allreduce_sums(lsum(l), gsum(l), 2 * c.cout);

@@ -562,22 +562,26 @@ bn_bwd_kernel(View<const TA> y, View<const TG> da, View<TG> dy, Geo g, int C, co
 // contiguous, four independent 16-byte loads per operand in flight per thread.
 //   MODE 0: sums[0:C] += sum y, sums[C:2C] += sum y^2                       (forward statistics)
 //   MODE 1: sums[0:C] += sum g, sums[C:2C] += sum g*xhat,  g = da*[y*scale+shift > 0]   (backward pass 1)
-constexpr int LIN_POS_PER_BLOCK = 1024;
+constexpr int LIN_POS_PER_BLOCK = 1024;     // positions per block-chunk; blocks stride over chunks (persistent-style grid)
+
+// launch geometry of bn_reduce_linear_kernel: at most two resident blocks per SM, each striding over 1024-position chunks
+static inline int lin_reduce_blocks(long long npos, int num_sms) {
+    const long long chunks = (npos + LIN_POS_PER_BLOCK - 1) / LIN_POS_PER_BLOCK;
+    const long long cap = 2LL * num_sms;
+    return (int)(chunks < cap ? chunks : cap);
+}
 
 template <typename TA, typename TG, int MODE>
-__global__ void __launch_bounds__(256)
+__global__ void __launch_bounds__(256, 2)
 bn_reduce_linear_kernel(View<const TA> y, View<const TG> da, long long npos, int C, const float* __restrict__ scale,
                         const float* __restrict__ shift, const float* __restrict__ mean, const float* __restrict__ istd,
                         double* __restrict__ sums) {
-    __shared__ float red[2][128];
+    // per-thread partials over all chunks of this block, ONE block-level reduction at the end: a [lanes][C] table in
+    // shared memory summed column-wise (the earlier per-chunk shared-memory float atomics were 32-way contended)
+    __shared__ float red[2][256 * 8];           // [2][lanes * C]: lanes * C == 256 threads * 8 channels == 2048
     const int t = threadIdx.x;
-    if (t < 128) { red[0][t] = 0.f; red[1][t] = 0.f; }
-    __syncthreads();
     const int groups = C / 8, lanes = 256 / groups;
     const int c0 = (t % groups) * 8, pl = t / groups;
-    const long long pbeg = (long long)blockIdx.x * LIN_POS_PER_BLOCK;
-    long long pend = pbeg + LIN_POS_PER_BLOCK;
-    if (pend > npos) pend = npos;
     float sc[8], sh[8], mu[8], is[8], r0[8], r1[8];
 #pragma unroll
     for (int j = 0; j < 8; ++j) {
@@ -585,35 +589,46 @@ bn_reduce_linear_kernel(View<const TA> y, View<const TG> da, long long npos, int
         if (MODE == 1) { sc[j] = scale[c0 + j]; sh[j] = shift[c0 + j]; mu[j] = mean[c0 + j]; is[j] = istd[c0 + j]; }
     }
     constexpr int U = 4;
-    for (long long p0 = pbeg + pl; p0 < pend; p0 += (long long)U * lanes) {
-        float yv[U][8], gv[U][8];
+    const long long nchunks = (npos + LIN_POS_PER_BLOCK - 1) / LIN_POS_PER_BLOCK;
+    for (long long chunk = blockIdx.x; chunk < nchunks; chunk += gridDim.x) {
+        const long long pbeg = chunk * LIN_POS_PER_BLOCK;
+        long long pend = pbeg + LIN_POS_PER_BLOCK;
+        if (pend > npos) pend = npos;
+        for (long long p0 = pbeg + pl; p0 < pend; p0 += (long long)U * lanes) {
+            float yv[U][8], gv[U][8];
 #pragma unroll
-        for (int u = 0; u < U; ++u) {
-            long long pp = p0 + (long long)u * lanes;
-            if (pp >= pend) pp = pend - 1;       // clamp (in-bounds re-read, masked below)
-            V8<TA>::ld(y.p + pp * y.cs + c0, yv[u]);
-            if (MODE == 1) V8<TG>::ld(da.p + pp * da.cs + c0, gv[u]);
-        }
+            for (int u = 0; u < U; ++u) {
+                long long pp = p0 + (long long)u * lanes;
+                if (pp >= pend) pp = pend - 1;       // clamp (in-bounds re-read, masked below)
+                V8<TA>::ld(y.p + pp * y.cs + c0, yv[u]);
+                if (MODE == 1) V8<TG>::ld(da.p + pp * da.cs + c0, gv[u]);
+            }
 #pragma unroll
-        for (int u = 0; u < U; ++u) {
-            const float m = (p0 + (long long)u * lanes < pend) ? 1.f : 0.f;
+            for (int u = 0; u < U; ++u) {
+                const float m = (p0 + (long long)u * lanes < pend) ? 1.f : 0.f;
 #pragma unroll
-            for (int j = 0; j < 8; ++j) {
-                if (MODE == 0) {
-                    const float v = yv[u][j] * m;
-                    r0[j] += v; r1[j] = fmaf(v, v, r1[j]);
-                } else {
-                    const float z = fmaf(yv[u][j], sc[j], sh[j]);
-                    const float gg = z > 0.f ? gv[u][j] * m : 0.f;
-                    r0[j] += gg; r1[j] = fmaf(gg, (yv[u][j] - mu[j]) * is[j], r1[j]);
+                for (int j = 0; j < 8; ++j) {
+                    if (MODE == 0) {
+                        const float v = yv[u][j] * m;
+                        r0[j] += v; r1[j] = fmaf(v, v, r1[j]);
+                    } else {
+                        const float z = fmaf(yv[u][j], sc[j], sh[j]);
+                        const float gg = z > 0.f ? gv[u][j] * m : 0.f;
+                        r0[j] += gg; r1[j] = fmaf(gg, (yv[u][j] - mu[j]) * is[j], r1[j]);
+                    }
                 }
             }
         }
     }
 #pragma unroll
-    for (int j = 0; j < 8; ++j) { atomicAdd(&red[0][c0 + j], r0[j]); atomicAdd(&red[1][c0 + j], r1[j]); }
+    for (int j = 0; j < 8; ++j) { red[0][pl * C + c0 + j] = r0[j]; red[1][pl * C + c0 + j] = r1[j]; }
     __syncthreads();
-    if (t < C) { atomicAdd(&sums[t], (double)red[0][t]); atomicAdd(&sums[C + t], (double)red[1][t]); }
+    if (t < 2 * C) {
+        const int q = t / C, c = t - q * C;
+        float acc = 0.f;
+        for (int l = 0; l < lanes; ++l) acc += red[q][l * C + c];
+        atomicAdd(&sums[q * C + c], (double)acc);
+    }
 }
 
 // after pass 1: local sums -> gradient arena (d beta, d gamma); global sums -> means for pass 2
