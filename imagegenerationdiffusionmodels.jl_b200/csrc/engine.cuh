@@ -760,7 +760,7 @@ void Engine::backward_t(ActSet& s, const float* xt_dev, const int* ts_dev, const
         const ConvSpec& c = kConv[l];
         const Geo& g = s.y[l].g;
         long long pixels = (long long)N * c.hw * c.hw;
-        int blocks = cdiv(pixels, BNB_PIX_PER_BLOCK);
+        int blocks = stride_blocks(pixels, BNB_PIX_PER_BLOCK, tc::state().num_sms, 3);
         double m = count_local * c.hw * c.hw;
         bn_reduce_linear_kernel<TA, TG, 1><<<lin_reduce_blocks(g.npos, tc::state().num_sms), 256, 0, stream>>>(
             s.y[l].cview<TA>(), da, g.npos, c.cout, tr_scale[l], tr_shift[l], tr_mean[l], tr_istd[l], lsum(l));
@@ -797,7 +797,7 @@ void Engine::backward_t(ActSet& s, const float* xt_dev, const int* ts_dev, const
     // ---- final 1x1 conv
     {
         long long pixels = (long long)N * HW;
-        final_bwd_kernel<TA, TG><<<cdiv(pixels, FINAL_BWD_PIX_PER_BLOCK), 256, 0, stream>>>(s.a[10].cview<TA>(), s.g32a.view<TG>(), s.a[10].g,
+        final_bwd_kernel<TA, TG><<<stride_blocks(pixels, FINAL_BWD_PIX_PER_BLOCK, tc::state().num_sms, 4), 256, 0, stream>>>(s.a[10].cview<TA>(), s.g32a.view<TG>(), s.a[10].g,
                                                                       arr(kFinalW), deps_dev, misc_sums + 8);
         f64_to_f32_kernel<<<1, 128, 0, stream>>>(misc_sums + 8, garr(kFinalW), 64, (double)alpha);
         f64_to_f32_kernel<<<1, 32, 0, stream>>>(misc_sums + 72, garr(kFinalB), 1, (double)alpha);
@@ -823,7 +823,7 @@ void Engine::backward_t(ActSet& s, const float* xt_dev, const int* ts_dev, const
         const Geo& gi = s.a[6].g;
         const Geo& go = s.u.g;
         long long pixels = (long long)N * HW;
-        channel_sum_kernel<TG><<<cdiv(pixels, BNB_PIX_PER_BLOCK), 256, 0, stream>>>(s.g32a.cview<TG>(), go, 64, misc_sums + 128);
+        channel_sum_kernel<TG><<<stride_blocks(pixels, BNB_PIX_PER_BLOCK, tc::state().num_sms, 4), 256, 0, stream>>>(s.g32a.cview<TG>(), go, 64, misc_sums + 128);
         f64_to_f32_kernel<<<1, 128, 0, stream>>>(misc_sums + 128, garr(kUpB), 64, (double)alpha);
         // da6[in][ci] = sum_{q,co} du[outpos(in,q)][co] * Wtd[ci][q*64+co]
         bool done = false;

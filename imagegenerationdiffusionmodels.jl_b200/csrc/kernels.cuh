@@ -457,34 +457,39 @@ template <typename TA, typename TG>
 __global__ void __launch_bounds__(256)
 final_bwd_kernel(View<const TA> a, View<TG> da, Geo g, const float* __restrict__ wf, const float* __restrict__ deps,
                  double* __restrict__ sums /*[64 dwf | 1 dbf]*/) {
-    __shared__ float red[65];
+    __shared__ float red[32 * 65];                    // [pixel lane][64 dwf | dbf], reduced once per block
     const int t = threadIdx.x;
-    if (t < 65) red[t] = 0.f;
-    __syncthreads();
     const int c0 = (t & 7) * 8, pl = t >> 3;          // 8 lanes per pixel, 32 pixels per pass
     const int HW = g.H * g.W;
     const long long total = (long long)g.N * HW;
-    const long long pbeg = (long long)blockIdx.x * FINAL_BWD_PIX_PER_BLOCK;
     float w8[8], acc[8], accb = 0.f;
 #pragma unroll
     for (int j = 0; j < 8; ++j) { w8[j] = wf[c0 + j]; acc[j] = 0.f; }
-    for (long long pix = pbeg + pl; pix < pbeg + FINAL_BWD_PIX_PER_BLOCK && pix < total; pix += 32) {
-        const int n = (int)(pix / HW);
-        const int rem = (int)(pix - (long long)n * HW);
-        const long long p = g.pos(n, rem / g.W, rem % g.W);
-        const float d = deps[pix];
-        float v[8], o[8];
-        V8<TA>::ld(a.p + p * a.cs + c0, v);
+    const long long nchunks = (total + FINAL_BWD_PIX_PER_BLOCK - 1) / FINAL_BWD_PIX_PER_BLOCK;
+    for (long long chunk = blockIdx.x; chunk < nchunks; chunk += gridDim.x) {
+        const long long pbeg = chunk * FINAL_BWD_PIX_PER_BLOCK;
+        for (long long pix = pbeg + pl; pix < pbeg + FINAL_BWD_PIX_PER_BLOCK && pix < total; pix += 32) {
+            const int n = (int)(pix / HW);
+            const int rem = (int)(pix - (long long)n * HW);
+            const long long p = g.pos(n, rem / g.W, rem % g.W);
+            const float d = deps[pix];
+            float v[8], o[8];
+            V8<TA>::ld(a.p + p * a.cs + c0, v);
 #pragma unroll
-        for (int j = 0; j < 8; ++j) { o[j] = d * w8[j]; acc[j] = fmaf(d, v[j], acc[j]); }
-        V8<TG>::st(da.p + p * da.cs + c0, o);
-        if (c0 == 0) accb += d;
+            for (int j = 0; j < 8; ++j) { o[j] = d * w8[j]; acc[j] = fmaf(d, v[j], acc[j]); }
+            V8<TG>::st(da.p + p * da.cs + c0, o);
+            if (c0 == 0) accb += d;
+        }
     }
 #pragma unroll
-    for (int j = 0; j < 8; ++j) atomicAdd(&red[c0 + j], acc[j]);
-    if (c0 == 0) atomicAdd(&red[64], accb);
+    for (int j = 0; j < 8; ++j) red[pl * 65 + c0 + j] = acc[j];
+    if (c0 == 0) red[pl * 65 + 64] = accb;
     __syncthreads();
-    if (t < 65) atomicAdd(&sums[t], (double)red[t]);
+    if (t < 65) {
+        float s = 0.f;
+        for (int l = 0; l < 32; ++l) s += red[l * 65 + t];
+        atomicAdd(&sums[t], (double)s);
+    }
 }
 
 // ------------------------------------------------------------------------------------ BatchNorm backward
@@ -494,23 +499,26 @@ final_bwd_kernel(View<const TA> a, View<TG> da, Geo g, const float* __restrict__
 // Each thread owns 8 channels and walks PIX_PER_THREAD pixels, so the block-level reduction is
 // one shared-memory atomic per channel per thread.
 constexpr int BNB_PIX_PER_BLOCK = 512;
+// grid of the chunk-striding backward kernels: at most `per_sm` resident blocks per SM
+static inline int stride_blocks(long long items, int per_block, int num_sms, int per_sm) {
+    const long long chunks = (items + per_block - 1) / per_block;
+    const long long cap = (long long)per_sm * num_sms;
+    return (int)(chunks < cap ? (chunks < 1 ? 1 : chunks) : cap);
+}
 
 template <typename TA, typename TG, int PASS>
 __global__ void __launch_bounds__(256)
 bn_bwd_kernel(View<const TA> y, View<const TG> da, View<TG> dy, Geo g, int C, const float* __restrict__ scale,
               const float* __restrict__ shift, const float* __restrict__ mean, const float* __restrict__ istd,
               const float* __restrict__ mg, const float* __restrict__ mgx, double* __restrict__ sums) {
-    __shared__ float red[2][128];
+    // blocks stride over 512-pixel chunks; per-thread partial sums live in registers for the whole block and are reduced
+    // ONCE through a [lanes][C] shared-memory table (per-chunk shared float atomics were 32-way contended)
+    __shared__ float red[2][256 * 8];
     const int t = threadIdx.x;
-    if (t < 128) { red[0][t] = 0.f; red[1][t] = 0.f; }
-    __syncthreads();
     const int groups = C / 8;
     const int lanes = 256 / groups;
     const int c0 = (t % groups) * 8, pl = t / groups;
     const long long total = (long long)g.N * g.H * g.W;
-    const long long pbeg = (long long)blockIdx.x * BNB_PIX_PER_BLOCK;
-    long long pend = pbeg + BNB_PIX_PER_BLOCK;
-    if (pend > total) pend = total;
     float sc[8], sh[8], mu[8], is[8], a0[8], a1[8], r0[8], r1[8];
 #pragma unroll
     for (int j = 0; j < 8; ++j) {
@@ -519,41 +527,46 @@ bn_bwd_kernel(View<const TA> y, View<const TG> da, View<TG> dy, Geo g, int C, co
         if (PASS == 2) { a0[j] = mg[c0 + j]; a1[j] = mgx[c0 + j]; }
     }
     const int HW = g.H * g.W;
-    for (long long pix = pbeg + pl; pix < pend; pix += lanes) {
-        int n = (int)(pix / HW);
-        int rem = (int)(pix - (long long)n * HW);
-        long long p = g.pos(n, rem / g.W, rem % g.W);
-        float yv[8], gv[8];
-        V8<TA>::ld(y.p + p * y.cs + c0, yv);
-        V8<TG>::ld(da.p + p * da.cs + c0, gv);
-        float o[8];
+    const long long nchunks = (total + BNB_PIX_PER_BLOCK - 1) / BNB_PIX_PER_BLOCK;
+    for (long long chunk = blockIdx.x; chunk < nchunks; chunk += gridDim.x) {
+        const long long pbeg = chunk * BNB_PIX_PER_BLOCK;
+        long long pend = pbeg + BNB_PIX_PER_BLOCK;
+        if (pend > total) pend = total;
+        for (long long pix = pbeg + pl; pix < pend; pix += lanes) {
+            int n = (int)(pix / HW);
+            int rem = (int)(pix - (long long)n * HW);
+            long long p = g.pos(n, rem / g.W, rem % g.W);
+            float yv[8], gv[8];
+            V8<TA>::ld(y.p + p * y.cs + c0, yv);
+            V8<TG>::ld(da.p + p * da.cs + c0, gv);
+            float o[8];
 #pragma unroll
-        for (int j = 0; j < 8; ++j) {
-            float z = fmaf(yv[j], sc[j], sh[j]);
-            float gg = z > 0.f ? gv[j] : 0.f;
-            float xh = (yv[j] - mu[j]) * is[j];
-            if (PASS == 1) {
-                r0[j] += gg; r1[j] += gg * xh;
-            } else {
-                float d = sc[j] * (gg - a0[j] - xh * a1[j]);
-                o[j] = d; r0[j] += d;
+            for (int j = 0; j < 8; ++j) {
+                float z = fmaf(yv[j], sc[j], sh[j]);
+                float gg = z > 0.f ? gv[j] : 0.f;
+                float xh = (yv[j] - mu[j]) * is[j];
+                if (PASS == 1) {
+                    r0[j] += gg; r1[j] += gg * xh;
+                } else {
+                    float d = sc[j] * (gg - a0[j] - xh * a1[j]);
+                    o[j] = d; r0[j] += d;
+                }
             }
+            if (PASS == 2) V8<TG>::st(dy.p + p * dy.cs + c0, o);
         }
-        if (PASS == 2) V8<TG>::st(dy.p + p * dy.cs + c0, o);
     }
 #pragma unroll
     for (int j = 0; j < 8; ++j) {
-        atomicAdd(&red[0][c0 + j], r0[j]);
-        if (PASS == 1) atomicAdd(&red[1][c0 + j], r1[j]);
+        red[0][pl * C + c0 + j] = r0[j];
+        if (PASS == 1) red[1][pl * C + c0 + j] = r1[j];
     }
     __syncthreads();
-    if (t < C) {
-        if (PASS == 1) {
-            atomicAdd(&sums[t], (double)red[0][t]);
-            atomicAdd(&sums[C + t], (double)red[1][t]);
-        } else {
-            atomicAdd(&sums[2 * C + t], (double)red[0][t]);
-        }
+    const int nq = (PASS == 1) ? 2 : 1;
+    if (t < nq * C) {
+        const int q = t / C, c = t - q * C;
+        float acc = 0.f;
+        for (int l = 0; l < lanes; ++l) acc += red[q][l * C + c];
+        atomicAdd(&sums[(PASS == 1 ? q : 2) * C + c], (double)acc);
     }
 }
 
@@ -810,32 +823,37 @@ __global__ void l1_wimg_grad_kernel(const float* __restrict__ Tw, long long B, f
 template <typename TG>
 __global__ void __launch_bounds__(256)
 channel_sum_kernel(View<const TG> d, Geo g, int C, double* __restrict__ sums) {
-    __shared__ float red[128];
+    __shared__ float red[256 * 8];                    // [lanes][C], reduced once per block (blocks stride over chunks)
     const int t = threadIdx.x;
-    if (t < 128) red[t] = 0.f;
-    __syncthreads();
     const int groups = C / 8, lanes = 256 / groups;
     const int c0 = (t % groups) * 8, pl = t / groups;
     const long long total = (long long)g.N * g.H * g.W;
-    const long long pbeg = (long long)blockIdx.x * BNB_PIX_PER_BLOCK;
-    long long pend = pbeg + BNB_PIX_PER_BLOCK;
-    if (pend > total) pend = total;
     float r[8];
 #pragma unroll
     for (int j = 0; j < 8; ++j) r[j] = 0.f;
     const int HW = g.H * g.W;
-    for (long long pix = pbeg + pl; pix < pend; pix += lanes) {
-        int n = (int)(pix / HW);
-        int rem = (int)(pix - (long long)n * HW);
-        float v[8];
-        V8<TG>::ld(d.p + g.pos(n, rem / g.W, rem % g.W) * d.cs + c0, v);
+    const long long nchunks = (total + BNB_PIX_PER_BLOCK - 1) / BNB_PIX_PER_BLOCK;
+    for (long long chunk = blockIdx.x; chunk < nchunks; chunk += gridDim.x) {
+        const long long pbeg = chunk * BNB_PIX_PER_BLOCK;
+        long long pend = pbeg + BNB_PIX_PER_BLOCK;
+        if (pend > total) pend = total;
+        for (long long pix = pbeg + pl; pix < pend; pix += lanes) {
+            int n = (int)(pix / HW);
+            int rem = (int)(pix - (long long)n * HW);
+            float v[8];
+            V8<TG>::ld(d.p + g.pos(n, rem / g.W, rem % g.W) * d.cs + c0, v);
 #pragma unroll
-        for (int j = 0; j < 8; ++j) r[j] += v[j];
+            for (int j = 0; j < 8; ++j) r[j] += v[j];
+        }
     }
 #pragma unroll
-    for (int j = 0; j < 8; ++j) atomicAdd(&red[c0 + j], r[j]);
+    for (int j = 0; j < 8; ++j) red[pl * C + c0 + j] = r[j];
     __syncthreads();
-    if (t < C) atomicAdd(&sums[t], (double)red[t]);
+    if (t < C) {
+        float acc = 0.f;
+        for (int l = 0; l < lanes; ++l) acc += red[l * C + t];
+        atomicAdd(&sums[t], (double)acc);
+    }
 }
 
 // per-channel sum and sum of squares over valid pixels (train-mode BatchNorm statistics when the
