@@ -6,14 +6,17 @@
 // M-tile of 128 consecutive positions a CTA
 //   1. TMA-loads ONE halo'ed slab of rows [m0-(Wp+1), m0+128+(Wp+1)) x 64 channels into shared memory
 //      (128B-swizzled, K-major) -- 1.5x the tile instead of the 9x an im2col gather would move;
-//   2. issues 9 taps x 4 K-steps of tcgen05.mma (M=128, N=64|128, K=16, kind::f16, FP32 accumulate
-//      in TMEM); tap (dy,dx) is just the shared-memory matrix descriptor advanced by that many
-//      128-byte rows -- no data is moved between taps;
-//   3. drains the accumulator with tcgen05.ld in 4 epilogue warps: y = acc*scale[c]+shift[c], ReLU,
-//      convert, store valid positions (halo positions are never written and stay zero).
+//   2. issues 9 taps x 4 K-steps of tcgen05.mma (kind::f16, FP32 accumulate in TMEM); tap (dy,dx) is just
+//      the shared-memory matrix descriptor advanced by that many 128-byte rows -- no data is moved
+//      between taps;
+//   3. drains the accumulator with tcgen05.ld: y = acc + shift[c] (any scale is folded into the weights),
+//      ReLU, convert, store (halo positions hold zeros).
 // The 9*Cin x Cout weights stay resident in shared memory for the lifetime of the persistent CTA.
-// Warp roles: warp 0 = TMA producer, warp 1 = MMA issuer (one thread), warps 2..5 = epilogue;
-// smem full/empty ring (TMA <-> MMA) and a 2-deep TMEM full/empty ring (MMA <-> epilogue).
+// By default two CTAs form a pair (cluster of 2, cta_group::2): M = 256 per instruction, each CTA stages
+// its own slab and half of the weight rows (see the comment above conv_tc_kernel).
+// Warp roles (352 threads): warp 0 = TMA producer, warps 1 and 6 = MMA issuers (alternate tiles), warps
+// 2..5 and 7..10 = two epilogue sets (alternate tiles); smem full/empty ring (TMA <-> MMA), one barrier per
+// weight tile, and a 4-deep TMEM full/empty ring (MMA <-> epilogue).
 //
 // Replaces NNlib.conv / ∇conv_data (im2col + SGEMM) behind Flux.Conv at
 // /root/reference/src/train_brain.jl:113-140 (forward) and Zygote's pullback (:267-269).

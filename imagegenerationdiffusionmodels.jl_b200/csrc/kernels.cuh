@@ -729,10 +729,10 @@ template <> __device__ __forceinline__ void ld4<__nv_bfloat16>(const __nv_bfloat
 template <typename TG>
 __global__ void __launch_bounds__(256)
 l1_bwd_kernel(View<const TG> dy, Geo g, const float* __restrict__ x, float* __restrict__ Tw, float* __restrict__ Ccls) {
-    __shared__ float tw_s[9 * 64], cl_s[9 * 64];
+    // block reduction: the two pixel lanes of a warp are combined with one shuffle, the eight warps through a
+    // [2][8][576] shared-memory table summed by all threads (72 contended shared-memory atomics per thread before)
+    __shared__ float red[2][8][9 * 64];
     const int t = threadIdx.x, n = blockIdx.x;
-    for (int i = t; i < 576; i += 256) { tw_s[i] = 0.f; cl_s[i] = 0.f; }
-    __syncthreads();
     const int H = g.H, W = g.W, TW = W + 2;
     const int c0 = (t & 15) * 4, pl = t >> 4;
     const float* xi = x + (long long)n * H * W;
@@ -768,17 +768,25 @@ l1_bwd_kernel(View<const TG> dy, Geo g, const float* __restrict__ x, float* __re
             for (int j = 0; j < 4; ++j) tw[tap][j] = fmaf(d[j], xv, tw[tap][j]);
         }
     }
+    const int warp = t >> 5;
 #pragma unroll
     for (int tap = 0; tap < 9; ++tap)
 #pragma unroll
         for (int j = 0; j < 4; ++j) {
-            atomicAdd(&tw_s[tap * 64 + c0 + j], tw[tap][j]);
-            atomicAdd(&cl_s[tap * 64 + c0 + j], cl[tap][j]);
+            const float a = tw[tap][j] + __shfl_xor_sync(0xffffffffu, tw[tap][j], 16);
+            const float b = cl[tap][j] + __shfl_xor_sync(0xffffffffu, cl[tap][j], 16);
+            if ((t & 16) == 0) {
+                red[0][warp][tap * 64 + c0 + j] = a;
+                red[1][warp][tap * 64 + c0 + j] = b;
+            }
         }
     __syncthreads();
-    for (int i = t; i < 576; i += 256) {
-        Tw[(long long)n * 576 + i] = tw_s[i];
-        Ccls[(long long)n * 576 + i] = cl_s[i];
+    for (int i = t; i < 2 * 576; i += 256) {
+        const int q = i / 576, k = i - q * 576;
+        float acc = 0.f;
+#pragma unroll
+        for (int w8 = 0; w8 < 8; ++w8) acc += red[q][w8][k];
+        (q == 0 ? Tw : Ccls)[(long long)n * 576 + k] = acc;
     }
 }
 
