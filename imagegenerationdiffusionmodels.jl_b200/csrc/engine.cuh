@@ -505,13 +505,24 @@ inline ActSet& Engine::get_set(int N, bool training, int slot) {
 // ------------------------------------------------------------------------------------ derived weights
 template <typename TA, typename TG>
 void Engine::pack_weights_t() {
+    PackJobs J{};
+    long long nmax = 0;
     for (int l = 2; l <= NUM_CONV; ++l) {
         const ConvSpec& c = kConv[l];
-        long long n = 9LL * c.cin * c.cout;
-        pack_conv3_kernel<TA><<<cdiv(n, 256), 256, 0, stream>>>(arr(c.w), c.cin, 0, c.cin, c.cout, 0, nullptr, (TA*)Wf[l]);
-        pack_conv3_kernel<TG><<<cdiv(n, 256), 256, 0, stream>>>(arr(c.w), c.cin, 0, c.cin, c.cout, 1, nullptr, (TG*)Wd[l]);
-        pack_conv3_rows_kernel<TA><<<cdiv(n, 256), 256, 0, stream>>>(arr(c.w), c.cin, c.cout, 0, nullptr, (TA*)W3f[l]);
-        pack_conv3_rows_kernel<TG><<<cdiv(n, 256), 256, 0, stream>>>(arr(c.w), c.cin, c.cout, 1, nullptr, (TG*)W3d[l]);
+        J.w[l - 2] = arr(c.w); J.cin[l - 2] = c.cin; J.cout[l - 2] = c.cout;
+        J.out_f[l - 2] = Wf[l]; J.out_d[l - 2] = Wd[l]; J.row_scale[l - 2] = nullptr;
+        nmax = std::max(nmax, 9LL * c.cin * c.cout);
+    }
+    pack_conv3_batch_kernel<TA, TG><<<dim3(cdiv(nmax, 256), NUM_CONV - 1, 2), 256, 0, stream>>>(J);
+    cnt_launches += 1;
+    if (opt_conv_v2) {      // the row-packed layouts are only read by the second conv formulation (conv3_tc.cuh)
+        for (int l = 2; l <= NUM_CONV; ++l) {
+            const ConvSpec& c = kConv[l];
+            long long n = 9LL * c.cin * c.cout;
+            pack_conv3_rows_kernel<TA><<<cdiv(n, 256), 256, 0, stream>>>(arr(c.w), c.cin, c.cout, 0, nullptr, (TA*)W3f[l]);
+            pack_conv3_rows_kernel<TG><<<cdiv(n, 256), 256, 0, stream>>>(arr(c.w), c.cin, c.cout, 1, nullptr, (TG*)W3d[l]);
+        }
+        cnt_launches += 2 * (NUM_CONV - 1);
     }
     long long nt = 4LL * 128 * 64;
     pack_up2_kernel<TA><<<cdiv(nt, 256), 256, 0, stream>>>(arr(kUpW), 128, 64, 0, (TA*)Wt);
@@ -519,7 +530,7 @@ void Engine::pack_weights_t() {
     long long n1 = 9LL * 64 * (D + 1);
     pack_l1_kernel<<<cdiv(n1, 256), 256, 0, stream>>>(arr(0), D, 64, Wimg, Wemb);
     DDPM_LAUNCH_CHECK();
-    cnt_launches += 4 * (NUM_CONV - 1) + 3;
+    cnt_launches += 3;
 }
 
 inline void Engine::pack_weights() {
@@ -542,14 +553,25 @@ inline void Engine::prepare_ecls() {
 
 template <typename TA, typename TG>
 void Engine::pack_infer_weights_t() {
+    PackJobs J{};
+    long long nmax = 0;
     for (int l = 2; l <= NUM_CONV; ++l) {
         const ConvSpec& c = kConv[l];
-        long long n = 9LL * c.cin * c.cout;
-        pack_conv3_kernel<TA><<<cdiv(n, 256), 256, 0, stream>>>(arr(c.w), c.cin, 0, c.cin, c.cout, 0, inf_scale[l], (TA*)Wfi[l]);
-        pack_conv3_rows_kernel<TA><<<cdiv(n, 256), 256, 0, stream>>>(arr(c.w), c.cin, c.cout, 0, inf_scale[l], (TA*)W3fi[l]);
+        J.w[l - 2] = arr(c.w); J.cin[l - 2] = c.cin; J.cout[l - 2] = c.cout;
+        J.out_f[l - 2] = Wfi[l]; J.out_d[l - 2] = nullptr; J.row_scale[l - 2] = inf_scale[l];
+        nmax = std::max(nmax, 9LL * c.cin * c.cout);
+    }
+    pack_conv3_batch_kernel<TA, TG><<<dim3(cdiv(nmax, 256), NUM_CONV - 1, 1), 256, 0, stream>>>(J);
+    cnt_launches += 1;
+    if (opt_conv_v2) {
+        for (int l = 2; l <= NUM_CONV; ++l) {
+            const ConvSpec& c = kConv[l];
+            long long n = 9LL * c.cin * c.cout;
+            pack_conv3_rows_kernel<TA><<<cdiv(n, 256), 256, 0, stream>>>(arr(c.w), c.cin, c.cout, 0, inf_scale[l], (TA*)W3fi[l]);
+        }
+        cnt_launches += NUM_CONV - 1;
     }
     DDPM_LAUNCH_CHECK();
-    cnt_launches += 2 * (NUM_CONV - 1);
 }
 
 // Inference: BatchNorm with running statistics is a per-channel affine map; its scale is folded into

@@ -957,6 +957,34 @@ __global__ void pack_conv3_kernel(const float* __restrict__ w, int Cin_total, in
         out[i] = from_f<TW>(w[(1 + dx) + 3 * (1 + dy) + 9LL * (ci + ci_off) + 9LL * Cin_total * co]);
     }
 }
+// All 3x3 convolutions of the network in ONE launch (the training step re-packs after every Adam update; nine to
+// eighteen 3-us launches were a visible share of a small-batch step): blockIdx.y = layer, blockIdx.z = 0 forward
+// layout (type TA, optional per-output-channel scale), 1 data-gradient layout (type TG).
+struct PackJobs {
+    const float* w[9];
+    int cin[9], cout[9];
+    void* out_f[9];
+    void* out_d[9];
+    const float* row_scale[9];
+};
+template <typename TA, typename TG>
+__global__ void pack_conv3_batch_kernel(const PackJobs J) {
+    const int l = blockIdx.y, dgrad = blockIdx.z;
+    const int Cin = J.cin[l], Cout = J.cout[l];
+    const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= 9LL * Cin * Cout) return;
+    const float* __restrict__ w = J.w[l];
+    if (!dgrad) {
+        const int ci = (int)(i % Cin), tap = (int)((i / Cin) % 9), co = (int)(i / (9LL * Cin));
+        const int dy = tap / 3 - 1, dx = tap % 3 - 1;
+        const float v = w[(1 - dx) + 3 * (1 - dy) + 9LL * ci + 9LL * Cin * co];
+        reinterpret_cast<TA*>(J.out_f[l])[i] = from_f<TA>(J.row_scale[l] ? v * J.row_scale[l][co] : v);
+    } else {
+        const int co = (int)(i % Cout), tap = (int)((i / Cout) % 9), ci = (int)(i / (9LL * Cout));
+        const int dy = tap / 3 - 1, dx = tap % 3 - 1;
+        reinterpret_cast<TG*>(J.out_d[l])[i] = from_f<TG>(w[(1 + dx) + 3 * (1 + dy) + 9LL * ci + 9LL * Cin * co]);
+    }
+}
 // Row-packed layout of conv3_tc.cuh: rows = (out-channel block of 64) x (dx, channel) = 192 per block, cols = (dy, k).
 //   forward : out channel = Flux co, k = Flux ci :  w[1-dx, 1-dy, ci, co] * row_scale[co]
 //   dgrad   : out channel = Flux ci, k = Flux co :  w[1+dx, 1+dy, ci, co]

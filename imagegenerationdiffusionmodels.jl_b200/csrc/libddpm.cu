@@ -410,7 +410,12 @@ int ddpm_set_option(ddpm_handle* h, const char* key, int64_t value) {
     else if (k == "tc_pair") { tc::state().pair_mask = value; for (auto& kv : e.infer_sets) kv.second->drop_graphs(); }
     else if (k == "tc_pdl") { tc::state().pdl = value != 0; for (auto& kv : e.infer_sets) kv.second->drop_graphs(); }
     else if (k == "conv1_tc") { e.opt_conv1_tc = value; for (auto& kv : e.infer_sets) kv.second->drop_graphs(); }
-    else if (k == "conv_v2") { e.opt_conv_v2 = value; for (auto& kv : e.infer_sets) kv.second->drop_graphs(); }
+    else if (k == "conv_v2") {
+        const bool turn_on = value && !e.opt_conv_v2;
+        e.opt_conv_v2 = value;
+        if (turn_on) e.pack_weights();        // the row-packed weight layouts are only maintained while the option is on
+        for (auto& kv : e.infer_sets) kv.second->drop_graphs();
+    }
     else if (k == "fuse_final") { e.opt_fuse_final = value; for (auto& kv : e.infer_sets) kv.second->drop_graphs(); }
     else if (k == "tc_role_profile") {
         // per-CTA cycle breakdown of the tcgen05 kernel roles, read back with ddpm_debug_fetch("tc_roles")
