@@ -56,12 +56,29 @@ def main():
         # conv biases in front of a train-mode BatchNorm have a mathematically zero gradient; Adam turns the
         # rounding noise there into +-eta steps, so those ten arrays are not comparable between any two runs
         free = {1, 7, 13, 19, 25, 31, 39, 45, 51, 57}
-        wrel = max(float(np.linalg.norm(a - b) / max(np.linalg.norm(b), 1e-12))
-                   for k, (a, b) in enumerate(zip(w_dp, w_ref)) if k not in free and np.linalg.norm(b) > 1e-3)
-        verdict.update(dp_losses=dp_losses, ref_losses=ref_losses, loss_rel=rel, weight_rel=wrel)
-        # Adam's first steps are sign-like (m/sqrt(v) ~ +-1), so 16-bit rounding differences between the two
-        # batch splits show up as O(eta) differences on small-norm arrays: loose bound in fp16 mode
-        ok &= max(rel) < (1e-4 if prec == capi.PREC_FP32 else 2e-3) and wrel < (5e-3 if prec == capi.PREC_FP32 else 5e-2)
+        # Criteria.  (i) arrays that carry real signal (norm > 0.05: all conv / ConvTranspose kernels): relative L2.
+        # (ii) every comparable array: Adam's first steps are sign-like (m/sqrt(v) ~ +-1), so an element whose gradient
+        # is rounding noise may move by up to eta per step in either direction in each run -- the hard bound between any
+        # two correct runs is 2*steps*eta per element; small-norm arrays (BatchNorm shifts near zero) are judged by that
+        # bound only, a relative norm over a handful of +-eta flips is meaningless for them.
+        eta, steps = 1e-4, 3
+        bases = (0, 6, 12, 18, 24, 30, 38, 44, 50, 56)
+        running = {b + 4 for b in bases} | {b + 5 for b in bases}      # BatchNorm running mean / variance: not Adam-updated
+        per = []
+        for k, (a, b) in enumerate(zip(w_dp, w_ref)):
+            if k in free:
+                continue
+            nb = float(np.linalg.norm(b))
+            per.append((k, nb, float(np.linalg.norm(a - b) / max(nb, 1e-12)), float(np.abs(a - b).max())))
+        big = [p for p in per if p[1] > 0.05]
+        wrel = max(p[2] for p in big)
+        wabs = max(p[3] for p in per if p[0] not in running)
+        worst = max(per, key=lambda p: p[2])
+        verdict.update(dp_losses=dp_losses, ref_losses=ref_losses, loss_rel=rel, weight_rel=wrel, adam_max_abs=wabs,
+                       worst_array={"index": worst[0], "norm": worst[1], "rel": worst[2], "max_abs": worst[3]})
+        ok &= max(rel) < (1e-4 if prec == capi.PREC_FP32 else 2e-3)
+        ok &= wrel < (5e-3 if prec == capi.PREC_FP32 else 5e-2)      # includes the running statistics (norm > 0.05)
+        ok &= wabs <= 2 * steps * eta * 1.01
         ref.close()
     # every rank must hold identical weights after the all-reduced update
     w0 = torch.tensor(np.concatenate([w.ravel() for w in w_dp])).cuda()
