@@ -97,3 +97,14 @@ def test_product_never_imports_the_oracle():
             if f.endswith((".py", ".cu", ".cuh", ".jl")):
                 txt = open(os.path.join(dirpath, f), errors="replace").read()
                 assert "ddpm_oracle" not in txt and "oracle/" not in txt, os.path.join(dirpath, f)
+
+
+def test_every_option_key_is_documented_in_the_header():
+    """ddpm_set_option keys accepted by the library (csrc/libddpm.cu) == keys listed in include/libddpm.h."""
+    src = open(os.path.join(ROOT, "imagegenerationdiffusionmodels.jl_b200", "csrc", "libddpm.cu")).read()
+    body = src[src.index("int ddpm_set_option("):src.index("int64_t ddpm_get_counter(")]
+    accepted = set(re.findall(r'k == "([a-z0-9_]+)"', body))
+    hdr = open(os.path.join(ROOT, "include", "libddpm.h")).read()
+    doc = hdr[hdr.index("Option keys"):hdr.index("int ddpm_set_option(")]
+    documented = set(re.findall(r"\b([a-z0-9]+(?:_[a-z0-9]+)+)\b", doc)) & (accepted | {"x"})
+    assert accepted and accepted == documented, accepted ^ documented
