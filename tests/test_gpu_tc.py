@@ -185,5 +185,7 @@ def test_first_conv_on_tensor_cores_matches_cuda_core_kernel(gpu_handles, model_
         h.set_option("conv1_tc", 1)
         _dump("conv1_tc_vs_simt.json", rep)
     assert rep["max_abs_a1"] > 0.1 and rep["frac_nonzero"] > 0.2, rep     # the layer really ran on real data
-    assert rep["frac_mismatch"] < 0.03 and rep["max_err_ulp"] <= 1.0, rep
+    # measured: 0.27 % of the elements differ, all by exactly one rounding step; the bound allows the second step that
+    # a small output after cancellation may take (tests/test_split_arithmetic.py)
+    assert rep["frac_mismatch"] < 0.03 and rep["max_err_ulp"] <= 2.0, rep
     assert rep["sampler_max_abs_diff"] < 1e-3, rep
