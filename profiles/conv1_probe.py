@@ -1,4 +1,7 @@
-"""Tensor-core first conv (hi/lo split operands) against the CUDA-core FP32 kernel inside the sampler."""
+"""Tensor-core first conv (hi/lo split operands) against the CUDA-core FP32 kernel inside the sampler.
+Note: after a full forward the a1 buffer is aliased by later layers -- the layer-level comparison lives in
+tests/test_gpu_tc.py (ddpm_time_kernel("conv1") leaves the first conv's output in place); this probe reports the
+sampler-level drift and the timings."""
 import os
 import sys
 
@@ -15,12 +18,6 @@ beta, _, acum = tables.beta_schedule(500)
 h.set_tables(beta, acum, tables.embedding_table(500))
 h.set_weights(api.SimpleUNet.load().arrays)
 rng = np.random.default_rng(0)
-sys.path.insert(0, os.path.join(ROOT, "oracle"))
-import torch  # noqa: E402
-import ddpm_oracle as oracle  # noqa: E402  (dev probe only: reference for the first layer)
-arrays = api.SimpleUNet.load().arrays
-net = oracle.Net(arrays)
-pe = tables.embedding_table(500)
 for B, tstart in ((5, 2), (37, 3), (3, 500)):
     xT = (3.0 * rng.standard_normal((B, 1, 32, 32))).astype(np.float32)
     z = rng.standard_normal((tstart - 1, B, 1, 32, 32)).astype(np.float32)
@@ -29,16 +26,6 @@ for B, tstart in ((5, 2), (37, 3), (3, 500)):
         h.set_option("conv1_tc", m)
         img = h.sample(B, x_T=xT, z=z, t_start=tstart)
         out[m] = (img, h.debug_fetch("infer:a1"))
-    if tstart == 2:
-        taps = {}
-        with torch.no_grad():
-            oracle.unet_forward(net, torch.tensor(xT), torch.tensor(np.repeat(pe[1:2], B, 0)), train=False, taps=taps)
-        want = taps["a1"].numpy().ravel()
-        for m in (0, 1):
-            e = out[m][1].ravel() - want
-            ulp = np.maximum(np.abs(want), 6.1e-5) * 2.0 ** -10
-            print(f"   conv1_tc={m}: a1 vs fp32 oracle: max abs err {np.abs(e).max():.3e}, rms err/ulp {np.sqrt(np.mean((e/ulp)**2)):.3f}, "
-                  f"frac |err| > 0.51 ulp: {np.mean(np.abs(e) > 0.51 * ulp):.4f}", flush=True)
     d = np.abs(out[0][1] - out[1][1])
     print(f"B={B} t_start={tstart}: a1 max abs diff {d.max():.3e} (max |a1| {np.abs(out[0][1]).max():.3f}), "
           f"mismatching elements {int((d > 0).sum())} of {d.size}; sample max diff {np.abs(out[0][0] - out[1][0]).max():.3e}", flush=True)
