@@ -6,10 +6,10 @@
   python bench.py --impl reference ...                     (CPU restatement of the Flux path)
 
 A "step" is one full pass of the hot path over one batch: `--images` images per GPU taken
-through all T-1 = 499 U-Net evaluations + reverse updates (BASELINE config 4 sharded: 12.6 steps of
-5200 images == the 65,536-image job on one GPU; 5200 = 4 graph chunks of 1300, the chunk size that fills the
-persistent kernels' tile rounds exactly).  Weak scaling: every rank samples its own
-`--images` images per step, global image indices are disjoint, no data-path collective.
+through all T-1 = 499 U-Net evaluations + reverse updates (5200 = 4 graph chunks of 1300, the chunk size that fills
+the persistent kernels' tile rounds exactly; 12.6 such steps == BASELINE config 4).  The end-to-end leg (`e2e`) runs
+config 4 LITERALLY: one `ddpm_sample(N=65536)` call through the C ABI per rank, pinned host x_T in, images out.
+Weak scaling: every rank samples its own images, global image indices are disjoint, no data-path collective.
 
 Prints ONE JSON line on rank 0 (see the contract in the task description / DESIGN.md).
 """
@@ -32,10 +32,18 @@ T_STEPS = 500
 FLOP_PER_EVAL_FOLDED = 735.31e6     # SURVEY.md Appendix A with the embedding fold (what the kernels execute)
 FLOP_PER_EVAL_REFERENCE = 886.31e6  # the reference's 129-channel formulation
 FLOP_PER_TRAIN_IMG = 2204.76e6      # fwd + dgrad + wgrad with the fold
-# dram__bytes_read.sum + dram__bytes_write.sum of ONE conv3x3 64->64 @32x32 launch from `ncu --set full`
-# keyed by images per launch: 512 -> profiles/conv_l2_r1_ncu.txt (single-CTA kernel, earlier in round 1),
-# 1300 -> profiles/conv_l2_r1b_ncu.txt (CTA-pair kernel, the default)
-NCU_TRAFFIC_CONV_L2 = {512: 98.6e6, 1300: 325.8e6}
+
+
+def ncu_traffic(kernel: str, images: int):
+    """dram__bytes_read.sum + dram__bytes_write.sum of ONE launch of `kernel` at `images` images per launch, read from
+    the committed summary of the `ncu --set full` captures (profiles/ncu_kernels.json, written by
+    profiles/summarize_ncu.py from the .ncu-rep files); None when no capture at that size exists."""
+    try:
+        d = json.load(open(os.path.join(ROOT, "profiles", "ncu_kernels.json")))
+        e = d.get(kernel, {}).get(str(images))
+        return None if e is None else float(e["dram_bytes_read"]) + float(e["dram_bytes_write"])
+    except Exception:
+        return None
 
 
 def load_peaks():
@@ -155,13 +163,26 @@ def run_reference(args):
     rank = int(os.environ.get("RANK", "0"))
     if rank != 0:
         return
+    import torch
+
+    # torchrun exports OMP_NUM_THREADS=1 to every rank: the CPU arm must ask for the host's cores itself
+    threads = os.cpu_count() or 1
+    torch.set_num_threads(threads)
     n_img, n_st = args.ref_images, args.ref_steps
+    # bound the whole `--steps K --warmup W` run to ~ref_budget seconds: calibrate on a small sample, then shrink the
+    # per-step sample (reverse steps first, then images) -- the metric is extrapolated per evaluation anyway
+    _, dt_cal, _ = cpu_reference_sampling(16, 4, threads)
+    per_eval = dt_cal / (16 * 4)
+    budget = args.ref_budget / max(1.0, args.steps + 0.25 * args.warmup)
+    while n_img * n_st * per_eval > budget and n_st > 4:
+        n_st = max(4, n_st // 2)
+    while n_img * n_st * per_eval > budget and n_img > 8:
+        n_img = max(8, n_img // 2)
     vals, tot = [], 0.0
     for _ in range(args.warmup):
-        cpu_reference_sampling(max(1, n_img // 4), max(2, n_st // 4))
-    threads = os.cpu_count()
+        cpu_reference_sampling(max(1, n_img // 4), max(2, n_st // 4), threads)
     for _ in range(args.steps):
-        v, dt, threads = cpu_reference_sampling(n_img, n_st)
+        v, dt, threads = cpu_reference_sampling(n_img, n_st, threads)
         vals.append(v)
         tot += dt
     value = float(np.mean(vals))
@@ -172,7 +193,7 @@ def run_reference(args):
         "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
         "config": {"workload": "generate_image: 499-evaluation reverse loop, 32x32, trained_model.bson weights",
                    "images_per_step_per_gpu": n_img, "T": T_STEPS,
-                   "note": "Flux-semantics CPU restatement (Julia unavailable in this image)"},
+                   "note": "Flux-semantics CPU restatement (Julia unavailable in this image); rank 0 only, all host threads"},
         "cpu_baseline": {"value": value, "unit": "img/s", "cores": threads, "kind": "port", "sample": sample},
         "e2e": {"value": value, "unit": "img/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
         "gpu_launches": 0,
@@ -198,7 +219,7 @@ def run_ours(args):
     h.set_option("sample_chunk", args.chunk)
     if args.streams > 0:
         h.set_option("sample_streams", args.streams)
-    for kv in filter(None, os.environ.get("DDPM_OPTS", "").split(",")):   # e.g. DDPM_OPTS=conv_v2=0,fuse_final=0
+    for kv in filter(None, os.environ.get("DDPM_OPTS", "").split(",")):   # e.g. DDPM_OPTS=tc_pair=0,fuse_final=0
         k, v = kv.split("=")
         h.set_option(k, int(v))
     t_start = args.t_start
@@ -222,6 +243,15 @@ def run_ours(args):
             line["train"]["scaling"] = "strong (global batch fixed at %d)" % (args.train_images * world)
             line["train"]["tflops"] = tl["roofline"]["whole_step_tflops"]
             line["train"]["frac_of_sustained_peak"] = tl["roofline"]["whole_step_frac_of_sustained"]
+            # strong-scaling efficiency against the committed 1-GPU figure of the same global batch (the driver
+            # recomputes it from its own per-N runs; this is the builder-side number for the record)
+            line["train"]["per_gpu_value"] = tl["value"] / world
+            try:
+                one = json.load(open(os.path.join(ROOT, "profiles", "r2", "train_1gpu.json")))
+                line["train"]["efficiency_vs_1gpu"] = tl["value"] / (world * one["value"])
+                line["train"]["one_gpu_value"] = one["value"]
+            except Exception:
+                line["train"]["efficiency_vs_1gpu"] = 1.0 if world == 1 else None
     if rank == 0:
         emit(line)
     if td is not None:
@@ -248,26 +278,34 @@ def run_workload(args, workload, h, td, rank, world, local, peaks, N, t_start, e
         clk = clocks.stop() if rank == 0 else None
         ms = max_over_ranks(td, ms, local)
         value = args.steps * N * world / (ms * 1e-3)
-        # ---- end to end through the public C-ABI call with pinned host buffers
+        # ---- end to end through the public C-ABI call with pinned host buffers: BASELINE config 4 literally,
+        #      ONE ddpm_sample(N = 65536) call per rank (x_T from pinned host memory, images back to pinned host memory)
         import torch
 
-        x_host = torch.empty((N, 1024), dtype=torch.float32, pin_memory=True)
-        o_host = torch.empty((N, 1024), dtype=torch.float32, pin_memory=True)
+        NE = args.e2e_images if args.e2e_images > 0 else N
+        x_host = torch.empty((NE, 1024), dtype=torch.float32, pin_memory=True)
+        o_host = torch.empty((NE, 1024), dtype=torch.float32, pin_memory=True)
         x_host.normal_(generator=torch.Generator().manual_seed(1 + rank))
         xin, oout = x_host.numpy(), o_host.numpy()
-        h.sample(N, x_T=xin, seed=args.seed, first_index=first_index(0), t_start=t_start, out=oout)
+        # warm-up: same balanced chunk size as the big call (ceil(NE / ceil(NE / chunk))), two chunks of it
+        kch = -(-NE // args.chunk)
+        bal = -(-NE // kch)
+        nw = min(NE, 2 * bal)
+        h.sample(nw, x_T=xin[:nw], seed=args.seed, first_index=0, t_start=t_start, out=oout[:nw])
         barrier(td, local)
         t0 = time.perf_counter()
         e2e_steps = max(1, min(args.steps, args.e2e_steps))
         for k in range(e2e_steps):
-            h.sample(N, x_T=xin, seed=args.seed, first_index=first_index(k), t_start=t_start, out=oout)
+            h.sample(NE, x_T=xin, seed=args.seed, first_index=(k * world + rank) * NE, t_start=t_start, out=oout)
         barrier(td, local)
         e2e_s = max_over_ranks(td, time.perf_counter() - t0, local)
-        e2e = {"value": e2e_steps * N * world / e2e_s, "unit": "img/s", "h2d_bytes_per_step": int(xin.nbytes),
-               "d2h_bytes_per_step": int(oout.nbytes), "steps": e2e_steps}
+        e2e = {"value": e2e_steps * NE * world / e2e_s, "unit": "img/s", "h2d_bytes_per_step": int(xin.nbytes),
+               "d2h_bytes_per_step": int(oout.nbytes), "steps": e2e_steps, "images_per_call_per_gpu": NE,
+               "note": "one ddpm_sample call of NE images per step per rank (NE = 65536: BASELINE config 4 as quoted)"}
         metric = "sampled img/s (500-step DDPM, 32x32)"
         workload_desc = (f"generate_image: {evals}-evaluation reverse loop (t={t_start}..2), 32x32, trained_model.bson weights, "
-                    f"device Philox noise; BASELINE config 4 (65,536 images) == {65536 / N:.1f} steps of {N}")
+                    f"device Philox noise; value: {N} device-resident images per step and GPU (BASELINE config 4 == {65536 / N:.1f} such steps); "
+                    f"e2e: config 4 as quoted, one ddpm_sample(N={args.e2e_images if args.e2e_images > 0 else N}) call with host buffers")
         flop_per_unit = FLOP_PER_EVAL_FOLDED * evals
     else:
         # ---- training throughput: data parallel, global batch = images * world
@@ -342,7 +380,7 @@ def run_workload(args, workload, h, td, rank, world, local, peaks, N, t_start, e
     else:
         peak_note = "kind::f16 tensor peak (cuBLAS bf16 burst)"
     roofline = {"bound": "tensor", "kernel": "conv3x3 64->64 @32x32 (layer 2)", "achieved": dom.get("tflops"),
-                "peak": peak_tf, "unit": "TFLOP/s", "frac": (dom.get("tflops") or 0.0) / peak_tf, "traffic": NCU_TRAFFIC_CONV_L2.get(chunk),
+                "peak": peak_tf, "unit": "TFLOP/s", "frac": (dom.get("tflops") or 0.0) / peak_tf, "traffic": ncu_traffic("conv_l2", chunk),
                 "peak_source": peaks["source"], "note": peak_note,
                 "whole_step_tflops": value * flop_per_unit / 1e12 / world,
                 "whole_step_frac_of_sustained": value * flop_per_unit / 1e12 / world / peaks["bf16_tflops_sustained"]}
@@ -353,7 +391,7 @@ def run_workload(args, workload, h, td, rank, world, local, peaks, N, t_start, e
     # ---- CPU baseline on the box's host cores, bounded sample
     cpu = None
     if world == 1 and not args.no_cpu and workload == "sample":
-        v, dt, threads = cpu_reference_sampling(args.ref_images, args.ref_steps)
+        v, dt, threads = cpu_reference_sampling(args.ref_images, args.ref_steps, os.cpu_count())
         cpu = {"value": v, "unit": "img/s", "cores": threads, "kind": "port",
                "sample": f"{args.ref_images} images x {args.ref_steps} of 499 reverse steps ({dt:.1f} s), extrapolated to 499; "
                          "Flux-semantics CPU restatement (oracle/ddpm_oracle.py, torch-CPU fp32)"}
@@ -407,6 +445,9 @@ def main():
     ap.add_argument("--seed", type=int, default=1234)
     ap.add_argument("--sync-bn", type=int, default=1)
     ap.add_argument("--e2e-steps", type=int, default=2)
+    ap.add_argument("--e2e-images", type=int, default=65536,
+                    help="images of the ONE ddpm_sample call the end-to-end leg times per step (BASELINE config 4; 0: --images)")
+    ap.add_argument("--ref-budget", type=float, default=200.0, help="seconds the --impl reference run may take in total")
     ap.add_argument("--ref-images", type=int, default=128)
     ap.add_argument("--ref-steps", type=int, default=100)
     ap.add_argument("--no-cpu", action="store_true")

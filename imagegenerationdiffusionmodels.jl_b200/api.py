@@ -94,7 +94,7 @@ class SimpleUNet:
     def save(self, path: str, epoch: Optional[int] = None):
         """``@save path model opt [epoch]`` (src/train_brain.jl:295-300): same BSON document
         structure as the reference's files."""
-        bson_io.save_checkpoint(path, self.template, self.arrays, epoch=epoch)
+        bson_io.save_checkpoint(path, self.template, self.arrays, epoch=epoch, eta=self.eta)
 
 
 # ----------------------------------------------------------------------------- engine cache
@@ -201,11 +201,16 @@ class TrainResult:
 def train(data=DEFAULT_DATA, lr: float = 1e-4, epochs: int = 100, patience: int = 10, min_delta: float = 0.001,
           batch_size: int = 64, T: int = tables.T_DEFAULT, model: Optional[SimpleUNet] = None,
           rng: Optional[np.random.Generator] = None, schedule=None, save_dir: Optional[str] = ".",
-          precision: int = capi.PREC_FP16, device: int = 0, log=print) -> TrainResult:
+          precision: int = capi.PREC_FP16, device: int = 0, log=print, resume_from: Optional[str] = None,
+          save_optimizer_state: bool = False) -> TrainResult:
     """``train(data, lr, epochs, patience, min_delta)`` (README.md:23) == ``main`` of
     src/train_brain.jl:246-304: load, rescale ``imgs .*= 2; imgs .-= 1``, Adam(lr), epochs of
     shuffled mini-batches (last batch 52 of 500), early stopping, BSON checkpoint every 5 epochs
     and ``trained_model.bson`` at the end.
+
+    Beyond the reference (which saves the Adam RULE only and cannot resume):
+    ``save_optimizer_state`` also writes the moments next to every checkpoint (``<name>.adam.bson``) and
+    ``resume_from=<checkpoint .bson>`` continues from that file's weights and, if present, its moment file.
 
     ``schedule(epoch, n_images)`` may return host-supplied draws
     ``(perm, [ts per batch], [eps per batch])`` for parity runs; otherwise ``rng`` draws them
@@ -214,10 +219,16 @@ def train(data=DEFAULT_DATA, lr: float = 1e-4, epochs: int = 100, patience: int 
     imgs = (imgs.reshape(-1, 1, 32, 32) * np.float32(2) - np.float32(1)).astype(np.float32)
     n = imgs.shape[0]
     rng = rng or np.random.default_rng()
+    if resume_from is not None:
+        model = SimpleUNet.load(resume_from)
     model = model or SimpleUNet.init()
     h = engine(T, precision, device)
     h.set_weights(model.arrays)
     h.set_adam(float(np.float32(lr)), 0.9, 0.999, 1e-8)
+    if resume_from is not None and os.path.exists(_adam_path(resume_from)):
+        m, v, bt, steps, _ = bson_io.load_adam_state(_adam_path(resume_from))
+        h.set_adam_state(m, v, bt, steps)
+    model.eta = float(np.float32(lr))        # `opt = Adam(lr)` is what @save writes next to the model
     res = TrainResult(model)
     best, no_improve = float("inf"), 0
     for epoch in range(1, epochs + 1):
@@ -251,12 +262,22 @@ def train(data=DEFAULT_DATA, lr: float = 1e-4, epochs: int = 100, patience: int 
             break
         if save_dir is not None and epoch % 5 == 0:
             model.arrays = h.get_weights()
-            model.save(os.path.join(save_dir, f"ddpm_epoch_{epoch}.bson"), epoch=epoch)
+            _save(model, h, os.path.join(save_dir, f"ddpm_epoch_{epoch}.bson"), epoch, save_optimizer_state)
     model.arrays = h.get_weights()
-    model.eta = lr
     if save_dir is not None:
-        model.save(os.path.join(save_dir, "trained_model.bson"))
+        _save(model, h, os.path.join(save_dir, "trained_model.bson"), None, save_optimizer_state)
     return res
+
+
+def _adam_path(checkpoint: str) -> str:
+    return (checkpoint[:-5] if checkpoint.endswith(".bson") else checkpoint) + ".adam.bson"
+
+
+def _save(model: SimpleUNet, h, path: str, epoch, with_optimizer_state: bool):
+    model.save(path, epoch=epoch)
+    if with_optimizer_state:
+        m, v, bt, steps = h.get_adam_state()
+        bson_io.save_adam_state(_adam_path(path), m, v, bt, steps, model.eta)
 
 
 def demo(out_dir: str = ".", seed: int = 0) -> dict:

@@ -254,10 +254,14 @@ def load_checkpoint(path: str):
     return arrays, meta
 
 
-def save_checkpoint(path: str, template_path: str, arrays, epoch=None):
+def save_checkpoint(path: str, template_path: str, arrays, epoch=None, eta=None):
     """Write a checkpoint with the exact document structure of ``template_path`` but the
     Float32 payloads replaced by ``arrays`` (ABI order).  Because structure, type tags and
-    backrefs are copied verbatim from a file BSON.jl wrote, ``@load`` accepts the result."""
+    backrefs are copied verbatim from a file BSON.jl wrote, ``@load`` accepts the result.
+
+    ``@save path model opt [epoch]`` (src/train_brain.jl:295-300) writes the LIVE rule and the current epoch:
+    ``eta`` replaces the Float32 learning rate inside ``opt`` (``Optimisers.Adam`` field 1), ``epoch`` sets the
+    ``epoch`` key and ``epoch=None`` removes one inherited from the template (``trained_model.bson`` has none)."""
     with open(template_path, "rb") as fh:
         doc = parse_bson(fh.read())
     res = _Resolver(doc)
@@ -292,5 +296,67 @@ def save_checkpoint(path: str, template_path: str, arrays, epoch=None):
     patch(doc["model"])
     if epoch is not None:
         doc["epoch"] = int(epoch)
+    elif "epoch" in doc:
+        del doc["epoch"]
+    if eta is not None:
+        opt = res.deref(doc.get("opt"))
+        if not (isinstance(opt, dict) and opt.get("tag") == "struct"):
+            raise ValueError("template checkpoint has no Optimisers.Adam rule to patch")
+        node = res.deref(opt["data"][0])
+        payload = np.float32(eta).tobytes()
+        if isinstance(node, dict):            # Float32 scalar lowered as struct{Core.Float32}(bytes)
+            raw = node["data"]
+            if isinstance(raw, (list, BsonArray)):
+                raw[0] = payload
+            else:
+                node["data"] = payload
+        else:
+            opt["data"][0] = float(np.float32(eta))
     with open(path, "wb") as fh:
         fh.write(emit_bson(doc))
+
+
+# ----------------------------------------------------------------------------- optimiser state (resume)
+def _dt(name):
+    return OrderedDict([("tag", "datatype"), ("name", BsonArray(name)), ("params", BsonArray())])
+
+
+def _f32_vector(a: np.ndarray):
+    a = np.ascontiguousarray(a, dtype=np.float32).reshape(-1)
+    return OrderedDict([("tag", "array"), ("type", _dt(["Core", "Float32"])), ("size", BsonArray([int(a.size)])),
+                        ("data", a.tobytes())])
+
+
+def save_adam_state(path: str, m, v, beta_t, steps: int, eta: float):
+    """Adam moments for a true resume, as a BSON.jl-shaped document (``BSON.load(path)`` yields a Dict with
+    ``:m``/``:v`` = 64 ``Vector{Float32}`` in the weight order, ``:beta_t``, ``:steps``, ``:eta``).  The reference
+    cannot resume: it saves the rule only (src/train_brain.jl:295-300)."""
+    if len(m) != 64 or len(v) != 64:
+        raise ValueError("expected 64 moment arrays")
+
+    def vec_of_vec(arrs):
+        any_t = OrderedDict([("tag", "datatype"), ("name", BsonArray(["Core", "Any"])), ("params", BsonArray())])
+        return OrderedDict([("tag", "array"), ("type", any_t), ("size", BsonArray([len(arrs)])),
+                            ("data", BsonArray([_f32_vector(a) for a in arrs]))])
+
+    doc = OrderedDict([
+        ("m", vec_of_vec(m)), ("v", vec_of_vec(v)),
+        ("beta_t", OrderedDict([("tag", "tuple"), ("data", BsonArray([float(beta_t[0]), float(beta_t[1])]))])),
+        ("steps", int(steps)), ("eta", float(eta)),
+    ])
+    with open(path, "wb") as fh:
+        fh.write(emit_bson(doc))
+
+
+def load_adam_state(path: str):
+    """Inverse of :func:`save_adam_state`: (m, v, (bt1, bt2), steps, eta)."""
+    with open(path, "rb") as fh:
+        doc = parse_bson(fh.read())
+    res = _Resolver(doc)
+    out = {}
+    for key in ("m", "v"):
+        arrs: List[JuliaArray] = []
+        _collect_arrays(doc[key], res, arrs)
+        out[key] = [a.flat for a in arrs]
+    bt = tuple(np.float32(x) for x in doc["beta_t"]["data"])
+    return out["m"], out["v"], (float(bt[0]), float(bt[1])), int(doc["steps"]), float(doc["eta"])

@@ -35,6 +35,8 @@ SIGNATURES = {
     "ddpm_set_weights": (C.c_int, [C.c_void_p, _pp, _i64p, C.c_int]),
     "ddpm_get_weights": (C.c_int, [C.c_void_p, _pp, _i64p, C.c_int]),
     "ddpm_set_adam": (C.c_int, [C.c_void_p, C.c_float, C.c_float, C.c_float, C.c_float]),
+    "ddpm_get_adam_state": (C.c_int, [C.c_void_p, _pp, _pp, _i64p, C.c_int, _f32p, _i64p]),
+    "ddpm_set_adam_state": (C.c_int, [C.c_void_p, _pp, _pp, _i64p, C.c_int, _f32p, C.c_int64]),
     "ddpm_q_sample": (C.c_int, [C.c_void_p, _f32p, _i32p, _f32p, C.c_int, _f32p]),
     "ddpm_predict_eps": (C.c_int, [C.c_void_p, _f32p, _i32p, C.c_int, C.c_int, _f32p]),
     "ddpm_train_step": (C.c_int, [C.c_void_p, _f32p, _i32p, _f32p, C.c_int, _f32p]),
@@ -44,6 +46,7 @@ SIGNATURES = {
     "ddpm_sample": (C.c_int, [C.c_void_p, _f32p, _f32p, C.c_uint64, C.c_int64, C.c_int64, C.c_int, _f32p]),
     "ddpm_sample_device": (C.c_int, [C.c_void_p, C.c_uint64, C.c_int64, C.c_int64, C.c_int]),
     "ddpm_sample_fetch": (C.c_int, [C.c_void_p, C.c_int64, _f32p]),
+    "ddpm_sample_fetch_u8": (C.c_int, [C.c_void_p, C.c_int64, C.POINTER(C.c_uint8)]),
     "ddpm_apply_noise_f64": (C.c_int, [_f64p, _f64p, C.c_int64, _f64p, C.c_int, _f64p]),
     "ddpm_comm_unique_id": (C.c_int, [C.c_void_p]),
     "ddpm_comm_init": (C.c_int, [C.c_void_p, C.c_void_p, C.c_int, C.c_int, C.c_int]),
@@ -188,6 +191,23 @@ class Handle:
     def set_adam(self, eta=1e-4, beta1=0.9, beta2=0.999, eps=1e-8):
         _check(self.lib.ddpm_set_adam(self._h, eta, beta1, beta2, eps))
 
+    def get_adam_state(self):
+        """(m arrays, v arrays, (beta1^t, beta2^t), applied steps) -- the optimiser state a resume needs."""
+        m = [np.zeros(n, np.float32) for n in self._lens]
+        v = [np.zeros(n, np.float32) for n in self._lens]
+        km, pm, lens = self._array_args(m)
+        kv, pv, _ = self._array_args(v)
+        bt = np.zeros(2, np.float32)
+        steps = C.c_int64()
+        _check(self.lib.ddpm_get_adam_state(self._h, pm, pv, lens, NUM_ARRAYS, _ptr(bt), C.byref(steps)))
+        return km, kv, (float(bt[0]), float(bt[1])), int(steps.value)
+
+    def set_adam_state(self, m, v, beta_t, steps: int):
+        km, pm, lens = self._array_args(m)
+        kv, pv, _ = self._array_args(v)
+        bt = np.asarray(beta_t, dtype=np.float32).reshape(2)
+        _check(self.lib.ddpm_set_adam_state(self._h, pm, pv, lens, NUM_ARRAYS, _ptr(bt), int(steps)))
+
     # ---- hot-path calls
     def _imgs(self, x, B=None) -> np.ndarray:
         x = _f32(x)
@@ -271,6 +291,11 @@ class Handle:
     def sample_fetch(self, N: int) -> np.ndarray:
         out = np.empty((N, self.H * self.W), np.float32)
         _check(self.lib.ddpm_sample_fetch(self._h, N, _ptr(out)))
+        return out.reshape(N, 1, self.H, self.W)
+
+    def sample_fetch_u8(self, N: int) -> np.ndarray:
+        out = np.empty((N, self.H * self.W), np.uint8)
+        _check(self.lib.ddpm_sample_fetch_u8(self._h, N, out.ctypes.data_as(C.POINTER(C.c_uint8))))
         return out.reshape(N, 1, self.H, self.W)
 
     # ---- multi-GPU

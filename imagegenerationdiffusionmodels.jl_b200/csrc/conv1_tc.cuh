@@ -264,11 +264,7 @@ bool conv1_shared_t(cudaStream_t st, const float* x, const float* Wimg, const fl
     CUtensorMap o = make_map_2d<TOut>(out - (size_t)g.guard * 64, (uint64_t)g.alloc_positions(), 64, TC_BM);
     constexpr size_t smem = 1024 + 64 * 128 + (size_t)C1_STAGES * TC_BM * 128 + 2 * TC_BM * 64 * 2 + 256 + 9 * 64 * 4 + 256;
     auto kern = conv1_tc_kernel<TOut>;
-    static bool attr_set = false;
-    if (!attr_set) {
-        DDPM_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-        attr_set = true;
-    }
+    ensure_smem_attr(kern, smem);
     int ctas = state().num_sms;
     if (ctas > p.num_tiles) ctas = p.num_tiles;
     cudaLaunchConfig_t cfg{};

@@ -471,7 +471,7 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constant__
         // instruction queue is shallow, so a single issuer drains it during every mbarrier wait (~150 cycles
         // each); with two independent streams one warp's waits overlap the other's MMAs.  Tiles are
         // independent (own TMEM accumulator, own slab), tcgen05.commit tracks the issuing thread's MMAs only.
-        // Dual issue is only legal when each pipeline stage is always consumed by the same warp (see conv3_tc.cuh).
+        // Dual issue is only legal when each pipeline stage is always consumed by the same warp.
         const int parity = (warp == 1) ? 0 : 1;
         constexpr int NISS = DUAL ? 2 : 1;
         bool w_pending = true;                   // first tile of this warp: wait for each weight tile right before its MMAs
@@ -716,10 +716,29 @@ struct State {
     // 8 = 64=>128 @16x16, 16 = the two data-gradient-only shapes (128=>64 @16x16, 64=>128 @32x32)
     int pair_mask = 31;
     bool pdl = true;            // launch the tcgen05 conv kernels as programmatic dependents of their stream predecessor
+    // per-DEVICE launch bookkeeping (function attributes and occupancy are properties of a (kernel, device) pair)
+    std::map<const void*, int> smem_attr;     // kernel -> dynamic shared memory size already granted on this device
+    std::map<const void*, int> max_pairs;     // kernel -> resident CTA pairs on this device
 };
+// One State per CUDA device: the ABI allows several handles on several devices in one process
+// (ddpm_create(..., device)); everything here is keyed by the CURRENT device (callers cudaSetDevice first).
+constexpr int MAX_DEVICES = 64;
 inline State& state() {
-    static State s;
-    return s;
+    static State s[MAX_DEVICES];
+    int dev = 0;
+    if (cudaGetDevice(&dev) != cudaSuccess) { cudaGetLastError(); dev = 0; }
+    return s[(dev >= 0 && dev < MAX_DEVICES) ? dev : 0];
+}
+
+// opt a kernel in to `smem` bytes of dynamic shared memory, once per (kernel, device)
+template <typename K>
+inline void ensure_smem_attr(K kern, size_t smem) {
+    State& st = state();
+    const void* key = reinterpret_cast<const void*>(kern);
+    auto it = st.smem_attr.find(key);
+    if (it != st.smem_attr.end() && it->second >= (int)smem) return;
+    DDPM_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    st.smem_attr[key] = (int)smem;
 }
 
 inline void init() {
@@ -738,7 +757,7 @@ inline void init() {
         for (int i = 0; i < 8; ++i) s.trap_host[i] = 0;
         int* dptr = nullptr;
         if (cudaHostGetDevicePointer(&dptr, s.trap_host, 0) == cudaSuccess)
-            cudaMemcpyToSymbol(g_trap_info, &dptr, sizeof dptr);
+            cudaMemcpyToSymbol(g_trap_info, &dptr, sizeof dptr);     // the symbol has one instance per device
     } else {
         cudaGetLastError();
         s.trap_host = nullptr;
@@ -785,11 +804,7 @@ void launch(cudaStream_t st, const CUtensorMap& a0, const CUtensorMap& a1, const
     DDPM_CHECK(p.g.Wp == WP && p.g.Hs == WP - 1 && p.g.npos + 2 * TC_BM < (1ll << 31),
                "conv_tc: geometry does not match the kernel's compile-time row width");
     auto kern = conv_tc_kernel<TAPS, CHUNKS, NOUT, WP, STAGES, EPI, TMAST, CG, TIn, TOut>;
-    static bool attr_set = false;
-    if (!attr_set) {
-        DDPM_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-        attr_set = true;
-    }
+    ensure_smem_attr(kern, smem);
     int ctas_x = state().num_sms / n_blocks_y;
     if (ctas_x > p.num_m_tiles) ctas_x = p.num_m_tiles;
     if (ctas_x < 1) ctas_x = 1;
@@ -812,14 +827,16 @@ void launch(cudaStream_t st, const CUtensorMap& a0, const CUtensorMap& a1, const
         ++na;
         // the kernel is persistent: never launch more pairs than the device can keep resident at once (a part with
         // an unpaired SM would otherwise run the surplus pair as a second wave and double the kernel time)
-        static int max_pairs = -1;
-        if (max_pairs < 0) {
+        const void* kkey = reinterpret_cast<const void*>(kern);
+        auto mp = state().max_pairs.find(kkey);
+        if (mp == state().max_pairs.end()) {
             cfg.attrs = attr;
             cfg.numAttrs = na;
             int nc = 0;
-            if (cudaOccupancyMaxActiveClusters(&nc, kern, &cfg) == cudaSuccess && nc > 0) max_pairs = nc;
-            else { cudaGetLastError(); max_pairs = state().num_sms / 2; }
+            if (cudaOccupancyMaxActiveClusters(&nc, kern, &cfg) != cudaSuccess || nc <= 0) { cudaGetLastError(); nc = state().num_sms / 2; }
+            mp = state().max_pairs.emplace(kkey, nc).first;
         }
+        const int max_pairs = mp->second;
         if (ctas_x * n_blocks_y > 2 * max_pairs) {
             ctas_x = (2 * max_pairs / n_blocks_y) & ~1;
             if (ctas_x < 2) ctas_x = 2;
@@ -1238,14 +1255,35 @@ __global__ void wgrad_up2_reduce_kernel(const float* __restrict__ partial, int n
     dW[(1 - px) + 2 * (1 - py) + 4 * co + 256 * ci] = alpha * s;
 }
 
+// Per-ENGINE scratch of the weight-gradient kernels (partial blocks of every CTA, sub-block tables): two handles on
+// one device (or on two devices) must not share it.
 struct WgScratch {
     float* partial = nullptr;
     size_t cap = 0;
-    int* sub = nullptr;     // device [8]: co chunk [0..3], ci chunk [4..7]
+    int* sub = nullptr;     // device [4][8]: co chunk [0..3], ci chunk [4..7] per (nco, nci) configuration
+    void release() {
+        if (partial) cudaFree(partial);
+        if (sub) cudaFree(sub);
+        partial = nullptr; sub = nullptr; cap = 0;
+    }
 };
-inline WgScratch& wg_scratch() {
-    static WgScratch s;
-    return s;
+
+// allocate the scratch once, outside any stream capture (wgrad3x3 / wgrad_up2 never allocate afterwards)
+inline void wg_reserve(WgScratch& sc) {
+    const size_t need = (size_t)4 * state().num_sms * 36864 * sizeof(float);
+    if (sc.cap < need) {
+        if (sc.partial) cudaFree(sc.partial);
+        sc.partial = nullptr; sc.cap = 0;
+        DDPM_CUDA(cudaMalloc(&sc.partial, need));
+        sc.cap = need;
+    }
+    if (!sc.sub) {
+        // all (co chunk, ci chunk) enumerations for nco x nci in {1,2}x{1,2}, indexed by (nco-1)*2 + (nci-1)
+        static const int h[4][8] = {{0, 0, 0, 0, 0, 0, 0, 0}, {0, 0, 0, 0, 0, 1, 0, 0}, {0, 1, 0, 0, 0, 0, 0, 0}, {0, 0, 1, 1, 0, 1, 0, 1}};
+        DDPM_CUDA(cudaMalloc(&sc.sub, sizeof h));
+        DDPM_CUDA(cudaMemcpy(sc.sub, h, sizeof h, cudaMemcpyHostToDevice));   // blocking copy from static storage
+        DDPM_CUDA(cudaDeviceSynchronize());
+    }
 }
 
 template <int WP, typename TDy, typename TX>
@@ -1255,11 +1293,7 @@ void launch_wgrad(cudaStream_t st, const CUtensorMap& mdy, const CUtensorMap& mx
     constexpr int STAGES = (227 * 1024 - 2048) / STAGE > 6 ? 6 : (227 * 1024 - 2048) / STAGE;
     constexpr size_t smem = 1024 + (size_t)STAGES * STAGE + 512;
     auto kern = wgrad_tc_kernel<WP, STAGES, TDy, TX>;
-    static bool attr_set = false;
-    if (!attr_set) {
-        DDPM_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-        attr_set = true;
-    }
+    ensure_smem_attr(kern, smem);
     kern<<<dim3(ctas_x, n_sub), WG_THREADS, smem, st>>>(mdy, mx, p);
     DDPM_LAUNCH_CHECK();
 }
@@ -1267,8 +1301,8 @@ void launch_wgrad(cudaStream_t st, const CUtensorMap& mdy, const CUtensorMap& mx
 // dW of Conv((3,3)) for dy [pos][Cout] and x [pos][Cx] (one source of the input; ci_off = its offset in the
 // layer's Cin_total input channels).  Writes (not accumulates) the Flux-layout block of the gradient arena.
 template <typename TG, typename TA>
-bool wgrad3x3(cudaStream_t st, const TG* dy, int Cout, const TA* x, int Cx, const Geo& g, float* dW, int Cin_total, int ci_off,
-              float alpha) {
+bool wgrad3x3(cudaStream_t st, WgScratch& sc, const TG* dy, int Cout, const TA* x, int Cx, const Geo& g, float* dW, int Cin_total,
+              int ci_off, float alpha) {
     if (!available()) return false;
     // kind::f16 requires A and B of the SAME 16-bit format (mixed bf16 x f16 raises an illegal-instruction
     // fault on B200, measured in round 1), hence gradients share the activation format.
@@ -1281,20 +1315,8 @@ bool wgrad3x3(cudaStream_t st, const TG* dy, int Cout, const TA* x, int Cx, cons
     int ctas_x = state().num_sms / n_sub;
     if (ctas_x > num_kblocks) ctas_x = num_kblocks;
     if (ctas_x < 1) ctas_x = 1;
-    WgScratch& sc = wg_scratch();
-    const size_t need = (size_t)n_sub * ctas_x * 36864 * sizeof(float);
-    if (sc.cap < need) {
-        DDPM_CUDA(cudaStreamSynchronize(st));
-        if (sc.partial) cudaFree(sc.partial);
-        DDPM_CUDA(cudaMalloc(&sc.partial, (size_t)4 * state().num_sms * 36864 * sizeof(float)));
-        sc.cap = (size_t)4 * state().num_sms * 36864 * sizeof(float);
-    }
-    if (!sc.sub) {
-        // all (co chunk, ci chunk) enumerations for nco x nci in {1,2}x{1,2}, indexed by (nco-1)*2 + (nci-1)
-        int h[4][8] = {{0, 0, 0, 0, 0, 0, 0, 0}, {0, 0, 0, 0, 0, 1, 0, 0}, {0, 1, 0, 0, 0, 0, 0, 0}, {0, 0, 1, 1, 0, 1, 0, 1}};
-        DDPM_CUDA(cudaMalloc(&sc.sub, sizeof h));
-        DDPM_CUDA(cudaMemcpy(sc.sub, h, sizeof h, cudaMemcpyHostToDevice));
-    }
+    wg_reserve(sc);                     // no-op after the first call (the engine reserves it when it builds a training set)
+    DDPM_CHECK((size_t)n_sub * ctas_x * 36864 * sizeof(float) <= sc.cap, "wgrad scratch too small");
     const int cfg = (nco - 1) * 2 + (nci - 1);
     static const int hsub[4][8] = {{0, 0, 0, 0, 0, 0, 0, 0}, {0, 0, 0, 0, 0, 1, 0, 0}, {0, 1, 0, 0, 0, 0, 0, 0}, {0, 0, 1, 1, 0, 1, 0, 1}};
     WgParams p{};
@@ -1316,7 +1338,7 @@ bool wgrad3x3(cudaStream_t st, const TG* dy, int Cout, const TA* x, int Cx, cons
 }
 
 template <typename T>
-bool wgrad_up2(cudaStream_t st, const T* du4, const T* a6, const Geo& g, float* dW, float alpha) {
+bool wgrad_up2(cudaStream_t st, WgScratch& sc, const T* du4, const T* a6, const Geo& g, float* dW, float alpha) {
     if (!available()) return false;
     if constexpr (sizeof(T) != 2) {
         return false;
@@ -1324,22 +1346,11 @@ bool wgrad_up2(cudaStream_t st, const T* du4, const T* a6, const Geo& g, float* 
     const int num_kblocks = cdiv(g.npos, WU_KB);
     int ctas = state().num_sms;
     if (ctas > num_kblocks) ctas = num_kblocks;
-    WgScratch& sc = wg_scratch();
-    const size_t need = (size_t)4 * state().num_sms * 36864 * sizeof(float);   // shared with wgrad3x3 (>= ctas*256*128)
-    if (sc.cap < need) {
-        DDPM_CUDA(cudaStreamSynchronize(st));
-        if (sc.partial) cudaFree(sc.partial);
-        DDPM_CUDA(cudaMalloc(&sc.partial, need));
-        sc.cap = need;
-    }
+    wg_reserve(sc);                     // shared with wgrad3x3 (>= ctas*256*128 floats)
     constexpr int STAGES = 4;
     constexpr size_t smem = 1024 + (size_t)STAGES * 6 * WU_KB * 128 + 512;
     auto kern = wgrad_up2_tc_kernel<STAGES, T>;
-    static bool attr_set = false;
-    if (!attr_set) {
-        DDPM_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-        attr_set = true;
-    }
+    ensure_smem_attr(kern, smem);
     const uint64_t rows = (uint64_t)g.alloc_positions();
     CUtensorMap m4 = make_map_2d<T>(du4 - (size_t)g.guard * 256, rows, 256, WU_KB);
     CUtensorMap m6 = make_map_2d<T>(a6 - (size_t)g.guard * 128, rows, 128, WU_KB);

@@ -15,7 +15,6 @@
 #include "kernels.cuh"
 #include "igemm_simt.cuh"
 #include "conv_tc.cuh"
-#include "conv3_tc.cuh"
 #include "conv1_tc.cuh"
 
 namespace ddpm {
@@ -138,12 +137,26 @@ struct ActSet {
     DevBuf rng;         // [seed, first_index] of the chunk this set is currently sampling (read by its graphs)
     // captured reverse loops, keyed by (t_start, zmode); they bake in this set's pointers
     std::map<std::pair<int, int>, GraphEntry> graphs;
+    // training only: device staging of one step's inputs (host batches or dataset indices), q_sample output, loss
+    // gradient and the first layer's backward scratch -- owned by the set so that a captured step never sees a
+    // re-allocated pointer
+    DevBuf x0, eps, ts, idx, xt, deps, Tw, Ccls, S;
+    // captured training iterations, keyed by gather*2 + update (the first call of a key runs eagerly and warms every
+    // lazily initialised resource, the second one is captured, later ones replay)
+    std::map<int, GraphEntry> train_graphs;
+    std::map<int, int> train_calls;
+    long long last_use = 0;
+    static void destroy(GraphEntry& g) {
+        if (g.exec) cudaGraphExecDestroy(g.exec);
+        if (g.graph) cudaGraphDestroy(g.graph);
+        g = GraphEntry();
+    }
     void drop_graphs() {
-        for (auto& kv : graphs) {
-            if (kv.second.exec) cudaGraphExecDestroy(kv.second.exec);
-            if (kv.second.graph) cudaGraphDestroy(kv.second.graph);
-        }
+        for (auto& kv : graphs) destroy(kv.second);
         graphs.clear();
+        for (auto& kv : train_graphs) destroy(kv.second);
+        train_graphs.clear();
+        train_calls.clear();
     }
 };
 
@@ -170,20 +183,26 @@ struct Engine {
 
     // parameters
     float *P = nullptr, *G = nullptr, *M1 = nullptr, *M2 = nullptr;
-    float eta = 1e-4f, b1 = 0.9f, b2 = 0.999f, aeps = 1e-8f, bt1 = 0.9f, bt2 = 0.999f;
+    float eta = 1e-4f, b1 = 0.9f, b2 = 0.999f, aeps = 1e-8f;
+    // Optimiser state that changes every step lives on the device (TrainState, kernels.cuh): the bias-correction
+    // powers beta^t, the non-finite-gradient flag of the current step and the skipped / applied step counters.  The
+    // host never needs them to enqueue a step, so a whole training iteration can be replayed from a CUDA graph.
+    TrainState* d_tstate = nullptr;
+    tc::WgScratch wg;             // partial-sum scratch of the tcgen05 weight-gradient kernels (per engine)
+    long long opt_loss_scale_log2 = 0;   // extra power-of-two factor on the static loss scale (tests trip the overflow guard with it)
     // Static loss scale of the 16-bit gradient tensors: d(loss)/d(eps_hat) is multiplied by
     // S = B_global*H*W/8 (so it is (eps_hat-eps)/4, O(1)) and every FP32 gradient written to the arena is
     // multiplied by 1/S.  Powers of two when B is: exact.  Keeps FP16 gradients ~3 decades below overflow
     // and the bulk above the subnormal range (measured ranges in DESIGN.md).  1 in FP32 mode.
-    float grad_scale(int B) const { return prec == 0 ? 1.f : (float)B * (float)world * (float)HW / 8.f; }
+    float grad_scale(int B) const {
+        const float base = prec == 0 ? 1.f : (float)B * (float)world * (float)HW / 8.f;
+        return std::ldexp(base, (int)opt_loss_scale_log2);
+    }
 
     // packed weights
     void* Wf[NUM_CONV + 1] = {};   // [cout][9][cin]  (TA)  -- L1 unused
     void* Wd[NUM_CONV + 1] = {};   // [cin][9][cout]  (TG)  -- L1 unused
     void* Wfi[NUM_CONV + 1] = {};  // Wf with the inference BatchNorm scale folded in (TA)
-    void* W3f[NUM_CONV + 1] = {};  // row-packed variants for conv3_tc.cuh: forward (TA), inference-folded (TA), dgrad (TG)
-    void* W3fi[NUM_CONV + 1] = {};
-    void* W3d[NUM_CONV + 1] = {};
     void *Wt = nullptr, *Wtd = nullptr;  // convT fwd (TA) [256][128], dgrad (TG) [128][256]
     float *Wimg = nullptr, *Wemb = nullptr;  // first conv, FP32
     float *Ptab = nullptr, *Ecls = nullptr;  // [T][9][64] embedding contributions
@@ -197,10 +216,14 @@ struct Engine {
     double* sums_g = nullptr;     // all-reduced copies (SyncBN)
     double* misc_sums = nullptr;  // [0]=loss, [8..72]=dwf, [72]=dbf, [128..192]=dbT
 
-    // activation sets: one for training, a small cache of inference sets keyed by batch size
-    ActSet train_set;
+    // activation sets: a two-entry cache of training sets (an epoch of the reference alternates 64- and 52-image
+    // batches, train_brain.jl:201-202) and a small cache of inference sets, both keyed by batch size
+    std::map<int, ActSet*> train_sets;
+    ActSet* last_train_set = nullptr;
+    long long use_clock = 0;
     std::map<int, ActSet*> infer_sets;
-    DevBuf d_x0, d_eps, d_xt, d_deps, d_ts, d_idx, d_Tw, d_Ccls, d_S, d_z, d_dataset, d_sample_out;
+    DevBuf d_x0, d_eps, d_xt, d_ts, d_dataset, d_sample_out, d_u8;     // q_sample API staging, dataset, sampler output
+    unsigned long long* d_trng = nullptr;     // [seed, first_index, step] of the current device-drawn training step
     long long dataset_n = 0;
     unsigned long long* d_rng = nullptr;  // [seed, first_index]
 
@@ -210,14 +233,11 @@ struct Engine {
 
     // options / counters
     long long opt_sample_streams = 1;
-    // 1 = row-packed tcgen05 conv (conv3_tc.cuh): MMAs at the tensor floor (96 cyc per M128 N192 K16) but its
-    // shuffle/exchange epilogue costs ~2300 cycles per tile, so the first formulation (conv_tc.cuh, ~2500 cycles per
-    // tile, smem-operand bound) is still faster end to end (B200, round 1: 1612 vs 1791 img/s) and stays the default.
-    long long opt_conv_v2 = 0;
     long long opt_conv1_tc = 1;    // sampler: first conv on tensor cores (hi/lo split operands) when the batch shares one timestep
     // images per captured reverse-loop graph.  1300 images fill the persistent conv kernels' tile rounds exactly
     // (32x32 layers: 77.0 rounds of 74 CTA-pair tiles, 16x16 layers: 21.0) -- 512 left the 16x16 layers at 92 %
     long long opt_sample_chunk = 1300, opt_use_graph = 1, opt_conv_impl = 0 /*0 auto, 1 simt, 2 tc*/, opt_fuse_final = 1;
+    long long opt_train_graph = 1;          // replay the training iteration from a CUDA graph (per set and step kind)
     long long cnt_launches = 0;
 
     Engine(int T_, int D_, int H_, int W_, int prec_, int dev_);
@@ -236,6 +256,7 @@ struct Engine {
         return prec != 0 && tc::available();
     }
 
+    void reset_train_state();
     void set_default_tables();
     void upload_tables();
     void alloc_tensor(ActSet& s, Tensor& t, int N, int hw, int C, size_t esz);
@@ -264,7 +285,10 @@ struct Engine {
     template <typename TA, typename TG> void backward_t(ActSet& s, const float* xt_dev, const int* ts_dev, const float* deps_dev, float alpha);
     void allreduce_sums(double* local, double* global, int n);
 
-    void train_core(int B, bool device_inputs, bool update, float* loss_out_host);
+    void train_enqueue(ActSet& s, bool gather, bool device_draws, bool update);
+    void train_core(ActSet& s, bool gather, bool device_draws, bool update, float* loss_out_host);
+    void drop_train_graphs() { for (auto& kv : train_sets) kv.second->drop_graphs(); }
+    void drop_all_graphs() { drop_train_graphs(); for (auto& kv : infer_sets) kv.second->drop_graphs(); }
     void sample_chunk(ActSet& s, bool host_z, unsigned long long seed, long long first_index, int t_start);
     template <typename TA, typename TG> void sample_steps_t(ActSet& s, float* x_dev, const float* z_dev, int N, int t_start);
 };
@@ -310,9 +334,11 @@ inline Engine::Engine(int T_, int D_, int H_, int W_, int prec_, int dev_)
         offs[k + 1] = offs[k] + ((lens[k] + 3) / 4) * 4;
     }
     n_params = offs[NUM_ARRAYS];
+    // every initialisation below is enqueued on `stream` (a non-blocking stream is NOT ordered after legacy-stream
+    // cudaMemset / cudaMemcpy); the constructor synchronises once at the end
     auto zalloc = [&](float** p, size_t n) {
         DDPM_CUDA(cudaMalloc(p, n * sizeof(float)));
-        DDPM_CUDA(cudaMemset(*p, 0, n * sizeof(float)));
+        DDPM_CUDA(cudaMemsetAsync(*p, 0, n * sizeof(float), stream));
     };
     zalloc(&P, n_params); zalloc(&G, n_params); zalloc(&M1, n_params); zalloc(&M2, n_params);
     zalloc(&d_sqrt_ac, T); zalloc(&d_sqrt_1mac, T); zalloc(&d_pe, (size_t)T * D);
@@ -328,9 +354,6 @@ inline Engine::Engine(int T_, int D_, int H_, int W_, int prec_, int dev_)
             DDPM_CUDA(cudaMalloc(&Wf[l], n * esz_a()));
             DDPM_CUDA(cudaMalloc(&Wd[l], n * esz_g()));
             DDPM_CUDA(cudaMalloc(&Wfi[l], n * esz_a()));
-            DDPM_CUDA(cudaMalloc(&W3f[l], n * esz_a()));
-            DDPM_CUDA(cudaMalloc(&W3fi[l], n * esz_a()));
-            DDPM_CUDA(cudaMalloc(&W3d[l], n * esz_g()));
         }
     }
     DDPM_CUDA(cudaMalloc(&Wt, (size_t)4 * 128 * 64 * esz_a()));
@@ -339,24 +362,36 @@ inline Engine::Engine(int T_, int D_, int H_, int W_, int prec_, int dev_)
     DDPM_CUDA(cudaMalloc(&sums_g, sizeof(double) * 384 * (NUM_CONV + 1)));
     DDPM_CUDA(cudaMalloc(&misc_sums, sizeof(double) * 256));
     DDPM_CUDA(cudaMalloc(&d_rng, 2 * sizeof(unsigned long long)));
+    DDPM_CUDA(cudaMalloc(&d_trng, 4 * sizeof(unsigned long long)));
+    DDPM_CUDA(cudaMalloc(&d_tstate, sizeof(TrainState)));
+    reset_train_state();
     tc::init();
     set_default_tables();
     // Flux default initialisation of the BatchNorm state so an un-loaded handle is well defined:
     // gamma = 1, var = 1; conv weights stay zero until ddpm_set_weights.
+    const std::vector<float> ones(128, 1.f);
     for (int l = 1; l <= NUM_CONV; ++l) {
         int C = kConv[l].cout;
-        std::vector<float> ones(C, 1.f);
-        DDPM_CUDA(cudaMemcpy(arr(kConv[l].bn + 1), ones.data(), C * 4, cudaMemcpyHostToDevice));
-        DDPM_CUDA(cudaMemcpy(arr(kConv[l].bn + 3), ones.data(), C * 4, cudaMemcpyHostToDevice));
+        DDPM_CUDA(cudaMemcpyAsync(arr(kConv[l].bn + 1), ones.data(), C * 4, cudaMemcpyHostToDevice, stream));
+        DDPM_CUDA(cudaMemcpyAsync(arr(kConv[l].bn + 3), ones.data(), C * 4, cudaMemcpyHostToDevice, stream));
     }
     pack_weights();
+    DDPM_CUDA(cudaStreamSynchronize(stream));
+}
+
+inline void Engine::reset_train_state() {
+    TrainState ts{};
+    ts.bt1 = b1; ts.bt2 = b2;
+    DDPM_CUDA(cudaMemcpyAsync(d_tstate, &ts, sizeof ts, cudaMemcpyHostToDevice, stream));
+    DDPM_CUDA(cudaStreamSynchronize(stream));
 }
 
 inline Engine::~Engine() {
     cudaSetDevice(dev);
     cudaDeviceSynchronize();
     if (comm) nccl().CommDestroy(comm);
-    free_set(train_set);
+    for (auto& kv : train_sets) { free_set(*kv.second); delete kv.second; }
+    train_sets.clear();
     for (auto& kv : infer_sets) { free_set(*kv.second); delete kv.second; }
     infer_sets.clear();
     float* fl[] = {P, G, M1, M2, d_sqrt_ac, d_sqrt_1mac, d_pe, Wimg, Wemb, Ptab, Ecls};
@@ -364,10 +399,12 @@ inline Engine::~Engine() {
     for (int l = 1; l <= NUM_CONV; ++l) {
         float* v[] = {inf_scale[l], inf_shift[l], tr_mean[l], tr_istd[l], tr_scale[l], tr_shift[l], bw_mg[l], bw_mgx[l]};
         for (float* p : v) cudaFree(p);
-        cudaFree(Wf[l]); cudaFree(Wd[l]); cudaFree(Wfi[l]); cudaFree(W3f[l]); cudaFree(W3fi[l]); cudaFree(W3d[l]);
+        cudaFree(Wf[l]); cudaFree(Wd[l]); cudaFree(Wfi[l]);
     }
-    cudaFree(Wt); cudaFree(Wtd); cudaFree(sums); cudaFree(sums_g); cudaFree(misc_sums); cudaFree(d_rng);
-    DevBuf* bufs[] = {&d_x0, &d_eps, &d_xt, &d_deps, &d_ts, &d_idx, &d_Tw, &d_Ccls, &d_S, &d_z, &d_dataset, &d_sample_out};
+    cudaFree(Wt); cudaFree(Wtd); cudaFree(sums); cudaFree(sums_g); cudaFree(misc_sums); cudaFree(d_rng); cudaFree(d_tstate);
+    wg.release();
+    cudaFree(d_trng);
+    DevBuf* bufs[] = {&d_x0, &d_eps, &d_xt, &d_ts, &d_dataset, &d_sample_out, &d_u8};
     for (DevBuf* b : bufs) b->release();
     for (auto& ev : ev_bucket) cudaEventDestroy(ev);
     cudaEventDestroy(ev_comm_done);
@@ -421,9 +458,10 @@ inline void Engine::upload_tables() {
         volatile float om = 1.f - a_t;
         sb[t - 1] = sqrtf(om);
     }
-    DDPM_CUDA(cudaMemcpy(d_sqrt_ac, sa.data(), T * 4, cudaMemcpyHostToDevice));
-    DDPM_CUDA(cudaMemcpy(d_sqrt_1mac, sb.data(), T * 4, cudaMemcpyHostToDevice));
-    DDPM_CUDA(cudaMemcpy(d_pe, h_pe.data(), (size_t)T * D * 4, cudaMemcpyHostToDevice));
+    DDPM_CUDA(cudaMemcpyAsync(d_sqrt_ac, sa.data(), T * 4, cudaMemcpyHostToDevice, stream));
+    DDPM_CUDA(cudaMemcpyAsync(d_sqrt_1mac, sb.data(), T * 4, cudaMemcpyHostToDevice, stream));
+    DDPM_CUDA(cudaMemcpyAsync(d_pe, h_pe.data(), (size_t)T * D * 4, cudaMemcpyHostToDevice, stream));
+    DDPM_CUDA(cudaStreamSynchronize(stream));      // sa / sb are locals
     ecls_valid = false;
     for (auto& kv : infer_sets) kv.second->drop_graphs();  // scalars are baked into captured graphs
 }
@@ -441,7 +479,8 @@ inline void Engine::free_set(ActSet& s) {
     s.drop_graphs();
     for (void* p : s.owned) cudaFree(p);
     s.owned.clear();
-    s.x.release(); s.eps_hat.release(); s.z.release(); s.zstep.release(); s.rng.release();
+    DevBuf* bufs[] = {&s.x, &s.eps_hat, &s.z, &s.zstep, &s.rng, &s.x0, &s.eps, &s.ts, &s.idx, &s.xt, &s.deps, &s.Tw, &s.Ccls, &s.S};
+    for (DevBuf* b : bufs) b->release();
     s = ActSet();
 }
 
@@ -475,15 +514,37 @@ inline void Engine::build_set(ActSet& s, int N, bool training) {
     s.x.ensure((size_t)N * HW * 4);
     s.eps_hat.ensure((size_t)N * HW * 4);
     if (!training) { s.zstep.ensure((size_t)N * HW * 4); s.rng.ensure(2 * sizeof(unsigned long long)); }
+    if (training) {
+        const size_t img = (size_t)N * HW * 4;
+        s.x0.ensure(img); s.eps.ensure(img); s.xt.ensure(img); s.deps.ensure(img);
+        s.ts.ensure((size_t)N * 4); s.idx.ensure((size_t)N * 4);
+        s.Tw.ensure((size_t)N * 576 * 4); s.Ccls.ensure((size_t)N * 576 * 4); s.S.ensure((size_t)N * 576 * 4);
+        if (use_tc()) tc::wg_reserve(wg);          // no allocation may happen inside a captured step
+    }
 }
 
 inline ActSet& Engine::get_set(int N, bool training, int slot) {
     if (training) {
-        if (train_set.N != N) {
+        auto it = train_sets.find(N);
+        if (it == train_sets.end()) {
             DDPM_CUDA(cudaStreamSynchronize(stream));
-            build_set(train_set, N, true);
+            if (train_sets.size() >= 2) {             // evict the least recently used set
+                auto victim = train_sets.begin();
+                for (auto jt = train_sets.begin(); jt != train_sets.end(); ++jt)
+                    if (jt->second->last_use < victim->second->last_use) victim = jt;
+                if (last_train_set == victim->second) last_train_set = nullptr;
+                free_set(*victim->second);
+                delete victim->second;
+                train_sets.erase(victim);
+            }
+            ActSet* ns = new ActSet();
+            build_set(*ns, N, true);
+            DDPM_CUDA(cudaStreamSynchronize(stream));
+            it = train_sets.emplace(N, ns).first;
         }
-        return train_set;
+        it->second->last_use = ++use_clock;
+        last_train_set = it->second;
+        return *it->second;
     }
     const int key = N * 8 + slot;   // one set per (batch size, concurrent-stream slot)
     auto it = infer_sets.find(key);
@@ -515,15 +576,6 @@ void Engine::pack_weights_t() {
     }
     pack_conv3_batch_kernel<TA, TG><<<dim3(cdiv(nmax, 256), NUM_CONV - 1, 2), 256, 0, stream>>>(J);
     cnt_launches += 1;
-    if (opt_conv_v2) {      // the row-packed layouts are only read by the second conv formulation (conv3_tc.cuh)
-        for (int l = 2; l <= NUM_CONV; ++l) {
-            const ConvSpec& c = kConv[l];
-            long long n = 9LL * c.cin * c.cout;
-            pack_conv3_rows_kernel<TA><<<cdiv(n, 256), 256, 0, stream>>>(arr(c.w), c.cin, c.cout, 0, nullptr, (TA*)W3f[l]);
-            pack_conv3_rows_kernel<TG><<<cdiv(n, 256), 256, 0, stream>>>(arr(c.w), c.cin, c.cout, 1, nullptr, (TG*)W3d[l]);
-        }
-        cnt_launches += 2 * (NUM_CONV - 1);
-    }
     long long nt = 4LL * 128 * 64;
     pack_up2_kernel<TA><<<cdiv(nt, 256), 256, 0, stream>>>(arr(kUpW), 128, 64, 0, (TA*)Wt);
     pack_up2_kernel<TG><<<cdiv(nt, 256), 256, 0, stream>>>(arr(kUpW), 128, 64, 1, (TG*)Wtd);
@@ -563,14 +615,6 @@ void Engine::pack_infer_weights_t() {
     }
     pack_conv3_batch_kernel<TA, TG><<<dim3(cdiv(nmax, 256), NUM_CONV - 1, 1), 256, 0, stream>>>(J);
     cnt_launches += 1;
-    if (opt_conv_v2) {
-        for (int l = 2; l <= NUM_CONV; ++l) {
-            const ConvSpec& c = kConv[l];
-            long long n = 9LL * c.cin * c.cout;
-            pack_conv3_rows_kernel<TA><<<cdiv(n, 256), 256, 0, stream>>>(arr(c.w), c.cin, c.cout, 0, inf_scale[l], (TA*)W3fi[l]);
-        }
-        cnt_launches += NUM_CONV - 1;
-    }
     DDPM_LAUNCH_CHECK();
 }
 
@@ -595,18 +639,12 @@ template <typename TA, typename TG>
 void Engine::conv3(const Tensor& s0, const Tensor* s1, int l, Tensor& out, bool infer_weights, const float* shift,
                    int relu, double* stats) {
     const void* weights = infer_weights ? Wfi[l] : Wf[l];
-    const void* weights3 = infer_weights ? W3fi[l] : W3f[l];
     const ConvSpec& c = kConv[l];
     const Geo& g = out.g;
     int C0 = s0.C, C1 = s1 ? s1->C : 0;
     DDPM_CHECK(C0 + C1 == c.cin && out.C == c.cout, "conv3: channel mismatch");
     if (use_tc()) {
-        bool ok = false;
-        if (opt_conv_v2)
-            ok = tc::conv3x3_v2<TA, TA>(stream, s0.pos0<TA>(), C0, s1 ? s1->pos0<TA>() : nullptr, C1, (const TA*)weights3, c.cout,
-                                        out.pos0<TA>(), g, shift, relu);
-        if (!ok)
-            ok = tc::conv3x3<TA, TA>(stream, s0.pos0<TA>(), C0, s1 ? s1->pos0<TA>() : nullptr, C1, (const TA*)weights, c.cout,
+        bool ok = tc::conv3x3<TA, TA>(stream, s0.pos0<TA>(), C0, s1 ? s1->pos0<TA>() : nullptr, C1, (const TA*)weights, c.cout,
                                      out.pos0<TA>(), g, shift, relu);
         if (ok) {
             cnt_launches += 1;
@@ -635,12 +673,7 @@ void Engine::dgrad3(const Tensor& dy, int l, Tensor& out, int out_c_total) {
     const Geo& g = out.g;
     DDPM_CHECK(dy.C == c.cout && out.C == out_c_total && out_c_total == c.cin, "dgrad3: channel mismatch");
     if (use_tc()) {
-        bool ok = false;
-        if (opt_conv_v2)
-            ok = tc::conv3x3_v2<TG, TG>(stream, dy.pos0<TG>(), c.cout, nullptr, 0, (const TG*)W3d[l], c.cin, out.pos0<TG>(), g,
-                                        nullptr, 0);
-        if (!ok)
-            ok = tc::conv3x3<TG, TG>(stream, dy.pos0<TG>(), c.cout, nullptr, 0, (const TG*)Wd[l], c.cin, out.pos0<TG>(), g,
+        bool ok = tc::conv3x3<TG, TG>(stream, dy.pos0<TG>(), c.cout, nullptr, 0, (const TG*)Wd[l], c.cin, out.pos0<TG>(), g,
                                      nullptr, 0);
         if (ok) {
             cnt_launches += 1;
@@ -804,7 +837,7 @@ void Engine::backward_t(ActSet& s, const float* xt_dev, const int* ts_dev, const
         const Geo& g = dy.g;
         bool done = false;
         if (use_tc())
-            done = tc::wgrad3x3<TG, TA>(stream, dy.pos0<TG>(), c.cout, x.pos0<TA>(), x.C, g, garr(c.w), c.cin, ci_off, alpha);
+            done = tc::wgrad3x3<TG, TA>(stream, wg, dy.pos0<TG>(), c.cout, x.pos0<TA>(), x.C, g, garr(c.w), c.cin, ci_off, alpha);
         if (!done) {
             MapConv3 mapB{g.Wp, -(long long)g.guard, g.npos + g.guard};
             launch_wgrad_simt<TG, TA>(stream, dy.cview<TG>(), x.cview<TA>(), g.npos, 9, c.cout, x.C, MapId{g.npos}, mapB,
@@ -864,7 +897,7 @@ void Engine::backward_t(ActSet& s, const float* xt_dev, const int* ts_dev, const
         bool wdone = false;
         if (done) {
             if constexpr (std::is_same<TG, TA>::value)
-                wdone = tc::wgrad_up2<TG>(stream, s.gdu4.pos0<TG>(), s.a[6].pos0<TA>(), gi, garr(kUpW), alpha);
+                wdone = tc::wgrad_up2<TG>(stream, wg, s.gdu4.pos0<TG>(), s.a[6].pos0<TA>(), gi, garr(kUpW), alpha);
         }
         if (!wdone)
             launch_wgrad_simt<TG, TA>(stream, s.g32a.cview<TG>(), s.a[6].cview<TA>(), gi.npos, 4, 64, 128, MapUp2{gi, go},
@@ -906,11 +939,10 @@ void Engine::backward_t(ActSet& s, const float* xt_dev, const int* ts_dev, const
     dgrad3<TA, TG>(s.g32b, 2, s.g32a, 64);
     bn_bwd(1, s.g32a.cview<TG>(), s.g32b);
     {   // first conv: image channel + folded embedding channels
-        d_Tw.ensure((size_t)N * 576 * 4); d_Ccls.ensure((size_t)N * 576 * 4); d_S.ensure((size_t)N * 576 * 4);
-        l1_bwd_kernel<TG><<<N, 256, 0, stream>>>(s.g32b.cview<TG>(), s.g32b.g, xt_dev, d_Tw.as<float>(), d_Ccls.as<float>());
-        l1_tap_sums_kernel<<<cdiv((long long)N * 576, 256), 256, 0, stream>>>(d_Ccls.as<float>(), d_S.as<float>(), N);
-        l1_wimg_grad_kernel<<<576, 256, 0, stream>>>(d_Tw.as<float>(), N, alpha, 129, garr(0));
-        View<const float> Sv{d_S.as<float>(), 576}, pev{d_pe, D};
+        l1_bwd_kernel<TG><<<N, 256, 0, stream>>>(s.g32b.cview<TG>(), s.g32b.g, xt_dev, s.Tw.as<float>(), s.Ccls.as<float>());
+        l1_tap_sums_kernel<<<cdiv((long long)N * 576, 256), 256, 0, stream>>>(s.Ccls.as<float>(), s.S.as<float>(), N);
+        l1_wimg_grad_kernel<<<576, 256, 0, stream>>>(s.Tw.as<float>(), N, alpha, 129, garr(0));
+        View<const float> Sv{s.S.as<float>(), 576}, pev{d_pe, D};
         launch_wgrad_simt<float, float>(stream, Sv, pev, (long long)N, 1, 576, D, MapId{(long long)N}, MapTs{ts_dev, (long long)N},
                                         IdxEmb{129, 64}, alpha, garr(0));
         DDPM_LAUNCH_CHECK();
@@ -927,36 +959,86 @@ void Engine::backward_t(ActSet& s, const float* xt_dev, const int* ts_dev, const
 }
 
 // ------------------------------------------------------------------------------------ one training iteration
-// inputs already on the device: d_x0 (or dataset gather via d_idx), d_ts, d_eps
-inline void Engine::train_core(int B, bool gather, bool update, float* loss_out_host) {
-    ActSet& s = get_set(B, true);
-    d_xt.ensure((size_t)B * HW * 4);
-    d_deps.ensure((size_t)B * HW * 4);
-    const float* x0 = gather ? d_dataset.as<float>() : d_x0.as<float>();
-    const int* idx = gather ? d_idx.as<int>() : nullptr;
+// Enqueues q_sample .. Adam .. weight re-packing on `stream`.  Inputs are resident in the set: s.x0 (or dataset rows
+// gathered through s.idx), s.ts, s.eps -- host-supplied, or drawn here from Philox keyed by d_trng = [seed, first
+// global image index, step].  Nothing in here depends on a host-side per-step scalar, so the sequence can be captured.
+inline void Engine::train_enqueue(ActSet& s, bool gather, bool device_draws, bool update) {
+    const int B = s.N;
+    const float* x0 = gather ? d_dataset.as<float>() : s.x0.as<float>();
+    const int* idx = gather ? s.idx.as<int>() : nullptr;
     long long n4 = (long long)B * HW / 4;
-    qsample_kernel<<<cdiv(n4, 256), 256, 0, stream>>>(x0, idx, d_eps.as<float>(), d_ts.as<int>(), d_sqrt_ac, d_sqrt_1mac,
-                                                      d_xt.as<float>(), B, HW);
+    if (device_draws) {
+        randint_ts_dev_kernel<<<cdiv(B, 256), 256, 0, stream>>>(s.ts.as<int>(), B, T, d_trng);
+        randn_train_dev_kernel<<<cdiv(n4, 256), 256, 0, stream>>>(s.eps.as<float>(), B, HW, d_trng);
+        cnt_launches += 2;
+    }
+    qsample_kernel<<<cdiv(n4, 256), 256, 0, stream>>>(x0, idx, s.eps.as<float>(), s.ts.as<int>(), d_sqrt_ac, d_sqrt_1mac,
+                                                      s.xt.as<float>(), B, HW);
     DDPM_LAUNCH_CHECK();
     cnt_launches += 1;
-    forward(s, d_xt.as<float>(), d_ts.as<int>(), 0, Mode::Train, update);
+    forward(s, s.xt.as<float>(), s.ts.as<int>(), 0, Mode::Train, update);
     DDPM_DISPATCH(prec, (final_conv_t<TA, TG>(s, s.eps_hat.as<float>())));
     DDPM_CUDA(cudaMemsetAsync(misc_sums, 0, sizeof(double), stream));
     // loss = mean over the GLOBAL batch; every rank contributes its local sum / (B*world*HW)
     float inv_count = 1.f / ((float)B * (float)world * (float)HW);
     const float gs = grad_scale(B);
-    mse_kernel<<<cdiv(n4, 256), 256, 0, stream>>>(s.eps_hat.as<float>(), d_eps.as<float>(), n4, inv_count * gs, misc_sums,
-                                                  d_deps.as<float>());
+    mse_kernel<<<cdiv(n4, 256), 256, 0, stream>>>(s.eps_hat.as<float>(), s.eps.as<float>(), n4, inv_count * gs, misc_sums,
+                                                  s.deps.as<float>());
     DDPM_LAUNCH_CHECK();
     cnt_launches += 1;
-    DDPM_DISPATCH(prec, (backward_t<TA, TG>(s, d_xt.as<float>(), d_ts.as<int>(), d_deps.as<float>(), 1.f / gs)));
+    DDPM_DISPATCH(prec, (backward_t<TA, TG>(s, s.xt.as<float>(), s.ts.as<int>(), s.deps.as<float>(), 1.f / gs)));
     if (update) {
-        adam_kernel<<<cdiv(n_params, 256), 256, 0, stream>>>(P, G, M1, M2, n_params, eta, b1, b2, aeps, bt1, bt2);
+        // overflow guard of the 16-bit gradient tensors: a non-finite value anywhere in the (all-reduced) gradient
+        // skips the update (weights and moments untouched, beta^t not advanced) and bumps a counter
+        grad_check_kernel<<<cdiv(n_params, 1024), 256, 0, stream>>>(G, n_params, d_tstate);
+        adam_kernel<<<cdiv(n_params, 256), 256, 0, stream>>>(P, G, M1, M2, n_params, eta, b1, b2, aeps, d_tstate);
+        adam_advance_kernel<<<1, 32, 0, stream>>>(d_tstate, b1, b2);
         DDPM_LAUNCH_CHECK();
-        cnt_launches += 1;
-        bt1 *= b1; bt2 *= b2;
+        cnt_launches += 3;
         pack_weights();
     }
+}
+
+inline void Engine::train_core(ActSet& s, bool gather, bool device_draws, bool update, float* loss_out_host) {
+    const int B = s.N;
+    const int key = (gather ? 4 : 0) + (device_draws ? 2 : 0) + (update ? 1 : 0);
+    bool replayed = false;
+    if (opt_train_graph) {
+        auto it = s.train_graphs.find(key);
+        if (it == s.train_graphs.end() && s.train_calls[key] >= 1) {
+            // second call of this kind on this set: capture it (the first, eager call initialised every lazily
+            // created resource -- function attributes, occupancy queries, derived tables)
+            ecls_valid = false;                       // the captured step must contain the embedding-fold refresh
+            DDPM_CUDA(cudaStreamSynchronize(stream));
+            GraphEntry ge;
+            const long long before = cnt_launches;
+            DDPM_CUDA(cudaStreamBeginCapture(stream, cudaStreamCaptureModeThreadLocal));
+            try {
+                train_enqueue(s, gather, device_draws, update);
+            } catch (...) {
+                cudaGraph_t g = nullptr;
+                cudaStreamEndCapture(stream, &g);
+                if (g) cudaGraphDestroy(g);
+                throw;
+            }
+            DDPM_CUDA(cudaStreamEndCapture(stream, &ge.graph));
+            DDPM_CUDA(cudaGraphInstantiate(&ge.exec, ge.graph, 0));
+            ge.launches = cnt_launches - before;
+            cnt_launches = before;
+            it = s.train_graphs.emplace(key, ge).first;
+        }
+        if (it != s.train_graphs.end()) {
+            DDPM_CUDA(cudaGraphLaunch(it->second.exec, stream));
+            cnt_launches += it->second.launches;
+            replayed = true;
+        }
+    }
+    if (!replayed) {
+        if (update) ecls_valid = false;
+        train_enqueue(s, gather, device_draws, update);
+    }
+    s.train_calls[key] += 1;
+    if (update) { ecls_valid = false; infer_affine_valid = false; }    // the weights moved (also when replayed)
     if (loss_out_host) {
         double ls = 0;
         if (comm) {
@@ -965,6 +1047,7 @@ inline void Engine::train_core(int B, bool gather, bool update, float* loss_out_
         }
         DDPM_CUDA(cudaMemcpyAsync(&ls, misc_sums, sizeof(double), cudaMemcpyDeviceToHost, stream));
         DDPM_CUDA(cudaStreamSynchronize(stream));
+        const float inv_count = 1.f / ((float)B * (float)world * (float)HW);
         *loss_out_host = (float)(ls * (double)inv_count);   // mse_kernel accumulates the UNscaled squared error
     }
 }
@@ -986,19 +1069,7 @@ void Engine::sample_steps_t(ActSet& s, float* x_dev, const float* z_dev, int N, 
         const float* sc = &h_samp[(size_t)(t - 1) * 4];
         if (use_tc() && opt_fuse_final) {
             forward_t<TA, TG>(s, x_dev, nullptr, t, Mode::Infer, false, true);
-            bool fused = false;
-            if (opt_conv_v2) {
-                if constexpr (sizeof(TA) == 2) {
-                    tc::C3Params fp{};
-                    fp.x = x_dev; fp.z = zstep; fp.wf = arr(kFinalW); fp.bf = arr(kFinalB);
-                    fp.sig = sc[0]; fp.sqa = sc[1]; fp.sqp = sc[2]; fp.sqv = sc[3];
-                    fp.final_clamp = t == 2 ? 1 : 0;
-                    fused = tc::conv3x3_v2<TA, TA>(stream, s.a[9].pos0<TA>(), 64, nullptr, 0, (const TA*)W3fi[10], 64, nullptr,
-                                                   s.a[9].g, inf_shift[10], 1, &fp);
-                }
-            }
-            if (!fused)
-                fused = tc::conv3x3_final<TA>(stream, s.a[9].pos0<TA>(), (const TA*)Wfi[10], s.a[9].g, inf_shift[10], x_dev, zstep,
+            bool fused = tc::conv3x3_final<TA>(stream, s.a[9].pos0<TA>(), (const TA*)Wfi[10], s.a[9].g, inf_shift[10], x_dev, zstep,
                                               arr(kFinalW), arr(kFinalB), sc, t == 2 ? 1 : 0);
             if (fused) {
                 cnt_launches += 1;

@@ -116,6 +116,27 @@ __global__ void randint_ts_kernel(int* __restrict__ ts, int B, int T, unsigned l
     ts[n] = 1 + (int)__umulhi(r.x, (uint32_t)T);
 }
 
+// training-step draws with (seed, first global image index, step) read from device memory (rng3), so that one
+// captured training iteration serves every step: ts as randint_ts_kernel, eps as randn_kernel with the eps stream's
+// seed (seed ^ 0x9E3779B97F4A7C15)
+__global__ void randint_ts_dev_kernel(int* __restrict__ ts, int B, int T, const unsigned long long* __restrict__ rng3) {
+    int n = blockIdx.x * blockDim.x + threadIdx.x;
+    if (n >= B) return;
+    const unsigned long long seed = rng3[0], img = rng3[1] + (unsigned long long)n;
+    uint4 r = Philox::gen(make_uint4(0xFFFFFFFFu, (uint32_t)img, (uint32_t)(img >> 32), (uint32_t)rng3[2]),
+                          make_uint2((uint32_t)seed, (uint32_t)(seed >> 32)));
+    ts[n] = 1 + (int)__umulhi(r.x, (uint32_t)T);
+}
+__global__ void randn_train_dev_kernel(float* __restrict__ x, long long n_img, int hw, const unsigned long long* __restrict__ rng3) {
+    long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    int qpi = hw / 4;
+    if (i >= n_img * qpi) return;
+    long long n = i / qpi;
+    int q = (int)(i - n * qpi);
+    float4 z = Philox::normal4(rng3[0] ^ 0x9E3779B97F4A7C15ull, rng3[1] + (unsigned long long)n, (uint32_t)rng3[2], (uint32_t)q);
+    *reinterpret_cast<float4*>(x + n * hw + 4 * q) = z;
+}
+
 // ------------------------------------------------------------------------------------ K1: q_sample
 // x_t = a_n*x0 + b_n*eps with a = sqrt(acum[t]), b = sqrt(1-acum[t]) from host-built Float32 tables.
 // Separately rounded multiplies and add (no FMA contraction) => bit-exact with the reference's
@@ -918,13 +939,41 @@ unshuffle2_kernel(View<const TG> du, View<TG> du4, Geo gf, Geo gc, int C) {
 }
 
 // ------------------------------------------------------------------------------------ Adam (Optimisers.jl 0.4.6)
+// Per-step optimiser state kept on the device so that a training iteration needs no host-side scalar:
+//   bt1, bt2  = beta1^t, beta2^t of the NEXT update (Optimisers.jl keeps them in the rule state)
+//   nonfinite = 1 if the gradient of the current step holds an inf/NaN (set by grad_check_kernel)
+//   skipped / applied = number of updates skipped by the overflow guard / applied so far
+struct TrainState {
+    float bt1, bt2;
+    int nonfinite;
+    int skipped;
+    long long applied;
+};
+
+// flags any non-finite element of the flat gradient arena (the 16-bit gradient tensors use a static loss scale;
+// an overflow anywhere upstream reaches the FP32 weight gradients as inf or NaN)
+__global__ void __launch_bounds__(256)
+grad_check_kernel(const float* __restrict__ g, long long n, TrainState* __restrict__ st) {
+    const long long i0 = ((long long)blockIdx.x * 256 + threadIdx.x) * 4;
+    bool bad = false;
+    if (i0 + 3 < n) {
+        const float4 v = *reinterpret_cast<const float4*>(g + i0);
+        bad = !(isfinite(v.x) && isfinite(v.y) && isfinite(v.z) && isfinite(v.w));
+    } else {
+        for (long long i = i0; i < n; ++i) bad |= !isfinite(g[i]);
+    }
+    if (__any_sync(0xffffffffu, bad) && (threadIdx.x & 31) == 0) atomicExch(&st->nonfinite, 1);
+}
+
 // m = b1*m + (1-b1)*g ; v = b2*v + (1-b2)*g^2 ; p -= m/(1-bt1) / (sqrt(v/(1-bt2)) + eps) * eta
 // over the whole flat parameter arena (running statistics have g = m = v = 0 => unchanged).
 __global__ void __launch_bounds__(256)
 adam_kernel(float* __restrict__ p, const float* __restrict__ g, float* __restrict__ m, float* __restrict__ v,
-            long long n, float eta, float b1, float b2, float eps, float bt1, float bt2) {
+            long long n, float eta, float b1, float b2, float eps, const TrainState* __restrict__ st) {
     long long i = (long long)blockIdx.x * 256 + threadIdx.x;
     if (i >= n) return;
+    if (st->nonfinite) return;            // overflow guard: skip the whole update
+    const float bt1 = st->bt1, bt2 = st->bt2;
     float gi = g[i];
     float mi = __fadd_rn(__fmul_rn(b1, m[i]), __fmul_rn(1.f - b1, gi));
     float vi = __fadd_rn(__fmul_rn(b2, v[i]), __fmul_rn(1.f - b2, __fmul_rn(gi, gi)));
@@ -932,6 +981,38 @@ adam_kernel(float* __restrict__ p, const float* __restrict__ g, float* __restric
     float num = __fdiv_rn(mi, 1.f - bt1);
     float den = __fadd_rn(__fsqrt_rn(__fdiv_rn(vi, 1.f - bt2)), eps);
     p[i] = __fsub_rn(p[i], __fmul_rn(__fdiv_rn(num, den), eta));
+}
+
+// after adam_kernel: beta^t <- beta^t * beta (Optimisers.jl), counters, and re-arm the overflow flag
+__global__ void adam_advance_kernel(TrainState* __restrict__ st, float b1, float b2) {
+    if (threadIdx.x != 0 || blockIdx.x != 0) return;
+    if (st->nonfinite) {
+        st->skipped += 1;
+        st->nonfinite = 0;
+    } else {
+        st->bt1 = __fmul_rn(st->bt1, b1);
+        st->bt2 = __fmul_rn(st->bt2, b2);
+        st->applied += 1;
+    }
+}
+
+// (x+1)/2 clamped to [0,1] and quantised to 8 bits, round-half-even in Float64 like the host PNG writer
+// (`(img .+ 1) ./ 2` then Gray -> N0f8, /root/reference/src/generate_images.jl:256-265)
+__global__ void __launch_bounds__(256)
+quantize_u8_kernel(const float* __restrict__ x, long long n4, uint32_t* __restrict__ out) {
+    const long long i = (long long)blockIdx.x * 256 + threadIdx.x;
+    if (i >= n4) return;
+    const float4 v = *reinterpret_cast<const float4*>(x + 4 * i);
+    const float f[4] = {v.x, v.y, v.z, v.w};
+    uint32_t w = 0;
+#pragma unroll
+    for (int k = 0; k < 4; ++k) {
+        float a = __fmul_rn(__fadd_rn(f[k], 1.f), 0.5f);
+        a = fminf(fmaxf(a, 0.f), 1.f);
+        const uint32_t q = (uint32_t)__double2int_rn((double)a * 255.0);
+        w |= q << (8 * k);
+    }
+    out[i] = w;
 }
 
 // ------------------------------------------------------------------------------------ weight packing
@@ -985,32 +1066,6 @@ __global__ void pack_conv3_batch_kernel(const PackJobs J) {
         reinterpret_cast<TG*>(J.out_d[l])[i] = from_f<TG>(w[(1 + dx) + 3 * (1 + dy) + 9LL * ci + 9LL * Cin * co]);
     }
 }
-// Row-packed layout of conv3_tc.cuh: rows = (out-channel block of 64) x (dx, channel) = 192 per block, cols = (dy, k).
-//   forward : out channel = Flux co, k = Flux ci :  w[1-dx, 1-dy, ci, co] * row_scale[co]
-//   dgrad   : out channel = Flux ci, k = Flux co :  w[1+dx, 1+dy, ci, co]
-template <typename TW>
-__global__ void pack_conv3_rows_kernel(const float* __restrict__ w, int CinFlux, int CoutFlux, int dgrad,
-                                       const float* __restrict__ row_scale, TW* __restrict__ out) {
-    const int K = dgrad ? CoutFlux : CinFlux;        // contraction channels of this conv
-    const int OC = dgrad ? CinFlux : CoutFlux;       // output channels of this conv
-    long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
-    const long long total = 9LL * K * OC;
-    if (i >= total) return;
-    const int col = (int)(i % (3 * K));
-    const int row = (int)(i / (3 * K));
-    const int nblk = row / 192, rr = row % 192, dxi = rr / 64, oc = nblk * 64 + (rr % 64);
-    const int dyi = col / K, kc = col % K;
-    const int dx = dxi - 1, dy = dyi - 1;
-    float v;
-    if (!dgrad) {
-        v = w[(1 - dx) + 3 * (1 - dy) + 9LL * kc + 9LL * CinFlux * oc];
-        if (row_scale) v *= row_scale[oc];
-    } else {
-        v = w[(1 + dx) + 3 * (1 + dy) + 9LL * oc + 9LL * CinFlux * kc];
-    }
-    out[i] = from_f<TW>(v);
-}
-
 // ConvTranspose weight w[a,b,co,ci]:  Wt[q*Cout+co][ci] (fwd, K = ci)  /  Wtd[ci][q*Cout+co] (dgrad, K = q,co)
 template <typename TW>
 __global__ void pack_up2_kernel(const float* __restrict__ w, int Cin, int Cout, int dgrad, TW* __restrict__ out) {

@@ -111,19 +111,28 @@ int ddpm_set_weights(ddpm_handle* h, const float* const* arrays, const int64_t* 
     check_lens(e, lens, n);
     std::vector<float> host((size_t)e.n_params, 0.f);
     for (int k = 0; k < n; ++k) std::memcpy(host.data() + e.offs[k], arrays[k], (size_t)lens[k] * 4);
-    DDPM_CUDA(cudaStreamSynchronize(e.stream));
-    DDPM_CUDA(cudaMemcpy(e.P, host.data(), (size_t)e.n_params * 4, cudaMemcpyHostToDevice));
+    // stream-ordered: the engine's stream is non-blocking, a legacy-stream cudaMemcpy would not be ordered before
+    // the re-packing kernels launched on it
+    DDPM_CUDA(cudaMemcpyAsync(e.P, host.data(), (size_t)e.n_params * 4, cudaMemcpyHostToDevice, e.stream));
     e.pack_weights();
-    DDPM_CUDA(cudaStreamSynchronize(e.stream));
+    DDPM_CUDA(cudaStreamSynchronize(e.stream));        // `host` goes out of scope
     API_END
 }
 
 static void fetch_arena(Engine& e, const float* dev, float* const* arrays, const int64_t* lens, int n) {
     check_lens(e, lens, n);
     std::vector<float> host((size_t)e.n_params);
+    DDPM_CUDA(cudaMemcpyAsync(host.data(), dev, (size_t)e.n_params * 4, cudaMemcpyDeviceToHost, e.stream));
     DDPM_CUDA(cudaStreamSynchronize(e.stream));
-    DDPM_CUDA(cudaMemcpy(host.data(), dev, (size_t)e.n_params * 4, cudaMemcpyDeviceToHost));
     for (int k = 0; k < n; ++k) std::memcpy(arrays[k], host.data() + e.offs[k], (size_t)lens[k] * 4);
+}
+
+static void store_arena(Engine& e, float* dev, const float* const* arrays, const int64_t* lens, int n) {
+    check_lens(e, lens, n);
+    std::vector<float> host((size_t)e.n_params, 0.f);
+    for (int k = 0; k < n; ++k) std::memcpy(host.data() + e.offs[k], arrays[k], (size_t)lens[k] * 4);
+    DDPM_CUDA(cudaMemcpyAsync(dev, host.data(), (size_t)e.n_params * 4, cudaMemcpyHostToDevice, e.stream));
+    DDPM_CUDA(cudaStreamSynchronize(e.stream));
 }
 
 int ddpm_get_weights(ddpm_handle* h, float* const* arrays, const int64_t* lens, int n) {
@@ -136,9 +145,40 @@ int ddpm_get_weights(ddpm_handle* h, float* const* arrays, const int64_t* lens, 
 int ddpm_set_adam(ddpm_handle* h, float eta, float beta1, float beta2, float eps) {
     API_BEGIN
     Engine& e = E(h);
-    e.eta = eta; e.b1 = beta1; e.b2 = beta2; e.aeps = eps; e.bt1 = beta1; e.bt2 = beta2;
+    e.eta = eta; e.b1 = beta1; e.b2 = beta2; e.aeps = eps;
     DDPM_CUDA(cudaMemsetAsync(e.M1, 0, (size_t)e.n_params * 4, e.stream));
     DDPM_CUDA(cudaMemsetAsync(e.M2, 0, (size_t)e.n_params * 4, e.stream));
+    e.reset_train_state();
+    e.drop_train_graphs();          // eta / beta / eps are baked into the captured Adam launch
+    API_END
+}
+
+int ddpm_get_adam_state(ddpm_handle* h, float* const* m, float* const* v, const int64_t* lens, int n, float* beta_t,
+                        int64_t* steps) {
+    API_BEGIN
+    Engine& e = E(h);
+    DDPM_CHECK(m && v, "null moment arrays");
+    fetch_arena(e, e.M1, m, lens, n);
+    fetch_arena(e, e.M2, v, lens, n);
+    TrainState ts{};
+    DDPM_CUDA(cudaMemcpyAsync(&ts, e.d_tstate, sizeof ts, cudaMemcpyDeviceToHost, e.stream));
+    DDPM_CUDA(cudaStreamSynchronize(e.stream));
+    if (beta_t) { beta_t[0] = ts.bt1; beta_t[1] = ts.bt2; }
+    if (steps) *steps = ts.applied;
+    API_END
+}
+
+int ddpm_set_adam_state(ddpm_handle* h, const float* const* m, const float* const* v, const int64_t* lens, int n,
+                        const float* beta_t, int64_t steps) {
+    API_BEGIN
+    Engine& e = E(h);
+    DDPM_CHECK(m && v && beta_t, "null moment arrays");
+    store_arena(e, e.M1, m, lens, n);
+    store_arena(e, e.M2, v, lens, n);
+    TrainState ts{};
+    ts.bt1 = beta_t[0]; ts.bt2 = beta_t[1]; ts.applied = steps;
+    DDPM_CUDA(cudaMemcpyAsync(e.d_tstate, &ts, sizeof ts, cudaMemcpyHostToDevice, e.stream));
+    DDPM_CUDA(cudaStreamSynchronize(e.stream));
     API_END
 }
 
@@ -146,14 +186,16 @@ static void check_ts(Engine& e, const int32_t* ts, int B) {
     for (int i = 0; i < B; ++i) DDPM_CHECK(ts[i] >= 1 && ts[i] <= e.T, "timestep out of range 1..T");
 }
 
-static void upload_batch(Engine& e, const float* x0, const int32_t* ts, const float* eps, int B) {
+// stage one host batch in the given device buffers (engine-level ones for ddpm_q_sample, a training set's for a step)
+static void upload_batch(Engine& e, const float* x0, const int32_t* ts, const float* eps, int B, DevBuf& bx0, DevBuf& bts,
+                         DevBuf& beps) {
     size_t nb = (size_t)B * e.HW * 4;
-    if (x0) { e.d_x0.ensure(nb); DDPM_CUDA(cudaMemcpyAsync(e.d_x0.p, x0, nb, cudaMemcpyHostToDevice, e.stream)); }
-    if (eps) { e.d_eps.ensure(nb); DDPM_CUDA(cudaMemcpyAsync(e.d_eps.p, eps, nb, cudaMemcpyHostToDevice, e.stream)); }
+    if (x0) { bx0.ensure(nb); DDPM_CUDA(cudaMemcpyAsync(bx0.p, x0, nb, cudaMemcpyHostToDevice, e.stream)); }
+    if (eps) { beps.ensure(nb); DDPM_CUDA(cudaMemcpyAsync(beps.p, eps, nb, cudaMemcpyHostToDevice, e.stream)); }
     if (ts) {
         check_ts(e, ts, B);
-        e.d_ts.ensure((size_t)B * 4);
-        DDPM_CUDA(cudaMemcpyAsync(e.d_ts.p, ts, (size_t)B * 4, cudaMemcpyHostToDevice, e.stream));
+        bts.ensure((size_t)B * 4);
+        DDPM_CUDA(cudaMemcpyAsync(bts.p, ts, (size_t)B * 4, cudaMemcpyHostToDevice, e.stream));
     }
 }
 
@@ -161,7 +203,7 @@ int ddpm_q_sample(ddpm_handle* h, const float* x0, const int32_t* ts, const floa
     API_BEGIN
     Engine& e = E(h);
     DDPM_CHECK(B > 0 && x0 && ts && eps && x_t, "bad arguments");
-    upload_batch(e, x0, ts, eps, B);
+    upload_batch(e, x0, ts, eps, B, e.d_x0, e.d_ts, e.d_eps);
     e.d_xt.ensure((size_t)B * e.HW * 4);
     long long n4 = (long long)B * e.HW / 4;
     qsample_kernel<<<cdiv(n4, 256), 256, 0, e.stream>>>(e.d_x0.as<float>(), nullptr, e.d_eps.as<float>(), e.d_ts.as<int>(),
@@ -178,9 +220,14 @@ int ddpm_predict_eps(ddpm_handle* h, const float* x_t, const int32_t* ts, int B,
     Engine& e = E(h);
     DDPM_CHECK(B > 0 && x_t && ts && eps_hat, "bad arguments");
     ActSet& s = e.get_set(B, train_mode != 0);
-    upload_batch(e, nullptr, ts, nullptr, B);
+    upload_batch(e, nullptr, ts, nullptr, B, e.d_x0, e.d_ts, e.d_eps);
     DDPM_CUDA(cudaMemcpyAsync(s.x.p, x_t, (size_t)B * e.HW * 4, cudaMemcpyHostToDevice, e.stream));
-    e.forward(s, s.x.as<float>(), e.d_ts.as<int>(), 0, train_mode ? Mode::Train : Mode::Infer, false);
+    // a batch that shares one timestep (what reverse_diffusion evaluates, generate_images.jl:176-183) takes the
+    // sampler's first-conv path (tensor-core kernel with the timestep's folded embedding constants)
+    bool uniform = !train_mode;
+    for (int i = 1; i < B && uniform; ++i) uniform = ts[i] == ts[0];
+    if (uniform) e.forward(s, s.x.as<float>(), nullptr, ts[0], Mode::Infer, false);
+    else e.forward(s, s.x.as<float>(), e.d_ts.as<int>(), 0, train_mode ? Mode::Train : Mode::Infer, false);
     DDPM_DISPATCH(e.prec, (e.final_conv_t<TA, TG>(s, s.eps_hat.as<float>())));
     DDPM_CUDA(cudaMemcpyAsync(eps_hat, s.eps_hat.p, (size_t)B * e.HW * 4, cudaMemcpyDeviceToHost, e.stream));
     DDPM_CUDA(cudaStreamSynchronize(e.stream));
@@ -190,10 +237,12 @@ int ddpm_predict_eps(ddpm_handle* h, const float* x_t, const int32_t* ts, int B,
 int ddpm_train_step(ddpm_handle* h, const float* x0, const int32_t* ts, const float* eps, int B, float* loss) {
     API_BEGIN
     Engine& e = E(h);
-    DDPM_CHECK(B > 1 && x0 && ts && eps, "bad arguments (B must be > 1 for batch statistics)");
-    upload_batch(e, x0, ts, eps, B);
+    // B == 1 is legal: Flux BatchNorm reduces over W*H*B, the reference trains on a trailing batch of one
+    DDPM_CHECK(B >= 1 && x0 && ts && eps, "bad arguments");
+    ActSet& s = e.get_set(B, true);
+    upload_batch(e, x0, ts, eps, B, s.x0, s.ts, s.eps);
     float l = 0.f;
-    e.train_core(B, false, true, &l);
+    e.train_core(s, false, false, true, &l);
     if (loss) *loss = l;
     API_END
 }
@@ -202,10 +251,11 @@ int ddpm_loss_and_grad(ddpm_handle* h, const float* x0, const int32_t* ts, const
                        float* const* grads, const int64_t* lens, int n) {
     API_BEGIN
     Engine& e = E(h);
-    DDPM_CHECK(B > 1 && x0 && ts && eps, "bad arguments");
-    upload_batch(e, x0, ts, eps, B);
+    DDPM_CHECK(B >= 1 && x0 && ts && eps, "bad arguments");
+    ActSet& s = e.get_set(B, true);
+    upload_batch(e, x0, ts, eps, B, s.x0, s.ts, s.eps);
     float l = 0.f;
-    e.train_core(B, false, false, &l);
+    e.train_core(s, false, false, false, &l);
     if (loss) *loss = l;
     if (grads) fetch_arena(e, e.G, grads, lens, n);
     API_END
@@ -216,8 +266,10 @@ int ddpm_upload_dataset(ddpm_handle* h, const float* imgs, int64_t n_imgs) {
     Engine& e = E(h);
     DDPM_CHECK(imgs && n_imgs > 0, "bad arguments");
     DDPM_CUDA(cudaStreamSynchronize(e.stream));
+    if (e.d_dataset.cap < (size_t)n_imgs * e.HW * 4) e.drop_train_graphs();   // captured gathers hold the old pointer
     e.d_dataset.ensure((size_t)n_imgs * e.HW * 4);
-    DDPM_CUDA(cudaMemcpy(e.d_dataset.p, imgs, (size_t)n_imgs * e.HW * 4, cudaMemcpyHostToDevice));
+    DDPM_CUDA(cudaMemcpyAsync(e.d_dataset.p, imgs, (size_t)n_imgs * e.HW * 4, cudaMemcpyHostToDevice, e.stream));
+    DDPM_CUDA(cudaStreamSynchronize(e.stream));       // the caller's buffer is only borrowed for the call
     e.dataset_n = n_imgs;
     API_END
 }
@@ -225,27 +277,21 @@ int ddpm_upload_dataset(ddpm_handle* h, const float* imgs, int64_t n_imgs) {
 int ddpm_train_step_device(ddpm_handle* h, const int32_t* idx, int B, uint64_t seed, int64_t step, float* loss) {
     API_BEGIN
     Engine& e = E(h);
-    DDPM_CHECK(B > 1 && e.dataset_n > 0, "upload a dataset first");
+    DDPM_CHECK(B >= 1 && e.dataset_n > 0, "upload a dataset first");
     std::vector<int> host_idx(B);
     for (int i = 0; i < B; ++i) {
         host_idx[i] = idx ? idx[i] : (int)(i % e.dataset_n);
         DDPM_CHECK(host_idx[i] >= 0 && host_idx[i] < e.dataset_n, "dataset index out of range");
     }
-    e.d_idx.ensure((size_t)B * 4);
-    DDPM_CUDA(cudaMemcpyAsync(e.d_idx.p, host_idx.data(), (size_t)B * 4, cudaMemcpyHostToDevice, e.stream));
-    e.d_ts.ensure((size_t)B * 4);
-    e.d_eps.ensure((size_t)B * e.HW * 4);
-    long long first = (long long)e.rank * B;
-    randint_ts_kernel<<<cdiv(B, 256), 256, 0, e.stream>>>(e.d_ts.as<int>(), B, e.T, seed, first, (uint32_t)step);
-    long long quads = (long long)B * e.HW / 4;
-    randn_kernel<<<cdiv(quads, 256), 256, 0, e.stream>>>(e.d_eps.as<float>(), B, e.HW, seed ^ 0x9E3779B97F4A7C15ull, first,
-                                                         (uint32_t)step);
-    DDPM_LAUNCH_CHECK();
-    e.cnt_launches += 2;
+    ActSet& s = e.get_set(B, true);
+    DDPM_CUDA(cudaMemcpyAsync(s.idx.p, host_idx.data(), (size_t)B * 4, cudaMemcpyHostToDevice, e.stream));
+    // ts ~ U{1..T} and eps ~ N(0,1) are drawn inside the step from Philox keyed by (seed, global image index, step)
+    const unsigned long long rng3[3] = {seed, (unsigned long long)((long long)e.rank * B), (unsigned long long)step};
+    DDPM_CUDA(cudaMemcpyAsync(e.d_trng, rng3, sizeof rng3, cudaMemcpyHostToDevice, e.stream));
     float l = 0.f;
-    e.train_core(B, true, true, loss ? &l : nullptr);
+    e.train_core(s, true, true, true, loss ? &l : nullptr);
     if (loss) *loss = l;
-    else DDPM_CUDA(cudaStreamSynchronize(e.stream));  // host_idx must outlive the async copy
+    else DDPM_CUDA(cudaStreamSynchronize(e.stream));  // host_idx / rng3 must outlive the async copies
     API_END
 }
 
@@ -340,8 +386,23 @@ int ddpm_sample_device(ddpm_handle* h, uint64_t seed, int64_t N, int64_t first_i
 int ddpm_sample_fetch(ddpm_handle* h, int64_t N, float* out) {
     API_BEGIN
     Engine& e = E(h);
-    DDPM_CHECK(out && (size_t)N * e.HW * 4 <= e.d_sample_out.cap, "nothing to fetch");
-    DDPM_CUDA(cudaMemcpy(out, e.d_sample_out.p, (size_t)N * e.HW * 4, cudaMemcpyDeviceToHost));
+    DDPM_CHECK(out && N > 0 && (size_t)N * e.HW * 4 <= e.d_sample_out.cap, "nothing to fetch");
+    DDPM_CUDA(cudaMemcpyAsync(out, e.d_sample_out.p, (size_t)N * e.HW * 4, cudaMemcpyDeviceToHost, e.stream));
+    DDPM_CUDA(cudaStreamSynchronize(e.stream));
+    API_END
+}
+
+int ddpm_sample_fetch_u8(ddpm_handle* h, int64_t N, uint8_t* out) {
+    API_BEGIN
+    Engine& e = E(h);
+    DDPM_CHECK(out && N > 0 && (size_t)N * e.HW * 4 <= e.d_sample_out.cap, "nothing to fetch");
+    const long long n4 = (long long)N * e.HW / 4;
+    e.d_u8.ensure((size_t)n4 * 4);
+    quantize_u8_kernel<<<cdiv(n4, 256), 256, 0, e.stream>>>(e.d_sample_out.as<float>(), n4, e.d_u8.as<uint32_t>());
+    DDPM_LAUNCH_CHECK();
+    e.cnt_launches += 1;
+    DDPM_CUDA(cudaMemcpyAsync(out, e.d_u8.p, (size_t)n4 * 4, cudaMemcpyDeviceToHost, e.stream));
+    DDPM_CUDA(cudaStreamSynchronize(e.stream));
     API_END
 }
 
@@ -405,17 +466,13 @@ int ddpm_set_option(ddpm_handle* h, const char* key, int64_t value) {
     else if (k == "sample_streams") { DDPM_CHECK(value >= 1 && value <= Engine::MAX_SAMPLE_STREAMS, "sample_streams must be 1..2"); e.opt_sample_streams = value; }
     else if (k == "use_graph") e.opt_use_graph = value;
     else if (k == "conv_impl") { e.opt_conv_impl = value; for (auto& kv : e.infer_sets) kv.second->drop_graphs(); }
-    else if (k == "sync_bn") e.sync_bn = (int)value;
+    else if (k == "sync_bn") { e.sync_bn = (int)value; e.drop_train_graphs(); }
+    else if (k == "train_graph") { e.opt_train_graph = value; e.drop_train_graphs(); }
+    else if (k == "loss_scale_log2") { DDPM_CHECK(value >= -30 && value <= 30, "loss_scale_log2 out of range"); e.opt_loss_scale_log2 = value; e.drop_train_graphs(); }
     else if (k == "tc_tma_store") { tc::state().tma_store = value != 0; for (auto& kv : e.infer_sets) kv.second->drop_graphs(); }
     else if (k == "tc_pair") { tc::state().pair_mask = value; for (auto& kv : e.infer_sets) kv.second->drop_graphs(); }
     else if (k == "tc_pdl") { tc::state().pdl = value != 0; for (auto& kv : e.infer_sets) kv.second->drop_graphs(); }
     else if (k == "conv1_tc") { e.opt_conv1_tc = value; for (auto& kv : e.infer_sets) kv.second->drop_graphs(); }
-    else if (k == "conv_v2") {
-        const bool turn_on = value && !e.opt_conv_v2;
-        e.opt_conv_v2 = value;
-        if (turn_on) e.pack_weights();        // the row-packed weight layouts are only maintained while the option is on
-        for (auto& kv : e.infer_sets) kv.second->drop_graphs();
-    }
     else if (k == "fuse_final") { e.opt_fuse_final = value; for (auto& kv : e.infer_sets) kv.second->drop_graphs(); }
     else if (k == "tc_role_profile") {
         // per-CTA cycle breakdown of the tcgen05 kernel roles, read back with ddpm_debug_fetch("tc_roles")
@@ -435,6 +492,15 @@ int64_t ddpm_get_counter(ddpm_handle* h, const char* key) {
     if (k == "n_params") return h->eng->n_params;
     if (k == "tc_available") return tc::available() ? 1 : 0;
     if (k == "uses_tc") return h->eng->use_tc() ? 1 : 0;
+    if (k == "skipped_steps" || k == "applied_steps") {
+        // device-resident optimiser counters (overflow guard): a synchronising read
+        Engine& e = *h->eng;
+        TrainState ts{};
+        if (cudaSetDevice(e.dev) != cudaSuccess) return -1;
+        if (cudaMemcpyAsync(&ts, e.d_tstate, sizeof ts, cudaMemcpyDeviceToHost, e.stream) != cudaSuccess) return -1;
+        if (cudaStreamSynchronize(e.stream) != cudaSuccess) return -1;
+        return k == "skipped_steps" ? (int64_t)ts.skipped : (int64_t)ts.applied;
+    }
     return -1;
 }
 
@@ -478,7 +544,7 @@ int ddpm_time_kernel(ddpm_handle* h, const char* name, int64_t n_images, int ite
     long long n4 = (long long)N * HW / 4;
     if (k == "qsample" || k == "mse") {
         e.d_x0.ensure((size_t)N * HW * 4); e.d_eps.ensure((size_t)N * HW * 4); e.d_xt.ensure((size_t)N * HW * 4);
-        e.d_ts.ensure((size_t)N * 4); e.d_deps.ensure((size_t)N * HW * 4);
+        e.d_ts.ensure((size_t)N * 4);
         randn_kernel<<<cdiv(n4, 256), 256, 0, e.stream>>>(e.d_x0.as<float>(), N, HW, 1, 0, 0);
         randn_kernel<<<cdiv(n4, 256), 256, 0, e.stream>>>(e.d_eps.as<float>(), N, HW, 2, 0, 0);
         randint_ts_kernel<<<cdiv(N, 256), 256, 0, e.stream>>>(e.d_ts.as<int>(), N, e.T, 3, 0, 0);
@@ -505,7 +571,7 @@ int ddpm_time_kernel(ddpm_handle* h, const char* name, int64_t n_images, int ite
         DDPM_CUDA(cudaMemsetAsync(sv.p, 0, (size_t)e.n_params * 4, e.stream));
         time_it([&] {
             adam_kernel<<<cdiv(e.n_params, 256), 256, 0, e.stream>>>(sp.as<float>(), e.G, sm.as<float>(), sv.as<float>(),
-                                                                     e.n_params, e.eta, e.b1, e.b2, e.aeps, e.bt1, e.bt2);
+                                                                     e.n_params, e.eta, e.b1, e.b2, e.aeps, e.d_tstate);
         });
         DDPM_CUDA(cudaStreamSynchronize(e.stream));
         sp.release(); sm.release(); sv.release();
@@ -598,12 +664,13 @@ int ddpm_debug_fetch(ddpm_handle* h, const char* name, float* out, int64_t capac
         for (size_t i = 0; i < hbuf.size(); ++i) out[i] = (float)hbuf[i];
         return 0;
     }
-    ActSet* sp = &e.train_set;
+    ActSet* sp = e.last_train_set;
     if (k.rfind("infer:", 0) == 0) {
         DDPM_CHECK(!e.infer_sets.empty(), "no inference activations");
         sp = e.infer_sets.rbegin()->second;
         k = k.substr(6);
     }
+    DDPM_CHECK(sp != nullptr, "no activations recorded yet");
     ActSet& s = *sp;
     DDPM_CHECK(s.N > 0, "no activations recorded yet");
     const Tensor* t = nullptr;

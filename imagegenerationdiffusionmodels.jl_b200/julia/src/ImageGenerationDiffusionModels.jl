@@ -13,7 +13,7 @@ using BSON: @save, @load
 include("LibDDPM.jl")
 using .LibDDPM
 
-export generate_grid, apply_noise, train, denoise_image, generate_image, demo, SimpleUNet
+export generate_grid, apply_noise, train, denoise_image, generate_image, demo
 
 # ---- constants of the scripts (src/train_brain.jl:17-24; T = 500 is the intended value, see SURVEY.md trap 2)
 const D = 128
@@ -35,27 +35,42 @@ function timestep_embedding(t::Integer; D::Int=D)          # src/train_brain.jl:
 end
 const PE = hcat((timestep_embedding(t) for t in 1:T)...)   # D x T, column t
 
-# ---- the model container: identical struct and constructor to src/train_brain.jl:89-145
-struct SimpleUNet
-    down1::Chain
-    down2::Chain
-    mid::Chain
-    up2::Chain
-    up1::Chain
-    final::Conv
+# ---- the model container: identical struct and constructor to src/train_brain.jl:89-145.
+# BSON.jl tags a struct with the module path of its type.  The shipped checkpoints were written by the driver SCRIPTS,
+# so their model type is `Main.SimpleUNet` (SURVEY.md Appendix C): `@load` resolves that name in Main, and a struct
+# defined inside this package would be SAVED as `ImageGenerationDiffusionModels.SimpleUNet` -- readable by nobody else.
+# To keep the on-disk format unchanged in BOTH directions the struct is therefore defined in Main when the package
+# loads (unless the user's script already did, as the reference's scripts do) and referred to through `unet_type()`.
+function __init__()
+    if !isdefined(Main, :SimpleUNet)
+        Core.eval(Main, quote
+            import Flux
+            struct SimpleUNet
+                down1::Flux.Chain
+                down2::Flux.Chain
+                mid::Flux.Chain
+                up2::Flux.Chain
+                up1::Flux.Chain
+                final::Flux.Conv
+            end
+        end)
+    end
 end
-function SimpleUNet(channels::Int=1)
+unet_type() = getfield(Main, :SimpleUNet)
+
+function SimpleUNet(channels::Int=1)                       # src/train_brain.jl:109-145
     down1 = Chain(Conv((3,3), channels + D => 64, pad=1), BatchNorm(64, relu), Conv((3,3), 64 => 64, pad=1), BatchNorm(64, relu))
     down2 = Chain(MaxPool((2,2)), Conv((3,3), 64 => 128, pad=1), BatchNorm(128, relu), Conv((3,3), 128 => 128, pad=1), BatchNorm(128, relu))
     mid   = Chain(Conv((3,3), 128 => 128, pad=1), BatchNorm(128, relu), Conv((3,3), 128 => 128, pad=1), BatchNorm(128, relu))
     up2   = Chain(ConvTranspose((2,2), 128 => 64, stride=2), Conv((3,3), 64 => 64, pad=1), BatchNorm(64, relu), Conv((3,3), 64 => 64, pad=1), BatchNorm(64, relu))
     up1   = Chain(Conv((3,3), 128 => 64, pad=1), BatchNorm(64, relu), Conv((3,3), 64 => 64, pad=1), BatchNorm(64, relu))
     final = Conv((1,1), 64 => 1)
-    SimpleUNet(down1, down2, mid, up2, up1, final)
+    # the type was created by `__init__` at run time: construct it in the latest world
+    return Base.invokelatest(unet_type(), down1, down2, mid, up2, up1, final)
 end
 
 "The 64 Float32 arrays in BSON order: conv (weight, bias); BatchNorm (β, γ, μ, σ²).  They alias the model."
-function flux_arrays(m::SimpleUNet)
+function flux_arrays(m)
     out = Array{Float32}[]
     for chain in (m.down1, m.down2, m.mid, m.up2, m.up1)
         for l in chain.layers
@@ -80,7 +95,7 @@ function engine()
     return _engine[]
 end
 
-const _model = Ref{Union{Nothing,SimpleUNet}}(nothing)
+const _model = Ref{Any}(nothing)
 function default_model()
     if _model[] === nothing
         @load joinpath(@__DIR__, "..", "..", "..", "fixtures", "trained_model.bson") model
@@ -139,7 +154,8 @@ function batch_iterator(imgs::Array{Float32,4}, bs::Int)   # src/train_brain.jl:
     end)
 end
 
-function train(data, lr::Float32=Float32(1e-4), epochs::Int=100, patience::Int=10, min_delta::Float64=0.001; batch_size::Int=64)
+function train(data, lr=1f-4, epochs::Int=100, patience::Int=10, min_delta::Real=0.001; batch_size::Int=64)
+    lr = Float32(lr)
     raw  = matread(data)["syntheticImages"]
     imgs = reshape(Float32.(raw), 32, 32, 1, :)
     imgs .*= 2; imgs .-= 1                                   # src/train_brain.jl:250-251

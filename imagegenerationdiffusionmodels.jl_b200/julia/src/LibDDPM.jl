@@ -64,6 +64,27 @@ end
 set_adam!(h::Handle, eta::Float32; beta=(0.9f0, 0.999f0), eps::Float32=1f-8) =
     check(ccall((:ddpm_set_adam, libddpm), Cint, (Ptr{Cvoid}, Cfloat, Cfloat, Cfloat, Cfloat), h.ptr, eta, beta[1], beta[2], eps))
 
+"Adam moments (64 arrays each, weight order), (beta1^t, beta2^t) of the next update and the applied-step count."
+function get_adam_state(h::Handle)
+    lens = array_lengths()
+    m = [zeros(Float32, n) for n in lens]; v = [zeros(Float32, n) for n in lens]
+    pm = Ptr{Float32}[pointer(a) for a in m]; pv = Ptr{Float32}[pointer(a) for a in v]
+    bt = zeros(Float32, 2); steps = Ref{Int64}(0)
+    GC.@preserve m v check(ccall((:ddpm_get_adam_state, libddpm), Cint,
+        (Ptr{Cvoid}, Ptr{Ptr{Float32}}, Ptr{Ptr{Float32}}, Ptr{Int64}, Cint, Ptr{Float32}, Ref{Int64}),
+        h.ptr, pm, pv, lens, length(lens), bt, steps))
+    return m, v, (bt[1], bt[2]), steps[]
+end
+
+function set_adam_state!(h::Handle, m::Vector{Vector{Float32}}, v::Vector{Vector{Float32}}, beta_t, steps::Integer)
+    lens = Int64[length(a) for a in m]
+    pm = Ptr{Float32}[pointer(a) for a in m]; pv = Ptr{Float32}[pointer(a) for a in v]
+    bt = Float32[beta_t[1], beta_t[2]]
+    GC.@preserve m v check(ccall((:ddpm_set_adam_state, libddpm), Cint,
+        (Ptr{Cvoid}, Ptr{Ptr{Float32}}, Ptr{Ptr{Float32}}, Ptr{Int64}, Cint, Ptr{Float32}, Int64),
+        h.ptr, pm, pv, lens, length(lens), bt, Int64(steps)))
+end
+
 function q_sample(h::Handle, x0::Array{Float32,4}, ts::Vector{Int32}, eps::Array{Float32,4})
     xt = similar(x0)
     check(ccall((:ddpm_q_sample, libddpm), Cint, (Ptr{Cvoid}, Ptr{Float32}, Ptr{Int32}, Ptr{Float32}, Cint, Ptr{Float32}),
@@ -100,6 +121,15 @@ function sample(h::Handle, N::Integer; x_T=nothing, z=nothing, seed::Integer=0, 
     GC.@preserve x_T z check(ccall((:ddpm_sample, libddpm), Cint,
         (Ptr{Cvoid}, Ptr{Float32}, Ptr{Float32}, UInt64, Int64, Int64, Cint, Ptr{Float32}),
         h.ptr, xp, zp, UInt64(seed), Int64(N), Int64(first_index), Cint(t_start), out))
+    return out
+end
+
+"Bulk dumps: sample N images on the device, then fetch them quantised to 8 bits ((x+1)/2 -> N0f8) -- 1 byte per pixel."
+function sample_u8(h::Handle, N::Integer; seed::Integer=0, first_index::Integer=0, t_start::Integer=h.T)
+    check(ccall((:ddpm_sample_device, libddpm), Cint, (Ptr{Cvoid}, UInt64, Int64, Int64, Cint),
+                h.ptr, UInt64(seed), Int64(N), Int64(first_index), Cint(t_start)))
+    out = Array{UInt8,4}(undef, 32, 32, 1, N)
+    check(ccall((:ddpm_sample_fetch_u8, libddpm), Cint, (Ptr{Cvoid}, Int64, Ptr{UInt8}), h.ptr, Int64(N), out))
     return out
 end
 

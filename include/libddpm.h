@@ -68,6 +68,16 @@ int ddpm_get_weights(ddpm_handle*, float* const* arrays, const int64_t* lens, in
 /* `Adam(lr)` + `Flux.setup` (src/train_brain.jl:255-257): sets the rule and zeroes the moments. */
 int ddpm_set_adam(ddpm_handle*, float eta, float beta1, float beta2, float eps);
 
+/* Optimiser state for a true resume.  The reference saves only the RULE (`@save ... model opt`,
+ * src/train_brain.jl:295-300; `state = Flux.setup(opt, model)` at :257 is never written), so a run continued from
+ * one of its checkpoints restarts Adam from zero moments.  These two calls move the moment arenas m, v (64 arrays in
+ * the weight order; zero for mu/sigma2), the bias-correction powers beta_t = (beta1^t, beta2^t) of the next update
+ * and the number of updates applied so far. */
+int ddpm_get_adam_state(ddpm_handle*, float* const* m, float* const* v, const int64_t* lens, int n,
+                        float* beta_t /*[2]*/, int64_t* steps);
+int ddpm_set_adam_state(ddpm_handle*, const float* const* m, const float* const* v, const int64_t* lens, int n,
+                        const float* beta_t /*[2]*/, int64_t steps);
+
 /* `x_t = a .* x0 .+ b .* eps` of train_step (src/train_brain.jl:230-233). */
 int ddpm_q_sample(ddpm_handle*, const float* x0, const int32_t* ts, const float* eps, int B, float* x_t);
 
@@ -105,6 +115,10 @@ int ddpm_sample(ddpm_handle*, const float* x_T, const float* z, uint64_t seed, i
  * an internal buffer readable with ddpm_sample_fetch. */
 int ddpm_sample_device(ddpm_handle*, uint64_t seed, int64_t N, int64_t first_index, int t_start);
 int ddpm_sample_fetch(ddpm_handle*, int64_t N, float* out);
+/* Output step of bulk dumps (`(img .+ 1) ./ 2` -> Gray image, src/generate_images.jl:256-265): the device-resident
+ * result of ddpm_sample_device quantised on the device to 8 bits, round(clamp((x+1)/2, 0, 1) * 255) with ties to
+ * even -- the byte the host PNG writer would produce --, N*H*W bytes in the image layout of `out` above. */
+int ddpm_sample_fetch_u8(ddpm_handle*, int64_t N, uint8_t* out);
 
 /* `apply_noise` (src/ImageGenerationDiffusionModels.jl:60-73): the same-eps recurrence
  * `img = sqrt(1-beta).*img + sqrt(beta).*epsilon` over the host-supplied Float64 `betas`
@@ -127,8 +141,11 @@ int ddpm_comm_init(ddpm_handle*, const void* id, int rank, int world, int sync_b
  *   fuse_final (1: last conv + final 1x1 conv + reverse update in one epilogue),
  *   tc_pair (bit mask of layer shapes run as CTA pairs / cta_group::2, 31 = all), tc_pdl (1: programmatic dependent
  *   launch of the tcgen05 kernels), conv1_tc (1: first conv of the sampler on tensor cores), tc_tma_store (1),
- *   conv_v2 (0: second, row-packed conv formulation), tc_role_profile (0: in-kernel cycle counters).
- * None of them changes results beyond the documented rounding of the selected kernels. */
+ *   tc_role_profile (0: in-kernel cycle counters), train_graph (1: replay the training iteration from a CUDA graph),
+ *   loss_scale_log2 (0: extra power-of-two factor on the static loss scale of the 16-bit gradient tensors).
+ * None of them changes results beyond the documented rounding of the selected kernels.
+ * Counter keys: launches, n_params, tc_available, uses_tc, skipped_steps (updates skipped by the overflow guard: a
+ * non-finite value in the reduced gradient leaves weights, moments and beta^t untouched), applied_steps. */
 int ddpm_set_option(ddpm_handle*, const char* key, int64_t value);
 int64_t ddpm_get_counter(ddpm_handle*, const char* key);
 /* CUDA-event stopwatch on the engine's launch stream (device time of everything enqueued between

@@ -82,7 +82,9 @@ def test_apply_noise_bit_exact(oracle):
 
 
 # ------------------------------------------------------------------------------ forward parity
-TOL_EPS = {"fp32": 2e-4, "fp16": 1e-2, "bf16": 3e-2}   # north_star: rel-L2 <= 1e-2 (bf16 is a reported mode)
+# north_star: rel-L2 <= 1e-2.  Bounds are <= 5x what round 1 measured on B200 (fp32 9e-7, fp16 6.6e-4 test / 8.2e-4 train
+# BatchNorm, bf16 5.2e-3 / 6.6e-3): a regression of one order of magnitude fails, and bf16 sits on the north_star bar.
+TOL_EPS = {"fp32": 5e-6, "fp16": 4e-3, "bf16": 1e-2}
 
 
 @pytest.mark.parametrize("mode", ["fp32", "fp16", "bf16"])
@@ -121,7 +123,7 @@ def test_per_layer_activations_fp32(gpu_handles, oracle, model_arrays, dataset, 
         got = h.debug_fetch(nm).reshape(want.shape)
         report[nm] = rel_l2(got, want)
     _dump("per_layer_fp32.json", report)
-    bad = {k: v for k, v in report.items() if v > 2e-4}
+    bad = {k: v for k, v in report.items() if v > 6e-6}     # measured <= 1.2e-6 on every tensor
     assert not bad, bad
 
 
@@ -140,7 +142,9 @@ def test_known_answer_through_abi(gpu_handles, model_arrays, tabs):
 
 
 # ------------------------------------------------------------------------------ backward parity
+# measured worst per-array rel-L2 (round 1, B200): fp32 8.4e-4, fp16 3.3e-2, bf16 9.1e-2 (forward rounding dominates)
 GRAD_TOL = {"fp32": 2e-3, "fp16": 6e-2, "bf16": 1.5e-1}
+LOSS_TOL = {"fp32": 2e-6, "fp16": 2e-5, "bf16": 1e-3}    # measured 7e-8 / 2e-6 / 1.4e-4 relative
 
 
 @pytest.mark.parametrize("mode", ["fp32", "fp16", "bf16"])
@@ -172,7 +176,7 @@ def test_loss_and_grad_parity(gpu_handles, oracle, model_arrays, dataset, tabs, 
         report[f"g{k}"] = {"rel": r, "norm": wn}
         worst = max(worst, r)
     _dump(f"grad_parity_{mode}.json", report)
-    assert abs(loss - want_loss) <= 1e-3 * want_loss, (loss, want_loss)
+    assert abs(loss - want_loss) <= LOSS_TOL[mode] * want_loss, (loss, want_loss)
     assert worst <= GRAD_TOL[mode], report
 
 
@@ -203,7 +207,8 @@ def test_training_epoch_loss_parity(gpu_handles, oracle, model_arrays, dataset, 
         stats[f"w{k}"] = rel_l2(w_gpu[k], w_cpu[k])
     _dump(f"train_epoch_{mode}.json", {"steps": rows, "weights": stats})
     assert len(rows) == 8 and rows[-1]["B"] == 52
-    assert max(r["rel"] for r in rows) <= 1e-3, rows
+    # north_star: 1e-3 relative; measured <= 1.4e-4 (fp16) and <= 1.1e-4 (fp32: the sign-like first Adam steps amplify summation-order noise)
+    assert max(r["rel"] for r in rows) <= (3e-4 if mode == "fp32" else 7e-4), rows
     h.set_weights(model_arrays)
 
 
@@ -215,11 +220,12 @@ def test_sampler_host_noise_parity_fp32(gpu_handles, oracle, model_arrays, tabs)
     xT = np.random.default_rng(5).standard_normal((2, 1, 32, 32)).astype(np.float32)
     z = np.random.default_rng(6).standard_normal((5, 2, 1, 32, 32)).astype(np.float32)
     got = h.sample(2, x_T=xT, z=z, t_start=6)
-    assert np.abs(got - g["samp_t6"]).max() < 2e-4
+    assert np.abs(got - g["samp_t6"]).max() < 2e-5
     assert np.abs(got).max() <= 1.0
 
 
-@pytest.mark.parametrize("mode,tol", [("fp32", 5e-3), ("fp16", 5e-2)])
+# mean abs error after all 499 steps, measured on B200: fp32 1.0e-7, fp16 1.9e-4 (max 2.6e-3)
+@pytest.mark.parametrize("mode,tol", [("fp32", 1e-6), ("fp16", 1e-3)])
 def test_sampler_full_500_steps(gpu_handles, oracle, model_arrays, tabs, mode, tol):
     """BASELINE config 1: generate_image(num_images=1) -- all 499 evaluations on identical host noise."""
     h = gpu_handles[mode]

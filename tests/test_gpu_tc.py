@@ -81,36 +81,6 @@ def test_fused_final_epilogue_matches_unfused(gpu_handles, model_arrays):
     assert np.abs(b).max() <= 1.0
 
 
-def test_row_packed_conv_matches_first_formulation(gpu_handles, oracle, model_arrays, dataset, tabs):
-    """conv3_tc.cuh (three column taps packed into N=192, epilogue shuffle recombination) against conv_tc.cuh
-    (one MMA per tap) on every layer, forward and backward, plus the fused sampler epilogue."""
-    h = gpu_handles["fp16"]
-    h.set_weights(model_arrays)
-    B = 9
-    x0, ts, eps = config2_batch(dataset, B)
-    xt = oracle.q_sample(x0, ts, eps, tabs["acum"])
-    xT = np.random.default_rng(0).standard_normal((3, 1, 32, 32)).astype(np.float32)
-    z = np.random.default_rng(1).standard_normal((7, 3, 1, 32, 32)).astype(np.float32)
-    try:
-        h.set_option("conv_v2", 0)
-        a = _layers(h, xt, ts)
-        la, ga = h.loss_and_grad(x0, ts, eps)
-        sa = h.sample(3, x_T=xT, z=z, t_start=8)
-        h.set_option("conv_v2", 1)
-        b = _layers(h, xt, ts)
-        lb, gb = h.loss_and_grad(x0, ts, eps)
-        sb = h.sample(3, x_T=xT, z=z, t_start=8)
-    finally:
-        h.set_option("conv_v2", 0)
-    rep = {nm: rel_l2(b[nm], a[nm]) for nm in NAMES}
-    _dump("conv_v2_vs_v1.json", rep)
-    assert max(rep.values()) < 2e-3, rep
-    assert abs(la - lb) <= 1e-4 * la
-    for k in (6, 12, 18, 36, 50, 56):
-        assert rel_l2(gb[k], ga[k]) < 3e-2
-    assert np.abs(sa - sb).max() < 5e-3
-
-
 def test_cta_pair_convs_match_single_cta_convs(gpu_handles, oracle, model_arrays, dataset, tabs):
     """cta_group::2 kernels (two CTAs share one M=256 MMA stream, each staging half of the weight rows) against the
     single-CTA kernels: same K order per output element, so test-mode outputs and the sampler are bit-identical;
