@@ -303,6 +303,18 @@ struct TcParams {
     const float* bf;
     float sig, sqa, sqp, sqv;   // sigma_t, sqrt(a_t), sqrt(a_prev), sqrt(post_var)
     int final_clamp;
+    // BNS != 0: per-channel reductions of the STORED (rounded) output tile, fused into the epilogue (train-mode
+    // BatchNorm, train_brain.jl:112-140): Float64 sums[2][stats_C], one atomic per channel, quantity and CTA.
+    //   BNS == 1 (forward):  sums[0][c] += sum out,  sums[1][c] += sum out^2      (batch statistics of y)
+    //   BNS == 2 (backward, the output is da = dL/d(BN-ReLU output) of the layer whose pre-BN tensor is bn_y):
+    //                        g = da * [bn_y*scale + shift > 0];  sums[0][c] += sum g,  sums[1][c] += sum g * xhat,
+    //                        xhat = (bn_y - mean) * istd          (first pass of the BatchNorm backward)
+    double* stats;
+    int stats_C;                // channel count of the statistics vectors (second quantity starts at stats_C)
+    int stats_nch;              // BNS == 2: only output channels [0, stats_nch) carry a BatchNorm (d(cat): first half)
+    const void* bn_y;           // BNS == 2: position 0 of the pre-BatchNorm tensor y (same geometry, bn_cs channels)
+    int bn_cs;
+    const float *bn_scale, *bn_shift, *bn_mean, *bn_istd;
 };
 
 // TAPS: 9 (3x3 conv, halo'ed slab) or 1 (plain GEMM rows); CHUNKS: 64-channel K chunks (1|2);
@@ -352,7 +364,7 @@ constexpr int pick_stages() {
 // channels); rank 0 issues M=256 MMAs that read both CTAs' shared memory, each CTA's TMEM receives all NOUT columns
 // of its own 128 positions.  Per SM and MMA the shared-memory operand traffic drops from 4 KB + NOUT*32 B to
 // 4 KB + NOUT*16 B, and 128 => 128 layers no longer need the Cout split that re-read every slab twice.
-template <int TAPS, int CHUNKS, int NOUT, int WP, int STAGES, int EPI, int TMAST, int CG, typename TIn, typename TOut>
+template <int TAPS, int CHUNKS, int NOUT, int WP, int STAGES, int EPI, int TMAST, int CG, int BNS, typename TIn, typename TOut>
 __global__ void __launch_bounds__(TC_THREADS, 1)
 conv_tc_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constant__ CUtensorMap tmA1,
                const __grid_constant__ CUtensorMap tmW, const __grid_constant__ CUtensorMap tmO, const TcParams p) {
@@ -390,6 +402,8 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constant__
     static_assert(8 * (NWG + 2 * STAGES + 2 * ACC_BUFS) + 4 <= 384, "barrier area overflows into the shift vector");
     float* s_shift = reinterpret_cast<float*>(misc + 384);               // [NOUT] per-channel shift of this CTA's N-slice
     float* s_wf = s_shift + 128;                                         // [64] final-conv weights (EPI == 2)
+    static_assert(BNS == 0 || (EPI == 0 && (TMAST || stage_cols<TAPS, CHUNKS, NOUT, WP, EPI, TMAST, CG>() > 0)),
+                  "fused BatchNorm reductions read the staged output tile");
 
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     long long dbg_acc[8] = {0, 0, 0, 0, 0, 0, 0, 0};
@@ -397,6 +411,7 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constant__
     const int n_blk = blockIdx.y;                 // N-slice (conv: half of Cout; up2: sub-position q)
     const uint32_t rank = (CG == 2) ? cluster_ctarank() : 0u;     // position half / weight-row half inside the CTA pair
     const bool leader = (rank == 0);
+    auto ch_off_of = [](int nb) { return (EPI == 1) ? 0 : nb * NOUT; };   // first output channel of this CTA's N-slice
     const int unit = blockIdx.x / CG, n_units = gridDim.x / CG;   // persistent work unit = CTA (CG 1) or CTA pair (CG 2)
     const int num_units_tiles = (p.num_m_tiles + CG - 1) / CG;    // tiles of CG*128 positions
 
@@ -537,6 +552,115 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constant__
         const uint32_t stage_o = s_o + (uint32_t)eset * (TC_BM * NOUT * 2);     // this set's staging tile (TMAST)
         const uint32_t wst = s_o + (uint32_t)(eset * 4 + lane_grp) * (32 * STC * 2);   // this warp's store patch (STC > 0)
         const int npos = (int)p.g.npos;
+        // fused BatchNorm reductions: every lane owns one channel PAIR of each staged fill (64 or 32 channels wide) and
+        // walks the rows its own warp staged; partial sums stay in registers for the whole kernel
+        constexpr int FW = TMAST ? 64 : (STC > 0 ? STC : 64);               // channels per staged fill
+        constexpr int NF = NOUT / FW;                                        // fills per tile
+        float bs1[NF][2], bs2[NF][2];
+#pragma unroll
+        for (int f = 0; f < NF; ++f) { bs1[f][0] = bs1[f][1] = bs2[f][0] = bs2[f][1] = 0.f; }
+        // BNS == 2: the pre-BatchNorm values y the lane needs for the fills of one 64-column round (32 rows x 1 channel
+        // pair when a fill is 64 channels wide, 2 fills x 16 rows x 1 pair when it is 32 wide) are fetched with 32
+        // INDEPENDENT loads issued before the round's TMEM loads, so one memory latency is paid per round, not per row
+        uint32_t ypre[(BNS == 2) ? 32 : 1];
+        auto bn_prefetch = [&](int cq, int tile) {
+            if constexpr (BNS == 2) {
+                constexpr int LPR = FW / 2;
+                const int cp = lane % LPR, rpar = lane / LPR;
+                const TOut* ybase = reinterpret_cast<const TOut*>(p.bn_y) +
+                                    (long long)(tile * TC_BM + lane_grp * 32) * p.bn_cs + ch_off_of(n_blk) + cq + 2 * cp;
+                const bool live = ch_off_of(n_blk) + cq < p.stats_nch;          // uniform per round (nch is a multiple of 64)
+#pragma unroll
+                for (int i = 0; i < 32; ++i) {
+                    // FW == 64: row i.  FW == 32: i < 16 -> first fill of the round, rows 2i+rpar; else second fill (+32 channels)
+                    const int r = (FW == 64) ? i : (2 * (i & 15) + rpar);
+                    const int coff = (FW == 64) ? 0 : ((i >> 4) * 32);
+                    ypre[i] = live ? __ldg(reinterpret_cast<const unsigned int*>(ybase + (long long)r * p.bn_cs + coff)) : 0u;
+                }
+            }
+        };
+        // column walk of one staged fill (fill_base = shared address of the first row this warp staged); yoff = index
+        // of the fill's first prefetched y word
+        auto bn_accumulate = [&](uint32_t fill_base, int f, int c_first, uint32_t vmask, int yoff) {
+            constexpr int ROWB = FW * 2;                                     // bytes per staged row
+            constexpr int LPR = FW / 2;                                      // lanes per row (one channel pair each)
+            constexpr int NR = LPR;                                          // rows per lane: 32 (FW=64) or 16 (FW=32)
+            const int cp = lane % LPR;                                       // channel pair inside the fill
+            const int rpar = lane / LPR;                                     // FW=32: row parity handled by this half-warp
+            const int cg = c_first + 2 * cp;                                  // first of the two output channels (CTA-local)
+            auto lds = [&](int r) {
+                const uint32_t sw = (FW == 64) ? (uint32_t)(r & 7) : (uint32_t)((r >> 1) & 3);
+                uint32_t w;
+                asm volatile("ld.shared.b32 %0, [%1];" : "=r"(w)
+                             : "r"(fill_base + (uint32_t)r * ROWB + ((((uint32_t)cp >> 2) ^ sw) << 4) + ((uint32_t)cp & 3u) * 4u));
+                return w;
+            };
+            if constexpr (BNS == 1) {
+                // forward statistics in FP32 (the variance is a difference of two sums: no 16-bit accumulation here)
+                float a1x = 0.f, a1y = 0.f, a2x = 0.f, a2y = 0.f;
+#pragma unroll
+                for (int i = 0; i < NR; ++i) {
+                    const int r = (FW == 64) ? i : (2 * i + rpar);          // warp-local row 0..31
+                    uint32_t w = lds(r);
+                    float2 v;
+                    if constexpr (std::is_same<TOut, __half>::value) v = __half22float2(*reinterpret_cast<__half2*>(&w));
+                    else v = __bfloat1622float2(*reinterpret_cast<__nv_bfloat162*>(&w));
+                    const float m = ((vmask >> r) & 1u) ? 1.f : 0.f;        // halo / out-of-range rows add nothing
+                    v.x *= m; v.y *= m;
+                    a1x += v.x; a1y += v.y; a2x = fmaf(v.x, v.x, a2x); a2y = fmaf(v.y, v.y, a2y);
+                }
+                bs1[f][0] += a1x; bs1[f][1] += a1y; bs2[f][0] += a2x; bs2[f][1] += a2y;
+            } else if constexpr (BNS == 2) {
+                // first BatchNorm-backward pass in packed 16-bit arithmetic (6 instructions per row and channel pair; the
+                // FP32 form made the epilogue the bottleneck of the kernel).  Per channel: the ReLU mask z > 0 becomes
+                // a threshold test on y (sgn*y > thr, thr rounded toward -inf so that the 16-bit test picks exactly the
+                // values the FP32 test picks), xhat = y*istd - mean*istd.  Row sums of one fill (<= 32 terms) are kept in
+                // 16 bits and widened to FP32 once per fill.
+                using T2 = typename std::conditional<std::is_same<TOut, __half>::value, __half2, __nv_bfloat162>::type;
+                if (ch_off_of(n_blk) + cg >= p.stats_nch) return;
+                const int c = ch_off_of(n_blk) + cg;
+                float thr[2], sg[2];
+#pragma unroll
+                for (int k = 0; k < 2; ++k) {
+                    const float scl = p.bn_scale[c + k], shf = p.bn_shift[c + k];
+                    sg[k] = scl < 0.f ? -1.f : 1.f;
+                    // scale == 0: the mask is the sign of the shift for every y
+                    thr[k] = scl != 0.f ? -shf / fabsf(scl) : (shf > 0.f ? -INFINITY : INFINITY);
+                }
+                T2 sgn2, thr2, is2, nm2;
+                const float i0 = p.bn_istd[c], i1 = p.bn_istd[c + 1];
+                if constexpr (std::is_same<TOut, __half>::value) {
+                    sgn2 = __floats2half2_rn(sg[0], sg[1]);
+                    thr2 = __halves2half2(__float2half_rd(thr[0]), __float2half_rd(thr[1]));
+                    is2 = __floats2half2_rn(i0, i1);
+                    nm2 = __floats2half2_rn(-p.bn_mean[c] * i0, -p.bn_mean[c + 1] * i1);
+                } else {
+                    sgn2 = __floats2bfloat162_rn(sg[0], sg[1]);
+                    thr2 = __halves2bfloat162(__float2bfloat16_rd(thr[0]), __float2bfloat16_rd(thr[1]));
+                    is2 = __floats2bfloat162_rn(i0, i1);
+                    nm2 = __floats2bfloat162_rn(-p.bn_mean[c] * i0, -p.bn_mean[c + 1] * i1);
+                }
+                T2 s1, s2;
+                if constexpr (std::is_same<TOut, __half>::value) { s1 = __float2half2_rn(0.f); s2 = s1; }
+                else { s1 = __float2bfloat162_rn(0.f); s2 = s1; }
+#pragma unroll
+                for (int i = 0; i < NR; ++i) {
+                    const int r = (FW == 64) ? i : (2 * i + rpar);
+                    uint32_t w = lds(r);
+                    if (!((vmask >> r) & 1u)) w = 0u;                         // halo / out-of-range rows add nothing
+                    uint32_t yw = ypre[yoff + i];
+                    const T2 v = *reinterpret_cast<T2*>(&w), y = *reinterpret_cast<T2*>(&yw);
+                    const T2 mk = __hgt2(__hmul2(y, sgn2), thr2);            // 1.0 where relu'(z) = 1
+                    const T2 g = __hmul2(v, mk);
+                    s1 = __hadd2(s1, g);
+                    s2 = __hfma2(g, __hfma2(y, is2, nm2), s2);
+                }
+                float2 f1, f2;
+                if constexpr (std::is_same<TOut, __half>::value) { f1 = __half22float2(s1); f2 = __half22float2(s2); }
+                else { f1 = __bfloat1622float2(s1); f2 = __bfloat1622float2(s2); }
+                bs1[f][0] += f1.x; bs1[f][1] += f1.y; bs2[f][0] += f2.x; bs2[f][1] += f2.y;
+            }
+        };
         for (int seq = eset, ut = unit + eset * n_units; ut < num_units_tiles; seq += 2, ut += 2 * n_units) {
             const int buf = seq % ACC_BUFS;
             const uint32_t acc_phase = (uint32_t)(seq / ACC_BUFS) & 1u;
@@ -555,6 +679,7 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constant__
             }
             const int oidx = valid ? (int)opos : -1;          // output row of this thread's position (staged stores)
             long long t0 = p.dbg ? clock64() : 0;
+            bn_prefetch(0, tile);                      // in flight while this warp waits for the accumulator
             mbar_wait(bar_accfull(buf), acc_phase);
             long long t1 = p.dbg ? clock64() : 0;
             if (p.dbg) dbg_acc[4] += t1 - t0;
@@ -571,6 +696,7 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constant__
 #pragma unroll
             for (int cq = 0; cq < NOUT; cq += 64) {
                 uint32_t racc[4][16];
+                if (cq > 0) bn_prefetch(cq, tile);
 #pragma unroll
                 for (int q = 0; q < 4; ++q) tmem_ld16(taddr + cq + q * 16, racc[q]);
                 tmem_ld_wait();
@@ -639,6 +765,7 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constant__
                             // patch complete: CPR lanes per row write one contiguous row segment each
                             __syncwarp();
                             const int c_lo = cb + 16 - STCX;                      // first channel held by the patch
+                            if (BNS) bn_accumulate(wst, c_lo / STCX, c_lo, __ballot_sync(0xffffffffu, valid), (STCX == 32) ? ((c_lo & 32) >> 1) : 0);
                             const uint32_t cj = (uint32_t)lane % CPR;
 #pragma unroll
                             for (int it = 0; it < CPR; ++it) {
@@ -669,6 +796,13 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constant__
                 if (p.final_clamp) xn = fminf(fmaxf(xn, -1.f), 1.f);
                 p.x[pix] = xn;
             }
+            if (TMAST && BNS) {
+                __syncwarp();                        // rows of this warp are staged by its own lanes
+                const uint32_t vm = __ballot_sync(0xffffffffu, valid);
+#pragma unroll
+                for (int f = 0; f < NF; ++f)
+                    bn_accumulate(stage_o + (uint32_t)f * (TC_BM * 128) + (uint32_t)(lane_grp * 32) * 128, f, f * 64, vm, 0);
+            }
             if (TMAST) {
                 fence_proxy_async();                 // generic-proxy smem writes -> visible to the TMA engine
                 named_bar_sync(1 + eset, 128);
@@ -680,6 +814,41 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constant__
                 }
             }
             if (p.dbg) { dbg_acc[5] += clock64() - t1; dbg_acc[6] += 1; }
+        }
+        if (BNS) {
+            // block-level reduction of the per-lane partials through the (now idle) staging area, then one Float64
+            // atomic per (quantity, channel) and CTA
+            if (TMAST && store_thread) tma_store_wait_all();          // the TMA engine has finished reading this set's tile
+            named_bar_sync(3, 256);                                   // both epilogue sets are done with their tiles
+            float* red = reinterpret_cast<float*>(smem + W_BYTES + STAGES * A_STAGE_BYTES);     // [8 warps][2][NOUT]
+            const int ew = eset * 4 + lane_grp;
+            constexpr int LPR = FW / 2;
+#pragma unroll
+            for (int f = 0; f < NF; ++f) {
+#pragma unroll
+                for (int j = 0; j < 2; ++j) {
+                    float a = bs1[f][j], b = bs2[f][j];
+                    if (FW == 32) {                                   // the two half-warps hold the two row parities
+                        a += __shfl_xor_sync(0xffffffffu, a, 16);
+                        b += __shfl_xor_sync(0xffffffffu, b, 16);
+                    }
+                    if (lane < LPR) {
+                        const int c = f * FW + 2 * (lane % LPR) + j;
+                        red[(ew * 2 + 0) * NOUT + c] = a;
+                        red[(ew * 2 + 1) * NOUT + c] = b;
+                    }
+                }
+            }
+            named_bar_sync(3, 256);
+            const int et = eset * 128 + lane_grp * 32 + lane;         // 0..255
+            for (int i = et; i < 2 * NOUT; i += 256) {
+                const int q = i / NOUT, c = i - q * NOUT;
+                float acc = 0.f;
+#pragma unroll
+                for (int w8 = 0; w8 < 8; ++w8) acc += red[(w8 * 2 + q) * NOUT + c];
+                const int cgl = ch_off_of(n_blk) + c;
+                if (BNS == 1 || cgl < p.stats_nch) atomicAdd(p.stats + (size_t)q * p.stats_C + cgl, (double)acc);
+            }
         }
     }
     if (TMAST && (threadIdx.x == 64 || threadIdx.x == 224)) tma_store_wait_all();
@@ -792,7 +961,7 @@ CUtensorMap make_map_2d(const void* base, uint64_t rows, uint64_t cols, uint32_t
     return m;
 }
 
-template <int TAPS, int CHUNKS, int NOUT, int WP, int EPI, int TMAST, typename TIn, typename TOut, int CG = 1>
+template <int TAPS, int CHUNKS, int NOUT, int WP, int EPI, int TMAST, typename TIn, typename TOut, int CG = 1, int BNS = 0>
 void launch(cudaStream_t st, const CUtensorMap& a0, const CUtensorMap& a1, const CUtensorMap& w, const CUtensorMap& o,
             const TcParams& p, int n_blocks_y) {
     constexpr int STAGES = pick_stages<TAPS, CHUNKS, NOUT, WP, EPI, TMAST, CG>();
@@ -803,7 +972,7 @@ void launch(cudaStream_t st, const CUtensorMap& a0, const CUtensorMap& a1, const
                             (size_t)epi_smem_bytes<TAPS, CHUNKS, NOUT, WP, EPI, TMAST, CG>() + 1280;
     DDPM_CHECK(p.g.Wp == WP && p.g.Hs == WP - 1 && p.g.npos + 2 * TC_BM < (1ll << 31),
                "conv_tc: geometry does not match the kernel's compile-time row width");
-    auto kern = conv_tc_kernel<TAPS, CHUNKS, NOUT, WP, STAGES, EPI, TMAST, CG, TIn, TOut>;
+    auto kern = conv_tc_kernel<TAPS, CHUNKS, NOUT, WP, STAGES, EPI, TMAST, CG, BNS, TIn, TOut>;
     ensure_smem_attr(kern, smem);
     int ctas_x = state().num_sms / n_blocks_y;
     if (ctas_x > p.num_m_tiles) ctas_x = p.num_m_tiles;
@@ -854,11 +1023,25 @@ void launch(cudaStream_t st, const CUtensorMap& a0, const CUtensorMap& a1, const
     DDPM_LAUNCH_CHECK();
 }
 
+// Optional BatchNorm reductions fused into the epilogue of conv3x3 (see TcParams::stats).
+struct BnFuse {
+    int mode = 0;                 // 0 none, 1 forward statistics (sum y, sum y^2), 2 backward pass 1 (sum g, sum g*xhat)
+    double* sums = nullptr;       // [2][C]
+    int C = 0;                    // channels of the statistics vectors
+    int nch = 0;                  // mode 2: output channels [0, nch) carry the BatchNorm
+    const void* y = nullptr;      // mode 2: pre-BatchNorm tensor (position 0), y_cs channels per position
+    int y_cs = 0;
+    const float *scale = nullptr, *shift = nullptr, *mean = nullptr, *istd = nullptr;
+};
+
 // Conv((3,3), C0+C1 => Cout, pad=1) on the padded layout.  src pointers are POSITION 0 pointers;
 // the tensor maps are based at the allocation start (position -guard).
+// bn: reductions to fuse into the epilogue; *bn_done tells the caller whether the launched variant did them (only the
+// default CTA-pair variants carry the fused code; otherwise the caller runs the stand-alone reduction kernel).
 template <typename TIn, typename TOut>
 bool conv3x3(cudaStream_t st, const TIn* s0, int C0, const TIn* s1, int C1, const TIn* Wt, int Cout, TOut* out,
-             const Geo& g, const float* shift, int relu) {
+             const Geo& g, const float* shift, int relu, const BnFuse* bn = nullptr, bool* bn_done = nullptr) {
+    if (bn_done) *bn_done = false;
     if (!available()) return false;
     if constexpr (sizeof(TIn) != 2 || sizeof(TOut) != 2) {
         return false;
@@ -871,6 +1054,12 @@ bool conv3x3(cudaStream_t st, const TIn* s0, int C0, const TIn* s1, int C1, cons
     p.num_m_tiles = cdiv(g.npos, TC_BM);
     p.chunk1_src1 = (s1 != nullptr) ? 1 : 0;
     p.dbg = state().dbg;
+    const int bm = (bn && bn->mode && !p.dbg) ? bn->mode : 0;
+    if (bm) {
+        p.stats = bn->sums; p.stats_C = bn->C; p.stats_nch = bn->nch; p.bn_y = bn->y; p.bn_cs = bn->y_cs;
+        p.bn_scale = bn->scale; p.bn_shift = bn->shift; p.bn_mean = bn->mean; p.bn_istd = bn->istd;
+    }
+    auto done = [&]() { if (bn_done) *bn_done = true; };
     const TIn* base0 = s0 - (size_t)g.guard * C0;
     constexpr int R32 = ((TC_BM + 2 * 35 + 7) / 8) * 8, R16 = ((TC_BM + 2 * 19 + 7) / 8) * 8;
     CUtensorMap a0 = make_map_2d<TIn>(base0, rows, C0, WP == 34 ? R32 : R16);
@@ -880,22 +1069,29 @@ bool conv3x3(cudaStream_t st, const TIn* s0, int C0, const TIn* s1, int C1, cons
         const bool pair = (state().pair_mask & 2) != 0;
         CUtensorMap w = make_map_2d<TIn>(Wt, 64, 9 * 64, pair ? 32 : 64);
         CUtensorMap o = make_map_2d<TOut>(out - (size_t)g.guard * Cout, rows, Cout, TC_BM);
-        if (pair) launch<9, 1, 64, 34, 0, 1, TIn, TOut, 2>(st, a0, a1, w, o, p, 1);
+        if (pair && bm == 1) { launch<9, 1, 64, 34, 0, 1, TIn, TOut, 2, 1>(st, a0, a1, w, o, p, 1); done(); }
+        else if (pair && bm == 2) { launch<9, 1, 64, 34, 0, 1, TIn, TOut, 2, 2>(st, a0, a1, w, o, p, 1); done(); }
+        else if (pair) launch<9, 1, 64, 34, 0, 1, TIn, TOut, 2>(st, a0, a1, w, o, p, 1);
         else if (state().tma_store) launch<9, 1, 64, 34, 0, 1, TIn, TOut>(st, a0, a1, w, o, p, 1);
         else launch<9, 1, 64, 34, 0, 0, TIn, TOut>(st, a0, a1, w, o, p, 1);
     } else if (WP == 34 && Cin == 128 && Cout == 64) {
         const bool pair = (state().pair_mask & 4) != 0;
         CUtensorMap w = make_map_2d<TIn>(Wt, 64, 9 * 128, pair ? 32 : 64);
-        if (pair) launch<9, 2, 64, 34, 0, 0, TIn, TOut, 2>(st, a0, a1, w, a0, p, 1);
+        if (pair && bm == 1) { launch<9, 2, 64, 34, 0, 0, TIn, TOut, 2, 1>(st, a0, a1, w, a0, p, 1); done(); }
+        else if (pair) launch<9, 2, 64, 34, 0, 0, TIn, TOut, 2>(st, a0, a1, w, a0, p, 1);
         else launch<9, 2, 64, 34, 0, 0, TIn, TOut>(st, a0, a1, w, a0, p, 1);
     } else if (WP == 18 && Cin == 64 && Cout == 128 && !s1) {
         const bool pair = (state().pair_mask & 8) != 0;
         CUtensorMap w = make_map_2d<TIn>(Wt, 128, 9 * 64, pair ? 64 : 128);
-        if (pair) launch<9, 1, 128, 18, 0, 0, TIn, TOut, 2>(st, a0, a1, w, a0, p, 1);
+        if (pair && bm == 1) { launch<9, 1, 128, 18, 0, 0, TIn, TOut, 2, 1>(st, a0, a1, w, a0, p, 1); done(); }
+        else if (pair) launch<9, 1, 128, 18, 0, 0, TIn, TOut, 2>(st, a0, a1, w, a0, p, 1);
         else launch<9, 1, 128, 18, 0, 0, TIn, TOut>(st, a0, a1, w, a0, p, 1);
     } else if (WP == 18 && Cin == 128 && Cout == 128 && !s1) {
         CUtensorMap w = make_map_2d<TIn>(Wt, 128, 9 * 128, 64);
-        if (state().pair_mask & 1)
+        const bool pair = (state().pair_mask & 1) != 0;
+        if (pair && bm == 1) { launch<9, 2, 128, 18, 0, 0, TIn, TOut, 2, 1>(st, a0, a1, w, a0, p, 1); done(); }
+        else if (pair && bm == 2) { launch<9, 2, 128, 18, 0, 0, TIn, TOut, 2, 2>(st, a0, a1, w, a0, p, 1); done(); }
+        else if (pair)
             launch<9, 2, 128, 18, 0, 0, TIn, TOut, 2>(st, a0, a1, w, a0, p, 1);  // CTA pair: each CTA stages 64 of the 128 weight rows
         else
             launch<9, 2, 64, 18, 0, 0, TIn, TOut>(st, a0, a1, w, a0, p, 2);      // Cout split over blockIdx.y so the weights fit
@@ -907,7 +1103,8 @@ bool conv3x3(cudaStream_t st, const TIn* s0, int C0, const TIn* s1, int C1, cons
     } else if (WP == 34 && Cin == 64 && Cout == 128 && !s1) {
         const bool pair = (state().pair_mask & 16) != 0;
         CUtensorMap w = make_map_2d<TIn>(Wt, 128, 9 * 64, pair ? 64 : 128);        // dgrad of up1.conv1 (d cat)
-        if (pair) launch<9, 1, 128, 34, 0, 0, TIn, TOut, 2>(st, a0, a1, w, a0, p, 1);
+        if (pair && bm == 2) { launch<9, 1, 128, 34, 0, 0, TIn, TOut, 2, 2>(st, a0, a1, w, a0, p, 1); done(); }
+        else if (pair) launch<9, 1, 128, 34, 0, 0, TIn, TOut, 2>(st, a0, a1, w, a0, p, 1);
         else launch<9, 1, 128, 34, 0, 0, TIn, TOut>(st, a0, a1, w, a0, p, 1);
     } else {
         return false;
@@ -964,7 +1161,9 @@ bool up2(cudaStream_t st, const TA* a6, const TA* Wt, TA* u, const Geo& gi, cons
 // out[pos][N=128] = A[pos][K=256] * Wt[n][k]^T over the valid positions of g (ConvTranspose data gradient
 // on the pixel-un-shuffled gradient): the conv kernel with one tap and four 64-channel K chunks.
 template <typename T>
-bool gemm_rows(cudaStream_t st, const T* a, int K, const T* Wt, int Nout, T* out, const Geo& g) {
+bool gemm_rows(cudaStream_t st, const T* a, int K, const T* Wt, int Nout, T* out, const Geo& g, const BnFuse* bn = nullptr,
+               bool* bn_done = nullptr) {
+    if (bn_done) *bn_done = false;
     if (!available()) return false;
     if constexpr (sizeof(T) != 2) {
         return false;
@@ -977,7 +1176,14 @@ bool gemm_rows(cudaStream_t st, const T* a, int K, const T* Wt, int Nout, T* out
     p.dbg = nullptr;
     CUtensorMap a0 = make_map_2d<T>(a - (size_t)g.guard * K, (uint64_t)g.alloc_positions(), K, TC_BM);
     CUtensorMap w = make_map_2d<T>(Wt, Nout, K, 128);
-    launch<1, 4, 128, 18, 0, 0, T, T>(st, a0, a0, w, a0, p, 1);
+    if (bn && bn->mode == 2) {
+        p.stats = bn->sums; p.stats_C = bn->C; p.stats_nch = bn->nch; p.bn_y = bn->y; p.bn_cs = bn->y_cs;
+        p.bn_scale = bn->scale; p.bn_shift = bn->shift; p.bn_mean = bn->mean; p.bn_istd = bn->istd;
+        launch<1, 4, 128, 18, 0, 0, T, T, 1, 2>(st, a0, a0, w, a0, p, 1);
+        if (bn_done) *bn_done = true;
+    } else {
+        launch<1, 4, 128, 18, 0, 0, T, T>(st, a0, a0, w, a0, p, 1);
+    }
     return true;
     }
 }

@@ -16,6 +16,7 @@
 #include "igemm_simt.cuh"
 #include "conv_tc.cuh"
 #include "conv1_tc.cuh"
+#include "l1_bwd.cuh"
 
 namespace ddpm {
 
@@ -140,7 +141,7 @@ struct ActSet {
     // training only: device staging of one step's inputs (host batches or dataset indices), q_sample output, loss
     // gradient and the first layer's backward scratch -- owned by the set so that a captured step never sees a
     // re-allocated pointer
-    DevBuf x0, eps, ts, idx, xt, deps, Tw, Ccls, S;
+    DevBuf x0, eps, ts, idx, xt, deps, Ccls, S;
     // captured training iterations, keyed by gather*2 + update (the first call of a key runs eagerly and warms every
     // lazily initialised resource, the second one is captured, later ones replay)
     std::map<int, GraphEntry> train_graphs;
@@ -215,6 +216,7 @@ struct Engine {
     double* sums = nullptr;       // [NUM_CONV+1][3*128] forward (sum, sumsq) / backward (g, g*xhat, dy)
     double* sums_g = nullptr;     // all-reduced copies (SyncBN)
     double* misc_sums = nullptr;  // [0]=loss, [8..72]=dwf, [72]=dbf, [128..192]=dbT
+    double* l1_acc = nullptr;     // [576] image-channel weight gradient of the first conv, summed over the batch
 
     // activation sets: a two-entry cache of training sets (an epoch of the reference alternates 64- and 52-image
     // batches, train_brain.jl:201-202) and a small cache of inference sets, both keyed by batch size
@@ -237,6 +239,7 @@ struct Engine {
     // images per captured reverse-loop graph.  1300 images fill the persistent conv kernels' tile rounds exactly
     // (32x32 layers: 77.0 rounds of 74 CTA-pair tiles, 16x16 layers: 21.0) -- 512 left the 16x16 layers at 92 %
     long long opt_sample_chunk = 1300, opt_use_graph = 1, opt_conv_impl = 0 /*0 auto, 1 simt, 2 tc*/, opt_fuse_final = 1;
+    long long opt_fuse_bn = 1;              // BatchNorm reductions inside the tcgen05 conv / data-gradient epilogues
     long long opt_train_graph = 1;          // replay the training iteration from a CUDA graph (per set and step kind)
     long long cnt_launches = 0;
 
@@ -274,7 +277,8 @@ struct Engine {
     void conv3(const Tensor& s0, const Tensor* s1, int l, Tensor& out, bool infer_weights, const float* shift, int relu,
                double* stats);
     template <typename TA, typename TG>
-    void dgrad3(const Tensor& dy, int l, Tensor& out, int out_c_total);
+    void dgrad3(ActSet& s, const Tensor& dy, int l, Tensor& out, int out_c_total, int bn_layer = 0, bool* bn_done = nullptr);
+    tc::BnFuse bn_bwd_fuse(ActSet& s, int bn_layer);
     template <typename TA, typename TG> void forward_t(ActSet& s, const float* x_dev, const int* ts_dev, int t_fixed, Mode mode, bool update_running,
                                                        bool skip_last = false);
     void forward(ActSet& s, const float* x_dev, const int* ts_dev, int t_fixed, Mode mode, bool update_running);
@@ -361,6 +365,7 @@ inline Engine::Engine(int T_, int D_, int H_, int W_, int prec_, int dev_)
     DDPM_CUDA(cudaMalloc(&sums, sizeof(double) * 384 * (NUM_CONV + 1)));
     DDPM_CUDA(cudaMalloc(&sums_g, sizeof(double) * 384 * (NUM_CONV + 1)));
     DDPM_CUDA(cudaMalloc(&misc_sums, sizeof(double) * 256));
+    DDPM_CUDA(cudaMalloc(&l1_acc, sizeof(double) * 576));
     DDPM_CUDA(cudaMalloc(&d_rng, 2 * sizeof(unsigned long long)));
     DDPM_CUDA(cudaMalloc(&d_trng, 4 * sizeof(unsigned long long)));
     DDPM_CUDA(cudaMalloc(&d_tstate, sizeof(TrainState)));
@@ -401,7 +406,7 @@ inline Engine::~Engine() {
         for (float* p : v) cudaFree(p);
         cudaFree(Wf[l]); cudaFree(Wd[l]); cudaFree(Wfi[l]);
     }
-    cudaFree(Wt); cudaFree(Wtd); cudaFree(sums); cudaFree(sums_g); cudaFree(misc_sums); cudaFree(d_rng); cudaFree(d_tstate);
+    cudaFree(Wt); cudaFree(Wtd); cudaFree(sums); cudaFree(sums_g); cudaFree(misc_sums); cudaFree(l1_acc); cudaFree(d_rng); cudaFree(d_tstate);
     wg.release();
     cudaFree(d_trng);
     DevBuf* bufs[] = {&d_x0, &d_eps, &d_xt, &d_ts, &d_dataset, &d_sample_out, &d_u8};
@@ -479,7 +484,7 @@ inline void Engine::free_set(ActSet& s) {
     s.drop_graphs();
     for (void* p : s.owned) cudaFree(p);
     s.owned.clear();
-    DevBuf* bufs[] = {&s.x, &s.eps_hat, &s.z, &s.zstep, &s.rng, &s.x0, &s.eps, &s.ts, &s.idx, &s.xt, &s.deps, &s.Tw, &s.Ccls, &s.S};
+    DevBuf* bufs[] = {&s.x, &s.eps_hat, &s.z, &s.zstep, &s.rng, &s.x0, &s.eps, &s.ts, &s.idx, &s.xt, &s.deps, &s.Ccls, &s.S};
     for (DevBuf* b : bufs) b->release();
     s = ActSet();
 }
@@ -518,7 +523,7 @@ inline void Engine::build_set(ActSet& s, int N, bool training) {
         const size_t img = (size_t)N * HW * 4;
         s.x0.ensure(img); s.eps.ensure(img); s.xt.ensure(img); s.deps.ensure(img);
         s.ts.ensure((size_t)N * 4); s.idx.ensure((size_t)N * 4);
-        s.Tw.ensure((size_t)N * 576 * 4); s.Ccls.ensure((size_t)N * 576 * 4); s.S.ensure((size_t)N * 576 * 4);
+        s.Ccls.ensure((size_t)N * 576 * 4); s.S.ensure((size_t)N * 576 * 4);
         if (use_tc()) tc::wg_reserve(wg);          // no allocation may happen inside a captured step
     }
 }
@@ -644,13 +649,16 @@ void Engine::conv3(const Tensor& s0, const Tensor* s1, int l, Tensor& out, bool 
     int C0 = s0.C, C1 = s1 ? s1->C : 0;
     DDPM_CHECK(C0 + C1 == c.cin && out.C == c.cout, "conv3: channel mismatch");
     if (use_tc()) {
+        // train-mode BatchNorm statistics of the stored (rounded) y: fused into the conv epilogue when the launched
+        // variant supports it, otherwise one streaming reduction over y
+        tc::BnFuse bf{};
+        bf.mode = (stats && opt_fuse_bn) ? 1 : 0; bf.sums = stats; bf.C = c.cout;
+        bool fused = false;
         bool ok = tc::conv3x3<TA, TA>(stream, s0.pos0<TA>(), C0, s1 ? s1->pos0<TA>() : nullptr, C1, (const TA*)weights, c.cout,
-                                     out.pos0<TA>(), g, shift, relu);
+                                      out.pos0<TA>(), g, shift, relu, &bf, &fused);
         if (ok) {
             cnt_launches += 1;
-            if (stats) {  // train-mode BatchNorm statistics of the stored (rounded) y
-                long long pixels = (long long)g.N * g.H * g.W;
-                (void)pixels;
+            if (stats && !fused) {
                 bn_reduce_linear_kernel<TA, TA, 0><<<lin_reduce_blocks(g.npos, tc::state().num_sms), 256, 0, stream>>>(
                     out.cview<TA>(), out.cview<TA>(), g.npos, c.cout, nullptr, nullptr, nullptr, nullptr, stats);
                 DDPM_LAUNCH_CHECK();
@@ -666,15 +674,32 @@ void Engine::conv3(const Tensor& s0, const Tensor* s1, int l, Tensor& out, bool 
     cnt_launches += 1;
 }
 
+// parameters of the first BatchNorm-backward pass of layer `bn_layer` for the kernel that PRODUCES its input gradient
+// da = dL/d(a_l):  sum g, sum g*xhat over the tile it just wrote (see tc::TcParams::stats)
+inline tc::BnFuse Engine::bn_bwd_fuse(ActSet& s, int bn_layer) {
+    tc::BnFuse bf{};
+    const ConvSpec& b = kConv[bn_layer];
+    bf.mode = 2; bf.sums = lsum(bn_layer); bf.C = b.cout; bf.nch = b.cout;
+    bf.y = s.y[bn_layer].base ? (const char*)s.y[bn_layer].base + (size_t)s.y[bn_layer].g.guard * b.cout * s.y[bn_layer].esz : nullptr;
+    bf.y_cs = b.cout;
+    bf.scale = tr_scale[bn_layer]; bf.shift = tr_shift[bn_layer]; bf.mean = tr_mean[bn_layer]; bf.istd = tr_istd[bn_layer];
+    return bf;
+}
+
 // data gradient of layer l: out[p][ci] = sum_tap sum_co dy[p - shift(tap)][co] * W[co][tap][ci]
+// bn_layer != 0: `out` (its first cout(bn_layer) channels) is the gradient w.r.t. the BatchNorm-ReLU output of that
+// layer; the epilogue then also accumulates the first pass of that BatchNorm's backward (*bn_done reports it).
 template <typename TA, typename TG>
-void Engine::dgrad3(const Tensor& dy, int l, Tensor& out, int out_c_total) {
+void Engine::dgrad3(ActSet& s, const Tensor& dy, int l, Tensor& out, int out_c_total, int bn_layer, bool* bn_done) {
     const ConvSpec& c = kConv[l];
     const Geo& g = out.g;
+    if (bn_done) *bn_done = false;
     DDPM_CHECK(dy.C == c.cout && out.C == out_c_total && out_c_total == c.cin, "dgrad3: channel mismatch");
     if (use_tc()) {
+        tc::BnFuse bf{};
+        if (bn_layer && opt_fuse_bn) bf = bn_bwd_fuse(s, bn_layer);
         bool ok = tc::conv3x3<TG, TG>(stream, dy.pos0<TG>(), c.cout, nullptr, 0, (const TG*)Wd[l], c.cin, out.pos0<TG>(), g,
-                                     nullptr, 0);
+                                     nullptr, 0, &bf, bn_done);
         if (ok) {
             cnt_launches += 1;
             return;
@@ -811,14 +836,18 @@ void Engine::backward_t(ActSet& s, const float* xt_dev, const int* ts_dev, const
     const double count_local = (double)N;
 
     // BatchNorm(relu) backward of layer l: da (view) -> dy tensor
-    auto bn_bwd = [&](int l, View<const TG> da, Tensor& dy) {
+    // have_sums: the kernel that produced da already accumulated sum g, sum g*xhat into lsum(l) (fused epilogue)
+    auto bn_bwd = [&](int l, View<const TG> da, Tensor& dy, bool have_sums) {
         const ConvSpec& c = kConv[l];
         const Geo& g = s.y[l].g;
         long long pixels = (long long)N * c.hw * c.hw;
         int blocks = stride_blocks(pixels, BNB_PIX_PER_BLOCK, tc::state().num_sms, 3);
         double m = count_local * c.hw * c.hw;
-        bn_reduce_linear_kernel<TA, TG, 1><<<lin_reduce_blocks(g.npos, tc::state().num_sms), 256, 0, stream>>>(
-            s.y[l].cview<TA>(), da, g.npos, c.cout, tr_scale[l], tr_shift[l], tr_mean[l], tr_istd[l], lsum(l));
+        if (!have_sums) {
+            bn_reduce_linear_kernel<TA, TG, 1><<<lin_reduce_blocks(g.npos, tc::state().num_sms), 256, 0, stream>>>(
+                s.y[l].cview<TA>(), da, g.npos, c.cout, tr_scale[l], tr_shift[l], tr_mean[l], tr_istd[l], lsum(l));
+            cnt_launches += 1;
+        }
         if (sync_bn && comm) {
             allreduce_sums(lsum(l), gsum(l), 2 * c.cout);
             m *= world;
@@ -829,7 +858,7 @@ void Engine::backward_t(ActSet& s, const float* xt_dev, const int* ts_dev, const
                                                              tr_shift[l], tr_mean[l], tr_istd[l], bw_mg[l], bw_mgx[l], lsum(l));
         f64_to_f32_kernel<<<1, 128, 0, stream>>>(lsum(l) + 2 * c.cout, garr(c.b), c.cout, (double)alpha);
         DDPM_LAUNCH_CHECK();
-        cnt_launches += 4;
+        cnt_launches += 3;
     };
     // weight gradient of a 3x3 conv: dW[co][tap][ci] = sum_p dy[p][co] * x[p + shift(tap)][ci]
     auto wgrad = [&](int l, const Tensor& dy, const Tensor& x, int ci_off) {
@@ -849,31 +878,37 @@ void Engine::backward_t(ActSet& s, const float* xt_dev, const int* ts_dev, const
     // memset the sums used by the backward (forward sums are no longer needed)
     DDPM_CUDA(cudaMemsetAsync(sums, 0, sizeof(double) * 384 * (NUM_CONV + 1), stream));
 
+    // f<l>: the kernel that produced d(a_l) also accumulated the first BatchNorm-backward pass of layer l.  Layers 10 and 2
+    // get their input gradient from HBM-bound elementwise kernels (final conv backward, pool/skip merge): fusing the
+    // reduction there made those kernels latency-bound (measured 122 -> 275 us and 156 -> 376 us at B = 2048), so they
+    // keep the streaming reduction kernel.
+    const bool fz = use_tc() && opt_fuse_bn && sizeof(TA) == 2;
+    bool f10 = false, f9 = false, f8 = false, f7 = false, f6 = false, f5 = false, f4 = false, f3 = false, f2 = false, f1 = false;
     // ---- final 1x1 conv
     {
         long long pixels = (long long)N * HW;
-        final_bwd_kernel<TA, TG><<<stride_blocks(pixels, FINAL_BWD_PIX_PER_BLOCK, tc::state().num_sms, 4), 256, 0, stream>>>(s.a[10].cview<TA>(), s.g32a.view<TG>(), s.a[10].g,
-                                                                      arr(kFinalW), deps_dev, misc_sums + 8);
+        final_bwd_kernel<TA, TG><<<stride_blocks(pixels, FINAL_BWD_PIX_PER_BLOCK, tc::state().num_sms, 4), 256, 0, stream>>>(
+            s.a[10].cview<TA>(), s.g32a.view<TG>(), s.a[10].g, arr(kFinalW), deps_dev, misc_sums + 8);
         f64_to_f32_kernel<<<1, 128, 0, stream>>>(misc_sums + 8, garr(kFinalW), 64, (double)alpha);
         f64_to_f32_kernel<<<1, 32, 0, stream>>>(misc_sums + 72, garr(kFinalB), 1, (double)alpha);
         DDPM_LAUNCH_CHECK();
         cnt_launches += 3;
     }
     // ---- up1
-    bn_bwd(10, s.g32a.cview<TG>(), s.g32b);
+    bn_bwd(10, s.g32a.cview<TG>(), s.g32b, f10);
     wgrad(10, s.g32b, s.a[9], 0);
-    dgrad3<TA, TG>(s.g32b, 10, s.g32a, 64);
-    bn_bwd(9, s.g32a.cview<TG>(), s.g32b);
+    dgrad3<TA, TG>(s, s.g32b, 10, s.g32a, 64, 9, &f9);
+    bn_bwd(9, s.g32a.cview<TG>(), s.g32b, f9);
     wgrad(9, s.g32b, s.a[8], 0);
     wgrad(9, s.g32b, s.a[2], 64);
-    dgrad3<TA, TG>(s.g32b, 9, s.gcat, 128);
+    dgrad3<TA, TG>(s, s.g32b, 9, s.gcat, 128, 8, &f8);      // d(cat): channels 0..63 = d(a8), 64..127 = skip half of d(h1)
     // ---- up2
-    bn_bwd(8, s.gcat.cview<TG>(0), s.g32b);
+    bn_bwd(8, s.gcat.cview<TG>(0), s.g32b, f8);
     wgrad(8, s.g32b, s.a[7], 0);
-    dgrad3<TA, TG>(s.g32b, 8, s.g32a, 64);
-    bn_bwd(7, s.g32a.cview<TG>(), s.g32b);
+    dgrad3<TA, TG>(s, s.g32b, 8, s.g32a, 64, 7, &f7);
+    bn_bwd(7, s.g32a.cview<TG>(), s.g32b, f7);
     wgrad(7, s.g32b, s.u, 0);
-    dgrad3<TA, TG>(s.g32b, 7, s.g32a, 64);  // g32a = d(u)
+    dgrad3<TA, TG>(s, s.g32b, 7, s.g32a, 64);  // g32a = d(u)
     {   // ConvTranspose backward
         const Geo& gi = s.a[6].g;
         const Geo& go = s.u.g;
@@ -885,7 +920,9 @@ void Engine::backward_t(ActSet& s, const float* xt_dev, const int* ts_dev, const
         if (use_tc()) {
             long long work = (long long)N * 16 * 16 * 4 * 8;
             unshuffle2_kernel<TG><<<cdiv(work, 256), 256, 0, stream>>>(s.g32a.cview<TG>(), s.gdu4.view<TG>(), go, gi, 64);
-            done = tc::gemm_rows<TG>(stream, s.gdu4.pos0<TG>(), 256, (const TG*)Wtd, 128, s.g16a.pos0<TG>(), gi);
+            tc::BnFuse bf{};
+            if (fz) bf = bn_bwd_fuse(s, 6);
+            done = tc::gemm_rows<TG>(stream, s.gdu4.pos0<TG>(), 256, (const TG*)Wtd, 128, s.g16a.pos0<TG>(), gi, &bf, &f6);
             cnt_launches += 1;
         }
         if (!done) {
@@ -913,18 +950,18 @@ void Engine::backward_t(ActSet& s, const float* xt_dev, const int* ts_dev, const
                                       comm, comm_stream), "ncclAllReduce(grad bucket 0)");
     }
     // ---- mid, down2
-    bn_bwd(6, s.g16a.cview<TG>(), s.g16b);
+    bn_bwd(6, s.g16a.cview<TG>(), s.g16b, f6);
     wgrad(6, s.g16b, s.a[5], 0);
-    dgrad3<TA, TG>(s.g16b, 6, s.g16a, 128);
-    bn_bwd(5, s.g16a.cview<TG>(), s.g16b);
+    dgrad3<TA, TG>(s, s.g16b, 6, s.g16a, 128, 5, &f5);
+    bn_bwd(5, s.g16a.cview<TG>(), s.g16b, f5);
     wgrad(5, s.g16b, s.a[4], 0);
-    dgrad3<TA, TG>(s.g16b, 5, s.g16a, 128);
-    bn_bwd(4, s.g16a.cview<TG>(), s.g16b);
+    dgrad3<TA, TG>(s, s.g16b, 5, s.g16a, 128, 4, &f4);
+    bn_bwd(4, s.g16a.cview<TG>(), s.g16b, f4);
     wgrad(4, s.g16b, s.a[3], 0);
-    dgrad3<TA, TG>(s.g16b, 4, s.g16a, 128);
-    bn_bwd(3, s.g16a.cview<TG>(), s.g16b);
+    dgrad3<TA, TG>(s, s.g16b, 4, s.g16a, 128, 3, &f3);
+    bn_bwd(3, s.g16a.cview<TG>(), s.g16b, f3);
     wgrad(3, s.g16b, s.p1, 0);
-    dgrad3<TA, TG>(s.g16b, 3, s.gp1, 64);
+    dgrad3<TA, TG>(s, s.g16b, 3, s.gp1, 64);
     // ---- down1: h1 receives the skip half of d(cat) plus the MaxPool-routed gradient
     {
         long long work = (long long)N * 16 * 16 * 8;
@@ -934,14 +971,28 @@ void Engine::backward_t(ActSet& s, const float* xt_dev, const int* ts_dev, const
         DDPM_LAUNCH_CHECK();
         cnt_launches += 1;
     }
-    bn_bwd(2, s.g32a.cview<TG>(), s.g32b);
+    bn_bwd(2, s.g32a.cview<TG>(), s.g32b, f2);
     wgrad(2, s.g32b, s.a[1], 0);
-    dgrad3<TA, TG>(s.g32b, 2, s.g32a, 64);
-    bn_bwd(1, s.g32a.cview<TG>(), s.g32b);
+    dgrad3<TA, TG>(s, s.g32b, 2, s.g32a, 64, 1, &f1);
+    bn_bwd(1, s.g32a.cview<TG>(), s.g32b, f1);
     {   // first conv: image channel + folded embedding channels
-        l1_bwd_kernel<TG><<<N, 256, 0, stream>>>(s.g32b.cview<TG>(), s.g32b.g, xt_dev, s.Tw.as<float>(), s.Ccls.as<float>());
+        {
+            // dy of the first conv -> per-image border-class sums (embedding channels) + image-channel weight gradient
+            DDPM_CUDA(cudaMemsetAsync(l1_acc, 0, 576 * sizeof(double), stream));
+            const int dt = std::is_same<TG, float>::value ? 0 : (std::is_same<TG, __half>::value ? 1 : 2);
+            View<const __half> vh{reinterpret_cast<const __half*>(s.g32b.pos0<TG>()), s.g32b.C};
+            View<const __nv_bfloat16> vb{reinterpret_cast<const __nv_bfloat16*>(s.g32b.pos0<TG>()), s.g32b.C};
+            View<const float> vf{reinterpret_cast<const float*>(s.g32b.pos0<TG>()), s.g32b.C};
+            if constexpr (sizeof(TG) == 2) {
+                // 16-bit gradients: dy staged through shared memory by bulk asynchronous copies (l1_bwd.cuh)
+                launch_l1_bwd_bulk<TG>(stream, s.g32b.pos0<TG>(), s.g32b.g, xt_dev, s.Ccls.as<float>(), l1_acc);
+            } else {
+                const int blocks = std::min(N, 2 * tc::state().num_sms);
+                l1_bwd_fused_kernel<<<blocks, 256, 0, stream>>>(vh, vb, vf, dt, s.g32b.g, xt_dev, s.Ccls.as<float>(), l1_acc);
+            }
+            l1_wimg_finish_kernel<<<3, 256, 0, stream>>>(l1_acc, alpha, 129, garr(0));
+        }
         l1_tap_sums_kernel<<<cdiv((long long)N * 576, 256), 256, 0, stream>>>(s.Ccls.as<float>(), s.S.as<float>(), N);
-        l1_wimg_grad_kernel<<<576, 256, 0, stream>>>(s.Tw.as<float>(), N, alpha, 129, garr(0));
         View<const float> Sv{s.S.as<float>(), 576}, pev{d_pe, D};
         launch_wgrad_simt<float, float>(stream, Sv, pev, (long long)N, 1, 576, D, MapId{(long long)N}, MapTs{ts_dev, (long long)N},
                                         IdxEmb{129, 64}, alpha, garr(0));

@@ -811,6 +811,112 @@ l1_bwd_kernel(View<const TG> dy, Geo g, const float* __restrict__ x, float* __re
     }
 }
 
+// Second formulation of the first conv's backward (the default): persistent blocks, one image per iteration.
+//   thread t: channels 8*(t&7).., pixel column w = t>>3 (fixed), rows h = 0..31 in turn  => every load instruction of
+//   a warp covers 4 whole 128-byte pixel rows; the border class of a thread's column never changes and the row class
+//   only at h = 0 / 31, so the nine class sums need no masks: top = row 0, bottom = row 31, middle = rows 1..30.
+//   The image-channel weight gradient is a sum over ALL images, so its 72 accumulators per thread live in registers
+//   across the block's images and are reduced ONCE (shuffles, shared memory, one Float64 atomic per value and block).
+// Outputs: Ccls[n][cls][co] per image (feeds the embedding-weight GEMM), wimg_acc[tap*64+co] += sum_n,p dy*x (Float64).
+__global__ void __launch_bounds__(256)
+l1_bwd_fused_kernel(View<const __half> dyh, View<const __nv_bfloat16> dyb, View<const float> dyf, int dtype /*0 f32, 1 f16, 2 bf16*/,
+                    Geo g, const float* __restrict__ x, float* __restrict__ Ccls, double* __restrict__ wimg_acc) {
+    constexpr int H = 32, W = 32, TW = W + 2;
+    __shared__ float tile[(H + 2) * TW];
+    __shared__ float red[32 * 3 * 64];                // class partials [w][row class][co]; reused as [8 warps][576] at the end
+    const int t = threadIdx.x;
+    const int c0 = (t & 7) * 8, w = t >> 3;
+    float tw[9][8];
+#pragma unroll
+    for (int a = 0; a < 9; ++a)
+#pragma unroll
+        for (int j = 0; j < 8; ++j) tw[a][j] = 0.f;
+    for (int n = blockIdx.x; n < g.N; n += gridDim.x) {
+        const float* xi = x + (long long)n * H * W;
+        for (int i = t; i < (H + 2) * TW; i += 256) {
+            const int rr = i / TW, cc = i - rr * TW;
+            const int hh = rr - 1, ww = cc - 1;
+            tile[i] = (hh >= 0 && hh < H && ww >= 0 && ww < W) ? __ldg(xi + hh * W + ww) : 0.f;
+        }
+        __syncthreads();
+        float top[8], mid[8], bot[8];
+#pragma unroll
+        for (int j = 0; j < 8; ++j) { top[j] = 0.f; mid[j] = 0.f; bot[j] = 0.f; }
+#pragma unroll 2
+        for (int h = 0; h < H; ++h) {
+            float d[8];
+            const long long pos = g.pos(n, h, w);
+            if (dtype == 1) V8<__half>::ld(dyh.p + pos * dyh.cs + c0, d);
+            else if (dtype == 2) V8<__nv_bfloat16>::ld(dyb.p + pos * dyb.cs + c0, d);
+            else V8<float>::ld(dyf.p + pos * dyf.cs + c0, d);
+            const float* tp = tile + h * TW + w;
+#pragma unroll
+            for (int tap = 0; tap < 9; ++tap) {
+                const float xv = tp[(tap / 3) * TW + (tap % 3)];
+#pragma unroll
+                for (int j = 0; j < 8; ++j) tw[tap][j] = fmaf(d[j], xv, tw[tap][j]);
+            }
+            if (h == 0) {
+#pragma unroll
+                for (int j = 0; j < 8; ++j) top[j] = d[j];
+            } else if (h == H - 1) {
+#pragma unroll
+                for (int j = 0; j < 8; ++j) bot[j] = d[j];
+            } else {
+#pragma unroll
+                for (int j = 0; j < 8; ++j) mid[j] += d[j];
+            }
+        }
+#pragma unroll
+        for (int j = 0; j < 8; ++j) {
+            red[(w * 3 + 0) * 64 + c0 + j] = top[j];
+            red[(w * 3 + 1) * 64 + c0 + j] = mid[j];
+            red[(w * 3 + 2) * 64 + c0 + j] = bot[j];
+        }
+        __syncthreads();
+        // class (rc, cc): cc = 0 -> column 0, cc = 2 -> column 31, cc = 1 -> columns 1..30
+        for (int i = t; i < 576; i += 256) {
+            const int co = i & 63, cls = i >> 6, rc = cls / 3, cc = cls - rc * 3;
+            float acc;
+            if (cc == 0) acc = red[(0 * 3 + rc) * 64 + co];
+            else if (cc == 2) acc = red[((W - 1) * 3 + rc) * 64 + co];
+            else {
+                acc = 0.f;
+                for (int ww = 1; ww < W - 1; ++ww) acc += red[(ww * 3 + rc) * 64 + co];
+            }
+            Ccls[(long long)n * 576 + i] = acc;
+        }
+        __syncthreads();                               // tile / red are rewritten by the next image
+    }
+    // image-channel weight gradient: combine the 4 pixel columns of a warp, then the 8 warps
+    const int warp = t >> 5;
+#pragma unroll
+    for (int tap = 0; tap < 9; ++tap)
+#pragma unroll
+        for (int j = 0; j < 8; ++j) {
+            float a = tw[tap][j];
+            a += __shfl_xor_sync(0xffffffffu, a, 8);
+            a += __shfl_xor_sync(0xffffffffu, a, 16);
+            if ((t & 31) < 8) red[warp * 576 + tap * 64 + c0 + j] = a;
+        }
+    __syncthreads();
+    for (int i = t; i < 576; i += 256) {
+        float acc = 0.f;
+#pragma unroll
+        for (int w8 = 0; w8 < 8; ++w8) acc += red[w8 * 576 + i];
+        atomicAdd(&wimg_acc[i], (double)acc);
+    }
+}
+
+// dWimg: arena[idx(tap,co)] = alpha * wimg_acc[tap*64+co]   (Flux index of input channel 0)
+__global__ void l1_wimg_finish_kernel(const double* __restrict__ acc, float alpha, int Cin_total, float* __restrict__ dW) {
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= 576) return;
+    const int tap = i / 64, co = i % 64;
+    const int dy = tap / 3 - 1, dx = tap % 3 - 1;
+    dW[(1 - dx) + 3 * (1 - dy) + 9LL * Cin_total * co] = (float)((double)alpha * acc[i]);
+}
+
 // S[n][tap][co] = sum of the class sums of the border classes for which tap stays inside the image
 __global__ void l1_tap_sums_kernel(const float* __restrict__ Ccls, float* __restrict__ S, long long B) {
     long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;

@@ -467,6 +467,7 @@ int ddpm_set_option(ddpm_handle* h, const char* key, int64_t value) {
     else if (k == "use_graph") e.opt_use_graph = value;
     else if (k == "conv_impl") { e.opt_conv_impl = value; for (auto& kv : e.infer_sets) kv.second->drop_graphs(); }
     else if (k == "sync_bn") { e.sync_bn = (int)value; e.drop_train_graphs(); }
+    else if (k == "fuse_bn") { e.opt_fuse_bn = value; e.drop_train_graphs(); }
     else if (k == "train_graph") { e.opt_train_graph = value; e.drop_train_graphs(); }
     else if (k == "loss_scale_log2") { DDPM_CHECK(value >= -30 && value <= 30, "loss_scale_log2 out of range"); e.opt_loss_scale_log2 = value; e.drop_train_graphs(); }
     else if (k == "tc_tma_store") { tc::state().tma_store = value != 0; for (auto& kv : e.infer_sets) kv.second->drop_graphs(); }
