@@ -63,6 +63,7 @@ struct NcclApi {
     ncclResult_t (*GetUniqueId)(ncclUniqueId*) = nullptr;
     ncclResult_t (*CommInitRank)(ncclComm_t*, int, ncclUniqueId, int) = nullptr;
     ncclResult_t (*AllReduce)(const void*, void*, size_t, ncclDataType_t, ncclRedOp_t, ncclComm_t, cudaStream_t) = nullptr;
+    ncclResult_t (*AllGather)(const void*, void*, size_t, ncclDataType_t, ncclComm_t, cudaStream_t) = nullptr;
     ncclResult_t (*CommDestroy)(ncclComm_t) = nullptr;
     const char* (*GetErrorString)(ncclResult_t) = nullptr;
     void load() {
@@ -76,6 +77,7 @@ struct NcclApi {
         GetUniqueId = (decltype(GetUniqueId))dlsym(lib, "ncclGetUniqueId");
         CommInitRank = (decltype(CommInitRank))dlsym(lib, "ncclCommInitRank");
         AllReduce = (decltype(AllReduce))dlsym(lib, "ncclAllReduce");
+        AllGather = (decltype(AllGather))dlsym(lib, "ncclAllGather");
         CommDestroy = (decltype(CommDestroy))dlsym(lib, "ncclCommDestroy");
         GetErrorString = (decltype(GetErrorString))dlsym(lib, "ncclGetErrorString");
         DDPM_CHECK(GetUniqueId && CommInitRank && AllReduce && CommDestroy, "libnccl is missing required symbols");
@@ -122,6 +124,15 @@ struct GraphEntry {
     cudaGraphExec_t exec = nullptr;
     long long launches = 0;
 };
+// A captured training iteration: the launch sequence cut into segments at every point where a gradient bucket goes to
+// NCCL.  The collectives themselves are issued eagerly between the segment launches (an NCCL call captured into a graph
+// next to uncaptured calls on the same communicator dead-locked on B200 / NCCL 2.28 -- measured in round 2), everything
+// else -- ~120 kernels and memsets, the peer-memory SyncBN exchanges included -- replays from the graphs.
+struct TrainGraph {
+    std::vector<GraphEntry> segs;
+    std::vector<std::pair<int, int>> buckets;     // arena array range [a0, a1) all-reduced after segment i
+    long long launches = 0;
+};
 
 // Activation set for one batch size.  Training keeps every y (pre-BN) and a (post-ReLU);
 // inference aliases a small rotating set and never materialises y.
@@ -144,7 +155,7 @@ struct ActSet {
     DevBuf x0, eps, ts, idx, xt, deps, Ccls, S;
     // captured training iterations, keyed by gather*2 + update (the first call of a key runs eagerly and warms every
     // lazily initialised resource, the second one is captured, later ones replay)
-    std::map<int, GraphEntry> train_graphs;
+    std::map<int, TrainGraph> train_graphs;
     std::map<int, int> train_calls;
     long long last_use = 0;
     static void destroy(GraphEntry& g) {
@@ -155,7 +166,8 @@ struct ActSet {
     void drop_graphs() {
         for (auto& kv : graphs) destroy(kv.second);
         graphs.clear();
-        for (auto& kv : train_graphs) destroy(kv.second);
+        for (auto& kv : train_graphs)
+            for (auto& g : kv.second.segs) destroy(g);
         train_graphs.clear();
         train_calls.clear();
     }
@@ -167,7 +179,7 @@ struct Engine {
     int T, D, H, W, prec, dev;
     int HW;
     cudaStream_t stream = nullptr, comm_stream = nullptr;
-    cudaEvent_t ev_bucket[2] = {nullptr, nullptr}, ev_comm_done = nullptr;
+    cudaEvent_t ev_bucket[5] = {}, ev_comm_done = nullptr;
     cudaEvent_t ev_t0 = nullptr, ev_t1 = nullptr;
     // Sampling can run consecutive chunks on alternating streams (chunks are independent).  Measured on B200
     // (round 1): no gain -- 4096 images, chunk 512: 1 stream 1786 img/s, 2 streams 1754; chunk 256 x 2 streams 1704 --
@@ -232,6 +244,16 @@ struct Engine {
     // communicator
     ncclComm_t comm = nullptr;
     int rank = 0, world = 1, sync_bn = 0;
+    // peer-memory mailboxes for the tiny SyncBN all-reduces (kernels.cuh: XReduce); xr_ok once every peer is mapped
+    XReduce xr{};
+    double* xr_own = nullptr;
+    void* xr_mapped[XR_MAX_WORLD] = {};
+    bool xr_ok = false;
+    std::string xr_note = "not initialised";
+    long long opt_bn_p2p = 1;      // SyncBN statistics over the peer-memory mailboxes (0: NCCL all-reduce per layer)
+    long long opt_dp_skip = 0;     // TIMING ONLY (results become wrong): bit 0 skips the gradient all-reduces, bit 1 the
+                                   // SyncBN all-reduces -- used to split a data-parallel step into compute / exposed comm
+    void init_peer_mailboxes();
 
     // options / counters
     long long opt_sample_streams = 1;
@@ -291,6 +313,25 @@ struct Engine {
 
     void train_enqueue(ActSet& s, bool gather, bool device_draws, bool update);
     void train_core(ActSet& s, bool gather, bool device_draws, bool update, float* loss_out_host);
+    TrainGraph* capturing = nullptr;        // non-null while train_core records a training iteration
+    void seg_begin() { DDPM_CUDA(cudaStreamBeginCapture(stream, cudaStreamCaptureModeThreadLocal)); }
+    void seg_end() {
+        GraphEntry ge;
+        DDPM_CUDA(cudaStreamEndCapture(stream, &ge.graph));
+        DDPM_CUDA(cudaGraphInstantiate(&ge.exec, ge.graph, 0));
+        capturing->segs.push_back(ge);
+    }
+    void issue_bucket(int a0, int a1, int k) {
+        cudaEvent_t ev = ev_bucket[k % 5];
+        DDPM_CUDA(cudaEventRecord(ev, stream));
+        DDPM_CUDA(cudaStreamWaitEvent(comm_stream, ev, 0));
+        nccl().check(nccl().AllReduce(G + offs[a0], G + offs[a0], (size_t)(offs[a1] - offs[a0]), ncclFloat32, ncclSum, comm,
+                                      comm_stream), "ncclAllReduce(gradient bucket)");
+    }
+    void join_comm() {
+        DDPM_CUDA(cudaEventRecord(ev_comm_done, comm_stream));
+        DDPM_CUDA(cudaStreamWaitEvent(stream, ev_comm_done, 0));
+    }
     void drop_train_graphs() { for (auto& kv : train_sets) kv.second->drop_graphs(); }
     void drop_all_graphs() { drop_train_graphs(); for (auto& kv : infer_sets) kv.second->drop_graphs(); }
     void sample_chunk(ActSet& s, bool host_z, unsigned long long seed, long long first_index, int t_start);
@@ -394,6 +435,10 @@ inline void Engine::reset_train_state() {
 inline Engine::~Engine() {
     cudaSetDevice(dev);
     cudaDeviceSynchronize();
+    for (int r = 0; r < XR_MAX_WORLD; ++r)
+        if (xr_mapped[r]) cudaIpcCloseMemHandle(xr_mapped[r]);
+    if (xr_own) cudaFree(xr_own);
+    if (xr.epoch) cudaFree(xr.epoch);
     if (comm) nccl().CommDestroy(comm);
     for (auto& kv : train_sets) { free_set(*kv.second); delete kv.second; }
     train_sets.clear();
@@ -729,13 +774,20 @@ void Engine::forward_t(ActSet& s, const float* x_dev, const int* ts_dev, int t_f
         // finalise batch statistics of layer l and apply BatchNorm+ReLU (train mode only)
         const ConvSpec& c = kConv[l];
         double m = count_local * c.hw * c.hw;
-        if (sync_bn && comm) {
-            allreduce_sums(lsum(l), gsum(l), 2 * c.cout);
-            m *= world;
+        // SyncBN: statistics of the GLOBAL batch.  With the peer-memory mailboxes the all-reduce happens inside
+        // bn_finalize_kernel; without them (P2P unavailable) it is an NCCL call in front of it.
+        int slot = -1;
+        const double* src = gsum(l);
+        if (sync_bn && comm && !(opt_dp_skip & 2)) {
+            if (xr_ok && opt_bn_p2p) { slot = l - 1; src = lsum(l); }
+            else allreduce_sums(lsum(l), gsum(l), 2 * c.cout);
+        } else if (sync_bn && comm) {
+            src = lsum(l);                 // timing-only mode: local statistics stand in for the global ones
         }
-        bn_finalize_kernel<<<1, 128, 0, stream>>>(gsum(l), m, arr(c.bn + 1), arr(c.bn), arr(c.bn + 2), arr(c.bn + 3),
+        if (sync_bn && comm) m *= world;
+        bn_finalize_kernel<<<1, 256, 0, stream>>>(src, m, arr(c.bn + 1), arr(c.bn), arr(c.bn + 2), arr(c.bn + 3),
                                                   tr_mean[l], tr_istd[l], tr_scale[l], tr_shift[l], c.cout, 1e-5f, 0.1f,
-                                                  update_running ? 1 : 0);
+                                                  update_running ? 1 : 0, xr, slot, gsum(l));
         long long work;
         if (pool) {
             work = (long long)N * 16 * 16 * (c.cout / 8);
@@ -823,6 +875,62 @@ void Engine::final_conv_t(ActSet& s, float* eps_hat_dev) {
     cnt_launches += 1;
 }
 
+// Map every rank's mailbox into this process (cudaIpc handles exchanged through the NCCL communicator that was just
+// created).  Any failure leaves xr_ok = false with the reason in xr_note: the NCCL all-reduce path is used instead.
+inline void Engine::init_peer_mailboxes() {
+    xr_ok = false;
+    if (world < 2 || world > XR_MAX_WORLD) { xr_note = "world size outside 2..16"; return; }
+    if (!nccl().AllGather) { xr_note = "ncclAllGather not found"; return; }
+    try {
+        DDPM_CUDA(cudaMalloc(&xr_own, XReduce::bytes()));
+        DDPM_CUDA(cudaMemset(xr_own, 0, XReduce::bytes()));
+        DDPM_CUDA(cudaMalloc(&xr.epoch, XR_SLOTS * sizeof(unsigned)));
+        DDPM_CUDA(cudaMemset(xr.epoch, 0, XR_SLOTS * sizeof(unsigned)));
+        cudaIpcMemHandle_t mine;
+        DDPM_CUDA(cudaIpcGetMemHandle(&mine, xr_own));
+        cudaIpcMemHandle_t* d_all = nullptr;
+        DDPM_CUDA(cudaMalloc(&d_all, sizeof(cudaIpcMemHandle_t) * (size_t)(world + 1)));
+        DDPM_CUDA(cudaMemcpy(d_all + world, &mine, sizeof mine, cudaMemcpyHostToDevice));
+        DDPM_CUDA(cudaDeviceSynchronize());
+        nccl().check(nccl().AllGather(d_all + world, d_all, sizeof(cudaIpcMemHandle_t), ncclChar, comm, stream),
+                     "ncclAllGather(ipc handles)");
+        DDPM_CUDA(cudaStreamSynchronize(stream));
+        std::vector<cudaIpcMemHandle_t> all(world);
+        DDPM_CUDA(cudaMemcpy(all.data(), d_all, sizeof(cudaIpcMemHandle_t) * (size_t)world, cudaMemcpyDeviceToHost));
+        cudaFree(d_all);
+        bool ok = true;
+        for (int r = 0; r < world; ++r) {
+            if (r == rank) { xr.peer[r] = xr_own; continue; }
+            void* p = nullptr;
+            cudaError_t e = cudaIpcOpenMemHandle(&p, all[r], cudaIpcMemLazyEnablePeerAccess);
+            if (e != cudaSuccess) {
+                cudaGetLastError();
+                xr_note = std::string("cudaIpcOpenMemHandle failed: ") + cudaGetErrorString(e);
+                ok = false;
+                break;
+            }
+            xr_mapped[r] = p;
+            xr.peer[r] = reinterpret_cast<double*>(p);
+        }
+        // every rank must take the same path: agree through a tiny all-reduce (min over ranks of `ok`)
+        int* d_ok = nullptr;
+        DDPM_CUDA(cudaMalloc(&d_ok, sizeof(int)));
+        int h_ok = ok ? 1 : 0;
+        DDPM_CUDA(cudaMemcpy(d_ok, &h_ok, sizeof(int), cudaMemcpyHostToDevice));
+        nccl().check(nccl().AllReduce(d_ok, d_ok, 1, ncclInt32, ncclMin, comm, stream), "ncclAllReduce(mailbox agreement)");
+        DDPM_CUDA(cudaStreamSynchronize(stream));
+        DDPM_CUDA(cudaMemcpy(&h_ok, d_ok, sizeof(int), cudaMemcpyDeviceToHost));
+        cudaFree(d_ok);
+        xr.rank = rank; xr.world = world;
+        xr_ok = h_ok == 1;
+        if (xr_ok) xr_note = "peer mailboxes mapped";
+        else if (ok) xr_note = "a peer could not map the mailboxes";
+    } catch (const std::exception& ex) {
+        xr_note = ex.what();
+        xr_ok = false;
+    }
+}
+
 inline void Engine::allreduce_sums(double* local, double* global, int n) {
     nccl().check(nccl().AllReduce(local, global, n, ncclFloat64, ncclSum, comm, stream), "ncclAllReduce(bn sums)");
 }
@@ -848,17 +956,36 @@ void Engine::backward_t(ActSet& s, const float* xt_dev, const int* ts_dev, const
                 s.y[l].cview<TA>(), da, g.npos, c.cout, tr_scale[l], tr_shift[l], tr_mean[l], tr_istd[l], lsum(l));
             cnt_launches += 1;
         }
-        if (sync_bn && comm) {
-            allreduce_sums(lsum(l), gsum(l), 2 * c.cout);
-            m *= world;
+        int slot = -1;
+        const double* gs = gsum(l);
+        if (sync_bn && comm && !(opt_dp_skip & 2)) {
+            if (xr_ok && opt_bn_p2p) slot = NUM_CONV + l - 1;
+            else allreduce_sums(lsum(l), gsum(l), 2 * c.cout);
+        } else if (sync_bn && comm) {
+            gs = lsum(l);
         }
-        bn_bwd_means_kernel<<<1, 128, 0, stream>>>(lsum(l), gsum(l), m, c.cout, bw_mg[l], bw_mgx[l], garr(c.bn), garr(c.bn + 1),
-                                                   alpha);
+        if (sync_bn && comm) m *= world;
+        bn_bwd_means_kernel<<<1, 256, 0, stream>>>(lsum(l), gs, m, c.cout, bw_mg[l], bw_mgx[l], garr(c.bn), garr(c.bn + 1),
+                                                   alpha, xr, slot, gsum(l));
         bn_bwd_kernel<TA, TG, 2><<<blocks, 256, 0, stream>>>(s.y[l].cview<TA>(), da, dy.view<TG>(), g, c.cout, tr_scale[l],
                                                              tr_shift[l], tr_mean[l], tr_istd[l], bw_mg[l], bw_mgx[l], lsum(l));
         f64_to_f32_kernel<<<1, 128, 0, stream>>>(lsum(l) + 2 * c.cout, garr(c.b), c.cout, (double)alpha);
         DDPM_LAUNCH_CHECK();
         cnt_launches += 3;
+    };
+    // Data parallel: the gradient arena is all-reduced in five layer-ordered buckets (arena order = constructor order:
+    // down1 | down2 | mid | up2 | up1+final); a bucket goes to the communication stream as soon as the backward pass
+    // has written its last gradient, so only the last one (down1, 0.45 MB) is exposed.  Arrays [a0, a1).
+    int n_bucket = 0;
+    auto grad_bucket = [&](int a0, int a1) {
+        if (!comm || (opt_dp_skip & 1)) return;
+        if (capturing) {                       // recording: close the segment here, the collective is issued at replay
+            seg_end();
+            capturing->buckets.emplace_back(a0, a1);
+            seg_begin();
+            return;
+        }
+        issue_bucket(a0, a1, n_bucket++);
     };
     // weight gradient of a 3x3 conv: dW[co][tap][ci] = sum_p dy[p][co] * x[p + shift(tap)][ci]
     auto wgrad = [&](int l, const Tensor& dy, const Tensor& x, int ci_off) {
@@ -902,6 +1029,7 @@ void Engine::backward_t(ActSet& s, const float* xt_dev, const int* ts_dev, const
     wgrad(9, s.g32b, s.a[8], 0);
     wgrad(9, s.g32b, s.a[2], 64);
     dgrad3<TA, TG>(s, s.g32b, 9, s.gcat, 128, 8, &f8);      // d(cat): channels 0..63 = d(a8), 64..127 = skip half of d(h1)
+    grad_bucket(50, NUM_ARRAYS);   // up1 + final complete
     // ---- up2
     bn_bwd(8, s.gcat.cview<TG>(0), s.g32b, f8);
     wgrad(8, s.g32b, s.a[7], 0);
@@ -942,13 +1070,7 @@ void Engine::backward_t(ActSet& s, const float* xt_dev, const int* ts_dev, const
         DDPM_LAUNCH_CHECK();
         cnt_launches += 4;
     }
-    // first gradient bucket complete: arrays [kUpW, 64) -- start its all-reduce while the rest runs
-    if (comm) {
-        DDPM_CUDA(cudaEventRecord(ev_bucket[0], stream));
-        DDPM_CUDA(cudaStreamWaitEvent(comm_stream, ev_bucket[0], 0));
-        nccl().check(nccl().AllReduce(G + offs[kUpW], G + offs[kUpW], (size_t)(n_params - offs[kUpW]), ncclFloat32, ncclSum,
-                                      comm, comm_stream), "ncclAllReduce(grad bucket 0)");
-    }
+    grad_bucket(kUpW, 50);         // up2 complete
     // ---- mid, down2
     bn_bwd(6, s.g16a.cview<TG>(), s.g16b, f6);
     wgrad(6, s.g16b, s.a[5], 0);
@@ -956,12 +1078,14 @@ void Engine::backward_t(ActSet& s, const float* xt_dev, const int* ts_dev, const
     bn_bwd(5, s.g16a.cview<TG>(), s.g16b, f5);
     wgrad(5, s.g16b, s.a[4], 0);
     dgrad3<TA, TG>(s, s.g16b, 5, s.g16a, 128, 4, &f4);
+    grad_bucket(24, 36);           // mid complete
     bn_bwd(4, s.g16a.cview<TG>(), s.g16b, f4);
     wgrad(4, s.g16b, s.a[3], 0);
     dgrad3<TA, TG>(s, s.g16b, 4, s.g16a, 128, 3, &f3);
     bn_bwd(3, s.g16a.cview<TG>(), s.g16b, f3);
     wgrad(3, s.g16b, s.p1, 0);
     dgrad3<TA, TG>(s, s.g16b, 3, s.gp1, 64);
+    grad_bucket(12, 24);           // down2 complete
     // ---- down1: h1 receives the skip half of d(cat) plus the MaxPool-routed gradient
     {
         long long work = (long long)N * 16 * 16 * 8;
@@ -999,14 +1123,8 @@ void Engine::backward_t(ActSet& s, const float* xt_dev, const int* ts_dev, const
         DDPM_LAUNCH_CHECK();
         cnt_launches += 4;
     }
-    if (comm) {
-        DDPM_CUDA(cudaEventRecord(ev_bucket[1], stream));
-        DDPM_CUDA(cudaStreamWaitEvent(comm_stream, ev_bucket[1], 0));
-        nccl().check(nccl().AllReduce(G, G, (size_t)offs[kUpW], ncclFloat32, ncclSum, comm, comm_stream),
-                     "ncclAllReduce(grad bucket 1)");
-        DDPM_CUDA(cudaEventRecord(ev_comm_done, comm_stream));
-        DDPM_CUDA(cudaStreamWaitEvent(stream, ev_comm_done, 0));
-    }
+    grad_bucket(0, 12);            // down1 complete: the only bucket whose all-reduce cannot hide behind backward work
+    if (comm && !(opt_dp_skip & 1) && !capturing) join_comm();      // (replay joins after its last bucket)
 }
 
 // ------------------------------------------------------------------------------------ one training iteration
@@ -1054,33 +1172,46 @@ inline void Engine::train_core(ActSet& s, bool gather, bool device_draws, bool u
     const int B = s.N;
     const int key = (gather ? 4 : 0) + (device_draws ? 2 : 0) + (update ? 1 : 0);
     bool replayed = false;
-    if (opt_train_graph) {
+    // SyncBN through NCCL (mailboxes unavailable or switched off) would put collectives inside the segments: run eagerly
+    const bool graph_ok = opt_train_graph && !(comm && sync_bn && !(xr_ok && opt_bn_p2p) && !(opt_dp_skip & 2));
+    if (graph_ok) {
         auto it = s.train_graphs.find(key);
         if (it == s.train_graphs.end() && s.train_calls[key] >= 1) {
-            // second call of this kind on this set: capture it (the first, eager call initialised every lazily
-            // created resource -- function attributes, occupancy queries, derived tables)
-            ecls_valid = false;                       // the captured step must contain the embedding-fold refresh
+            // second call of this kind on this set: record it (the first, eager call initialised every lazily
+            // created resource -- function attributes, occupancy queries, derived tables, NCCL channels)
+            ecls_valid = false;                       // the recorded step must contain the embedding-fold refresh
             DDPM_CUDA(cudaStreamSynchronize(stream));
-            GraphEntry ge;
+            DDPM_CUDA(cudaStreamSynchronize(comm_stream));
+            TrainGraph tg;
             const long long before = cnt_launches;
-            DDPM_CUDA(cudaStreamBeginCapture(stream, cudaStreamCaptureModeThreadLocal));
+            capturing = &tg;
             try {
+                seg_begin();
                 train_enqueue(s, gather, device_draws, update);
+                seg_end();
             } catch (...) {
                 cudaGraph_t g = nullptr;
                 cudaStreamEndCapture(stream, &g);
                 if (g) cudaGraphDestroy(g);
+                capturing = nullptr;
+                for (auto& ge : tg.segs) ActSet::destroy(ge);
                 throw;
             }
-            DDPM_CUDA(cudaStreamEndCapture(stream, &ge.graph));
-            DDPM_CUDA(cudaGraphInstantiate(&ge.exec, ge.graph, 0));
-            ge.launches = cnt_launches - before;
+            capturing = nullptr;
+            tg.launches = cnt_launches - before;
             cnt_launches = before;
-            it = s.train_graphs.emplace(key, ge).first;
+            it = s.train_graphs.emplace(key, tg).first;
         }
         if (it != s.train_graphs.end()) {
-            DDPM_CUDA(cudaGraphLaunch(it->second.exec, stream));
-            cnt_launches += it->second.launches;
+            TrainGraph& tg = it->second;
+            for (size_t i = 0; i < tg.segs.size(); ++i) {
+                DDPM_CUDA(cudaGraphLaunch(tg.segs[i].exec, stream));
+                if (i < tg.buckets.size()) {
+                    issue_bucket(tg.buckets[i].first, tg.buckets[i].second, (int)i);
+                    if (i + 1 == tg.buckets.size()) join_comm();
+                }
+            }
+            cnt_launches += tg.launches;
             replayed = true;
         }
     }

@@ -296,14 +296,87 @@ __global__ void emb_class_sums_kernel(const float* __restrict__ P, float* __rest
     Ecls[i] = s;
 }
 
+// ------------------------------------------------------------------------------------ one-shot all-reduce over peer memory
+// SyncBN needs 20 all-reduces of 128..256 doubles per training step, each on the critical path between a convolution
+// and the BatchNorm that follows it.  As NCCL calls they cost a launch plus a multi-hop protocol each; here the
+// exchange is a few lines INSIDE the kernel that consumes the result (bn_finalize_kernel / bn_bwd_means_kernel):
+// every rank stores its vector straight into every peer's mailbox over NVLink (peer pointers from cudaIpc handles),
+// publishes a flag, waits for the world's flags in its own mailbox and sums the rows in rank order -- bit-identical
+// on every rank.  Mailbox of one rank:  data[parity][slot][src rank][384] doubles, flag[parity][slot][src rank] u32.
+// `slot` identifies the call site inside a step (forward layer l: l-1, backward layer l: 10+l-1), the epoch of a slot
+// (how often it ran) comes from a per-slot device counter, so the kernel arguments never change (CUDA-graph safe);
+// the epoch's parity double-buffers the mailbox.  A rank can only be one slot ahead of the slowest rank (it needs
+// everybody's flag to leave a slot), so a mailbox entry is never overwritten before its reader is done.
+constexpr int XR_SLOTS = 24;
+constexpr int XR_MAX_WORLD = 16;
+constexpr int XR_VEC = 384;
+struct XReduce {
+    double* peer[XR_MAX_WORLD];     // base of every rank's mailbox in THIS process's address space (peer[rank] = own)
+    unsigned* epoch;                // [XR_SLOTS] per-slot run counters (device, private)
+    int rank, world;
+    __host__ __device__ static size_t data_doubles() { return (size_t)2 * XR_SLOTS * XR_MAX_WORLD * XR_VEC; }
+    __host__ __device__ static size_t bytes() { return data_doubles() * sizeof(double) + (size_t)2 * XR_SLOTS * XR_MAX_WORLD * sizeof(unsigned); }
+};
+__device__ __forceinline__ void xr_store_release_sys(unsigned* p, unsigned v) {
+    asm volatile("st.release.sys.global.u32 [%0], %1;" ::"l"(p), "r"(v) : "memory");
+}
+__device__ __forceinline__ unsigned xr_load_acquire_sys(const unsigned* p) {
+    unsigned v;
+    asm volatile("ld.acquire.sys.global.u32 %0, [%1];" : "=r"(v) : "l"(p) : "memory");
+    return v;
+}
+// Block-wide (one block, >= max(n, world) threads): out[i] = sum over ranks of local[i], i < n <= 384.
+__device__ __forceinline__ void xr_allreduce_block(const XReduce& x, int slot, const double* __restrict__ local, int n,
+                                                   double* __restrict__ out) {
+    const int t = threadIdx.x;
+    const unsigned e = x.epoch[slot];
+    const int par = (int)(e & 1u);
+    const size_t row = ((size_t)(par * XR_SLOTS + slot) * XR_MAX_WORLD);
+    if (t < n) {
+        const double v = local[t];
+        for (int r = 0; r < x.world; ++r) x.peer[r][(row + x.rank) * XR_VEC + t] = v;       // NVLink stores
+    }
+    __threadfence_system();
+    __syncthreads();
+    if (t < x.world) {
+        unsigned* fl = reinterpret_cast<unsigned*>(x.peer[t] + XReduce::data_doubles());
+        xr_store_release_sys(fl + row + x.rank, e + 1u);
+    }
+    if (t < x.world) {
+        const unsigned* mine = reinterpret_cast<const unsigned*>(x.peer[x.rank] + XReduce::data_doubles()) + row + t;
+        unsigned long long spins = 0;
+        while (xr_load_acquire_sys(mine) != e + 1u) {
+            if (++spins > (1ull << 22)) __trap();       // a lost peer must fault (after a few seconds), never hang the GPU
+        }
+    }
+    __syncthreads();
+    if (t < n) {
+        const volatile double* d = x.peer[x.rank] + row * XR_VEC + t;
+        double s = 0.0;
+        for (int r = 0; r < x.world; ++r) s += d[(size_t)r * XR_VEC];
+        out[t] = s;
+    }
+    __syncthreads();
+    if (t == 0) x.epoch[slot] = e + 1u;
+}
+
 // ------------------------------------------------------------------------------------ BatchNorm forward
 // Flux BatchNorm(c, relu), eps=1e-5, momentum=0.1.
 // sums = [sum y | sum y^2] (Float64, accumulated from the FP32 conv accumulators).
-__global__ void bn_finalize_kernel(const double* __restrict__ sums, double count, const float* __restrict__ gamma,
-                                   const float* __restrict__ beta, float* __restrict__ run_mu, float* __restrict__ run_var,
-                                   float* __restrict__ mean_o, float* __restrict__ istd_o, float* __restrict__ scale_o,
-                                   float* __restrict__ shift_o, int C, float eps, float momentum, int update_running) {
-    int c = blockIdx.x * blockDim.x + threadIdx.x;
+// xr_slot >= 0: `sums` are this rank's LOCAL sums; the kernel first all-reduces them over peer memory into gsums
+// (SyncBN: the statistics of the GLOBAL batch, `count` = global element count) -- compute step and collective in one
+// launch.  xr_slot < 0: `sums` are used as they are.  One block of 256 threads.
+__global__ void __launch_bounds__(256)
+bn_finalize_kernel(const double* __restrict__ sums, double count, const float* __restrict__ gamma,
+                   const float* __restrict__ beta, float* __restrict__ run_mu, float* __restrict__ run_var,
+                   float* __restrict__ mean_o, float* __restrict__ istd_o, float* __restrict__ scale_o,
+                   float* __restrict__ shift_o, int C, float eps, float momentum, int update_running,
+                   XReduce xr, int xr_slot, double* __restrict__ gsums) {
+    if (xr_slot >= 0) {
+        xr_allreduce_block(xr, xr_slot, sums, 2 * C, gsums);
+        sums = gsums;
+    }
+    int c = threadIdx.x;
     if (c >= C) return;
     double mean = sums[c] / count;
     double var = sums[C + c] / count - mean * mean;
@@ -665,11 +738,18 @@ bn_reduce_linear_kernel(View<const TA> y, View<const TG> da, long long npos, int
     }
 }
 
-// after pass 1: local sums -> gradient arena (d beta, d gamma); global sums -> means for pass 2
-__global__ void bn_bwd_means_kernel(const double* __restrict__ local_sums, const double* __restrict__ global_sums,
-                                    double count, int C, float* __restrict__ mg, float* __restrict__ mgx,
-                                    float* __restrict__ dbeta, float* __restrict__ dgamma, float alpha) {
-    int c = blockIdx.x * blockDim.x + threadIdx.x;
+// after pass 1: local sums -> gradient arena (d beta, d gamma); global sums -> means for pass 2.
+// xr_slot >= 0: the global sums are produced here by the peer-memory all-reduce of the local ones (see above).
+__global__ void __launch_bounds__(256)
+bn_bwd_means_kernel(const double* __restrict__ local_sums, const double* __restrict__ global_sums,
+                    double count, int C, float* __restrict__ mg, float* __restrict__ mgx,
+                    float* __restrict__ dbeta, float* __restrict__ dgamma, float alpha, XReduce xr, int xr_slot,
+                    double* __restrict__ gsums) {
+    if (xr_slot >= 0) {
+        xr_allreduce_block(xr, xr_slot, local_sums, 2 * C, gsums);
+        global_sums = gsums;
+    }
+    int c = threadIdx.x;
     if (c >= C) return;
     dbeta[c] = (float)((double)alpha * local_sums[c]);        // alpha = 1/loss-scale
     dgamma[c] = (float)((double)alpha * local_sums[C + c]);

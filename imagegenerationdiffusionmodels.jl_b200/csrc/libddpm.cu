@@ -454,6 +454,9 @@ int ddpm_comm_init(ddpm_handle* h, const void* id, int rank, int world, int sync
     std::memcpy(&uid, id, sizeof uid);
     nccl().check(nccl().CommInitRank(&e.comm, world, uid, rank), "ncclCommInitRank");
     e.rank = rank; e.world = world; e.sync_bn = sync_bn;
+    e.drop_train_graphs();
+    e.init_peer_mailboxes();
+    if (getenv("DDPM_DEBUG")) fprintf(stderr, "[libddpm] rank %d/%d: peer mailboxes: %s\n", rank, world, e.xr_note.c_str());
     API_END
 }
 
@@ -467,6 +470,8 @@ int ddpm_set_option(ddpm_handle* h, const char* key, int64_t value) {
     else if (k == "use_graph") e.opt_use_graph = value;
     else if (k == "conv_impl") { e.opt_conv_impl = value; for (auto& kv : e.infer_sets) kv.second->drop_graphs(); }
     else if (k == "sync_bn") { e.sync_bn = (int)value; e.drop_train_graphs(); }
+    else if (k == "bn_p2p") { e.opt_bn_p2p = value; e.drop_train_graphs(); }
+    else if (k == "dp_skip") { e.opt_dp_skip = value; e.drop_train_graphs(); }
     else if (k == "fuse_bn") { e.opt_fuse_bn = value; e.drop_train_graphs(); }
     else if (k == "train_graph") { e.opt_train_graph = value; e.drop_train_graphs(); }
     else if (k == "loss_scale_log2") { DDPM_CHECK(value >= -30 && value <= 30, "loss_scale_log2 out of range"); e.opt_loss_scale_log2 = value; e.drop_train_graphs(); }
@@ -493,6 +498,7 @@ int64_t ddpm_get_counter(ddpm_handle* h, const char* key) {
     if (k == "n_params") return h->eng->n_params;
     if (k == "tc_available") return tc::available() ? 1 : 0;
     if (k == "uses_tc") return h->eng->use_tc() ? 1 : 0;
+    if (k == "bn_p2p_active") return (h->eng->xr_ok && h->eng->opt_bn_p2p && h->eng->sync_bn && h->eng->comm) ? 1 : 0;
     if (k == "skipped_steps" || k == "applied_steps") {
         // device-resident optimiser counters (overflow guard): a synchronising read
         Engine& e = *h->eng;

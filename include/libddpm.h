@@ -142,10 +142,12 @@ int ddpm_comm_init(ddpm_handle*, const void* id, int rank, int world, int sync_b
  *   tc_pair (bit mask of layer shapes run as CTA pairs / cta_group::2, 31 = all), tc_pdl (1: programmatic dependent
  *   launch of the tcgen05 kernels), conv1_tc (1: first conv of the sampler on tensor cores), tc_tma_store (1),
  *   tc_role_profile (0: in-kernel cycle counters), train_graph (1: replay the training iteration from a CUDA graph),
+ *   bn_p2p (1: SyncBN statistics exchanged over peer-memory mailboxes inside the finalize kernels; 0: one NCCL all-reduce
+ *   per layer), dp_skip (0; TIMING ONLY, results become wrong: bit 0 skips the gradient all-reduces, bit 1 the SyncBN ones),
  *   fuse_bn (1: train-mode BatchNorm reductions inside the tcgen05 conv / data-gradient epilogues),
  *   loss_scale_log2 (0: extra power-of-two factor on the static loss scale of the 16-bit gradient tensors).
  * None of them changes results beyond the documented rounding of the selected kernels.
- * Counter keys: launches, n_params, tc_available, uses_tc, skipped_steps (updates skipped by the overflow guard: a
+ * Counter keys: launches, n_params, tc_available, uses_tc, bn_p2p_active, skipped_steps (updates skipped by the overflow guard: a
  * non-finite value in the reduced gradient leaves weights, moments and beta^t untouched), applied_steps. */
 int ddpm_set_option(ddpm_handle*, const char* key, int64_t value);
 int64_t ddpm_get_counter(ddpm_handle*, const char* key);

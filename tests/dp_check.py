@@ -37,6 +37,11 @@ def main():
     # ---- data-parallel training with SyncBN == single-GPU global batch
     h = make_handle(local, prec)
     dist.init_data_parallel(h, sync_bn=True)
+    verdict["bn_p2p_active"] = h.counter("bn_p2p_active")      # SyncBN over peer-memory mailboxes (else NCCL per layer)
+    if os.environ.get("DP_BN_P2P") is not None:
+        h.set_option("bn_p2p", int(os.environ["DP_BN_P2P"]))
+    if os.environ.get("DP_TRAIN_GRAPH") is not None:
+        h.set_option("train_graph", int(os.environ["DP_TRAIN_GRAPH"]))
     dp_losses = []
     for k in range(3):
         ts = np.random.default_rng(100 + k).integers(1, 501, Bg)
