@@ -210,7 +210,7 @@ def run_ours(args):
     if capi.device_count() < 1:
         raise SystemExit("bench.py needs a CUDA device: libddpm has no CPU fallback")
     peaks = load_peaks()
-    prec = {"fp32": capi.PREC_FP32, "fp16": capi.PREC_FP16, "bf16": capi.PREC_BF16}[args.precision]
+    prec = {"fp32": capi.PREC_FP32, "fp16": capi.PREC_FP16, "bf16": capi.PREC_BF16, "tf32": capi.PREC_TF32}[args.precision]
     h = capi.Handle(T=T_STEPS, precision=prec, device=local)
     beta, _, acum = tables.beta_schedule(T_STEPS)
     h.set_tables(beta, acum, tables.embedding_table(T_STEPS))
@@ -399,7 +399,7 @@ def run_workload(args, workload, h, td, rank, world, local, peaks, N, t_start, e
     line = {
         "metric": metric, "value": value, "unit": "img/s", "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
         "ms_per_step": ms / args.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
-        "dtype": {"fp32": "f32", "fp16": "f16", "bf16": "bf16"}[args.precision], "data": "synthetic",
+        "dtype": {"fp32": "f32", "fp16": "f16", "bf16": "bf16", "tf32": "tf32"}[args.precision], "data": "synthetic",
         "config": {"workload": workload_desc, "images_per_step_per_gpu": N, "T": T_STEPS, "chunk": args.chunk,
                    "precision": args.precision, "tensor_cores": bool(uses_tc),
                    "l2_policy": "per-step activation working set exceeds the 126 MB L2" if N * 0.4 > 126 else
@@ -440,7 +440,7 @@ def main():
                     help="training batch per step per GPU (default: BASELINE config 5, global batch 4096 => 4096/n_gpus)")
     ap.add_argument("--chunk", type=int, default=1300, help="images per captured reverse-loop graph")
     ap.add_argument("--streams", type=int, default=0, help="concurrent chunk streams of the sampler (0: library default)")
-    ap.add_argument("--precision", default="fp16", choices=["fp32", "fp16", "bf16"])
+    ap.add_argument("--precision", default="fp16", choices=["fp32", "fp16", "bf16", "tf32"])
     ap.add_argument("--t-start", type=int, default=T_STEPS)
     ap.add_argument("--seed", type=int, default=1234)
     ap.add_argument("--sync-bn", type=int, default=1)

@@ -13,7 +13,7 @@ import numpy as np
 HERE = os.path.dirname(os.path.abspath(__file__))
 LIB_PATH = os.path.join(HERE, "libddpm.so")
 
-PREC_FP32, PREC_FP16, PREC_BF16 = 0, 1, 2
+PREC_FP32, PREC_FP16, PREC_BF16, PREC_TF32 = 0, 1, 2, 3
 NUM_ARRAYS = 64
 
 _f32p = C.POINTER(C.c_float)

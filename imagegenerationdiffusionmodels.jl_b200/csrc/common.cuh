@@ -105,6 +105,14 @@ template <> __device__ __forceinline__ float from_f<float>(float v) { return v; 
 template <> __device__ __forceinline__ __half from_f<__half>(float v) { return __float2half_rn(v); }
 template <> __device__ __forceinline__ __nv_bfloat16 from_f<__nv_bfloat16>(float v) { return __float2bfloat16_rn(v); }
 
+// FP32 -> nearest TF32 (10-bit mantissa), returned as an FP32 bit pattern.  tcgen05.mma.kind::tf32 ignores the low 13
+// mantissa bits (truncation); rounding operands to nearest beforehand halves the operand error and removes its bias.
+__device__ __forceinline__ float tf32_rn(float v) {
+    uint32_t u;
+    asm("cvt.rna.tf32.f32 %0, %1;" : "=r"(u) : "f"(v));
+    return __uint_as_float(u);
+}
+
 __device__ __forceinline__ float warp_sum(float v) {
 #pragma unroll
     for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);

@@ -171,6 +171,18 @@ __device__ __forceinline__ void umma_f16(uint32_t d_tmem, uint64_t a_desc, uint6
         : "memory");
 }
 // same, descriptors passed as (lo, hi) halves so that advancing the start address is one 32-bit add
+// same for FP32 operands read as TF32 (kind::tf32: K = 8 elements = the same 32 bytes per instruction), single CTA
+__device__ __forceinline__ void umma_tf32_lh(uint32_t d_tmem, uint32_t a_lo, uint32_t b_lo, uint32_t desc_hi, uint32_t idesc,
+                                             uint32_t accumulate) {
+    asm volatile(
+        "{\n\t.reg .pred p;\n\t.reg .b64 da, db;\n\t"
+        "mov.b64 da, {%1, %3};\n\t"
+        "mov.b64 db, {%2, %3};\n\t"
+        "setp.ne.b32 p, %5, 0;\n\t"
+        "tcgen05.mma.cta_group::1.kind::tf32 [%0], da, db, %4, p;\n\t}"
+        ::"r"(d_tmem), "r"(a_lo), "r"(b_lo), "r"(desc_hi), "r"(idesc), "r"(accumulate)
+        : "memory");
+}
 template <int CG = 1>
 __device__ __forceinline__ void umma_f16_lh(uint32_t d_tmem, uint32_t a_lo, uint32_t b_lo, uint32_t desc_hi, uint32_t idesc,
                                             uint32_t accumulate) {
@@ -232,8 +244,10 @@ __device__ __forceinline__ uint64_t make_desc_sw128(uint32_t saddr, uint32_t bas
     return d;
 }
 
+// operand format field of the instruction descriptor: kind::f16 -> 0 = F16, 1 = BF16;  kind::tf32 -> 2 = TF32
 template <typename T> struct IsBf16 { static constexpr uint32_t v = 0; };
 template <> struct IsBf16<__nv_bfloat16> { static constexpr uint32_t v = 1; };
+template <> struct IsBf16<float> { static constexpr uint32_t v = 2; };
 
 // instruction descriptor for kind::f16: D=F32, A/B = F16 or BF16, both K-major, M x N tile
 __host__ __device__ constexpr uint32_t make_idesc(uint32_t fmt, uint32_t M, uint32_t N) {
@@ -268,8 +282,16 @@ __device__ __forceinline__ void store16<__nv_bfloat16>(__nv_bfloat16* p, const f
     *reinterpret_cast<uint4*>(p + 8) = b;
 }
 
+template <>
+__device__ __forceinline__ void store16<float>(float* p, const float v[16]) {
+#pragma unroll
+    for (int i = 0; i < 4; ++i) *reinterpret_cast<float4*>(p + 4 * i) = make_float4(v[4 * i], v[4 * i + 1], v[4 * i + 2], v[4 * i + 3]);
+}
+
 template <typename TOut>
 __device__ __forceinline__ void pack16(const float v[16], uint4& a, uint4& b);
+template <>
+__device__ __forceinline__ void pack16<float>(const float*, uint4&, uint4&) {}      // (staged epilogues are 16-bit only)
 template <>
 __device__ __forceinline__ void pack16<__half>(const float v[16], uint4& a, uint4& b) {
     __half2* ha = reinterpret_cast<__half2*>(&a);
@@ -341,22 +363,22 @@ constexpr int stages_for(int extra) {
 // channels per pass of the per-warp store staging (direct-store epilogues): every epilogue warp transposes its
 // 32 rows x STC channels through a private shared-memory patch so that a store instruction writes whole 128-byte
 // (STC=64) or 64-byte (STC=32) row segments instead of 32 scattered 16-byte pieces.  0 = no room, direct stores.
-template <int TAPS, int CHUNKS, int NOUT, int WP, int EPI, int TMAST, int CG>
+template <int TAPS, int CHUNKS, int NOUT, int WP, int EPI, int TMAST, int CG, int ESZ = 2>
 constexpr int stage_cols() {
-    if (TMAST || EPI == 2) return 0;
+    if (TMAST || EPI == 2 || ESZ != 2) return 0;       // FP32 outputs (TF32 variants): direct 16-byte stores
     const int full = stages_for<TAPS, CHUNKS, NOUT, WP, CG>(0);
     const int want = full < 4 ? full : 4;
     if (stages_for<TAPS, CHUNKS, NOUT, WP, CG>(8 * 32 * 64 * 2) >= want) return 64;
     if (stages_for<TAPS, CHUNKS, NOUT, WP, CG>(8 * 32 * 32 * 2) >= want) return 32;
     return 0;
 }
-template <int TAPS, int CHUNKS, int NOUT, int WP, int EPI, int TMAST, int CG>
+template <int TAPS, int CHUNKS, int NOUT, int WP, int EPI, int TMAST, int CG, int ESZ = 2>
 constexpr int epi_smem_bytes() {
-    return TMAST ? 2 * TC_BM * NOUT * 2 : 8 * 32 * stage_cols<TAPS, CHUNKS, NOUT, WP, EPI, TMAST, CG>() * 2;
+    return TMAST ? 2 * TC_BM * NOUT * 2 : 8 * 32 * stage_cols<TAPS, CHUNKS, NOUT, WP, EPI, TMAST, CG, ESZ>() * 2;
 }
-template <int TAPS, int CHUNKS, int NOUT, int WP, int EPI, int TMAST, int CG = 1>
+template <int TAPS, int CHUNKS, int NOUT, int WP, int EPI, int TMAST, int CG = 1, int ESZ = 2>
 constexpr int pick_stages() {
-    return stages_for<TAPS, CHUNKS, NOUT, WP, CG>(epi_smem_bytes<TAPS, CHUNKS, NOUT, WP, EPI, TMAST, CG>());
+    return stages_for<TAPS, CHUNKS, NOUT, WP, CG>(epi_smem_bytes<TAPS, CHUNKS, NOUT, WP, EPI, TMAST, CG, ESZ>());
 }
 
 // CG: 1 = one CTA per 128-position tile; 2 = CTA pair (cluster of 2, tcgen05 cta_group::2): the pair works on 256
@@ -382,8 +404,11 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constant__
     extern __shared__ uint8_t smem_raw[];
     uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
     // epilogue staging: TMAST -> two tiles [128][NOUT] (one per epilogue set); else 8 per-warp patches [32][STC]
-    constexpr int STC = stage_cols<TAPS, CHUNKS, NOUT, WP, EPI, TMAST, CG>();
-    constexpr uint32_t O_BYTES = (uint32_t)epi_smem_bytes<TAPS, CHUNKS, NOUT, WP, EPI, TMAST, CG>();
+    constexpr int STC = stage_cols<TAPS, CHUNKS, NOUT, WP, EPI, TMAST, CG, (int)sizeof(TOut)>();
+    constexpr uint32_t O_BYTES = (uint32_t)epi_smem_bytes<TAPS, CHUNKS, NOUT, WP, EPI, TMAST, CG, (int)sizeof(TOut)>();
+    constexpr bool TF32 = std::is_same<TIn, float>::value;     // FP32 operands read as TF32 (kind::tf32), FP32 output
+    constexpr int CPC = 128 / (int)sizeof(TIn);                // channels per 128-byte K chunk: 64 (16-bit) or 32 (FP32)
+    static_assert(!TF32 || (CG == 1 && TMAST == 0 && BNS == 0 && EPI == 0), "TF32 variants: single CTA, plain conv epilogue");
     const uint32_t s_w = smem_u32(smem);
     const uint32_t s_a = s_w + W_BYTES;
     const uint32_t s_o = s_a + STAGES * A_STAGE_BYTES;
@@ -399,10 +424,10 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constant__
     auto bar_accempty = [&](int b) { return s_bar + 8u * (NWG + 2 * STAGES + ACC_BUFS + b); };
     uint8_t* misc = smem + W_BYTES + STAGES * A_STAGE_BYTES + O_BYTES;
     uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(misc + 8 * (NWG + 2 * STAGES + 2 * ACC_BUFS));
-    static_assert(8 * (NWG + 2 * STAGES + 2 * ACC_BUFS) + 4 <= 384, "barrier area overflows into the shift vector");
-    float* s_shift = reinterpret_cast<float*>(misc + 384);               // [NOUT] per-channel shift of this CTA's N-slice
+    static_assert(8 * (NWG + 2 * STAGES + 2 * ACC_BUFS) + 4 <= 512, "barrier area overflows into the shift vector");
+    float* s_shift = reinterpret_cast<float*>(misc + 512);               // [NOUT] per-channel shift of this CTA's N-slice
     float* s_wf = s_shift + 128;                                         // [64] final-conv weights (EPI == 2)
-    static_assert(BNS == 0 || (EPI == 0 && (TMAST || stage_cols<TAPS, CHUNKS, NOUT, WP, EPI, TMAST, CG>() > 0)),
+    static_assert(BNS == 0 || (EPI == 0 && (TMAST || stage_cols<TAPS, CHUNKS, NOUT, WP, EPI, TMAST, CG, (int)sizeof(TOut)>() > 0)),
                   "fused BatchNorm reductions read the staged output tile");
 
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
@@ -450,10 +475,10 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constant__
                     if (leader) mbar_expect_tx(bar_w(c * TAPS + t), W_TILE_BYTES * CG);
                     const uint32_t bw = lead(bar_w(c * TAPS + t));
                     if (CG == 2)
-                        tma_load_2d_pair(s_w + (t * CHUNKS + c) * W_TILE_BYTES, &tmW, (t * CHUNKS + c) * 64,
+                        tma_load_2d_pair(s_w + (t * CHUNKS + c) * W_TILE_BYTES, &tmW, (t * CHUNKS + c) * CPC,
                                          n_blk * NOUT + (int)rank * NB, bw);
                     else
-                        tma_load_2d(s_w + (t * CHUNKS + c) * W_TILE_BYTES, &tmW, (t * CHUNKS + c) * 64, n_blk * NOUT, bw);
+                        tma_load_2d(s_w + (t * CHUNKS + c) * W_TILE_BYTES, &tmW, (t * CHUNKS + c) * CPC, n_blk * NOUT, bw);
                 }
         }
         __syncwarp();
@@ -469,12 +494,13 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constant__
                 if (p.dbg) dbg_acc[0] += clock64() - t0;
                 if (elect_one()) {
                     if (leader) mbar_expect_tx(bar_afull(stage), A_STAGE_BYTES * CG);
-                    const bool second = (c == 1) && p.chunk1_src1;
+                    // channel concat: the second half of the K chunks comes from the second tensor map
+                    const bool second = p.chunk1_src1 && (c >= CHUNKS / 2);
+                    const int ccol = (second ? c - CHUNKS / 2 : c) * CPC;
                     if (CG == 2)
-                        tma_load_2d_pair(s_a + stage * A_STAGE_BYTES, second ? &tmA1 : &tmA0, second ? 0 : c * 64, row0,
-                                         lead(bar_afull(stage)));
+                        tma_load_2d_pair(s_a + stage * A_STAGE_BYTES, second ? &tmA1 : &tmA0, ccol, row0, lead(bar_afull(stage)));
                     else
-                        tma_load_2d(s_a + stage * A_STAGE_BYTES, second ? &tmA1 : &tmA0, second ? 0 : c * 64, row0, bar_afull(stage));
+                        tma_load_2d(s_a + stage * A_STAGE_BYTES, second ? &tmA1 : &tmA0, ccol, row0, bar_afull(stage));
                 }
                 __syncwarp();
                 if (++stage == STAGES) { stage = 0; phase ^= 1; }
@@ -522,9 +548,14 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constant__
                         }
 #pragma unroll
                         for (int ks = 0; ks < 4; ++ks) {
-                            umma_f16_lh<CG>(d_tmem, a_lo + ((shift * 128 + ks * 32) >> 4),
-                                            b_lo_base + (((t * CHUNKS + c) * W_TILE_BYTES + ks * 32) >> 4), DESC_HI, IDESC,
-                                            (c | t | ks) ? 1u : 0u);
+                            if constexpr (TF32)
+                                umma_tf32_lh(d_tmem, a_lo + ((shift * 128 + ks * 32) >> 4),
+                                             b_lo_base + (((t * CHUNKS + c) * W_TILE_BYTES + ks * 32) >> 4), DESC_HI, IDESC,
+                                             (c | t | ks) ? 1u : 0u);
+                            else
+                                umma_f16_lh<CG>(d_tmem, a_lo + ((shift * 128 + ks * 32) >> 4),
+                                                b_lo_base + (((t * CHUNKS + c) * W_TILE_BYTES + ks * 32) >> 4), DESC_HI, IDESC,
+                                                (c | t | ks) ? 1u : 0u);
                         }
                     }
                     umma_commit<CG>(bar_aempty(stage));                       // slab reusable once these MMAs retire
@@ -555,7 +586,7 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constant__
         // fused BatchNorm reductions: every lane owns one channel PAIR of each staged fill (64 or 32 channels wide) and
         // walks the rows its own warp staged; partial sums stay in registers for the whole kernel
         constexpr int FW = TMAST ? 64 : (STC > 0 ? STC : 64);               // channels per staged fill
-        constexpr int NF = NOUT / FW;                                        // fills per tile
+        constexpr int NF = NOUT >= FW ? NOUT / FW : 1;                       // fills per tile
         float bs1[NF][2], bs2[NF][2];
 #pragma unroll
         for (int f = 0; f < NF; ++f) { bs1[f][0] = bs1[f][1] = bs2[f][0] = bs2[f][1] = 0.f; }
@@ -693,14 +724,15 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constant__
             }
             // 64 accumulator columns of this row per round trip (4 loads in flight, one wait); the TMEM buffer is handed
             // back to the MMA warp right after the last load, BEFORE the arithmetic / stores of the epilogue
+            constexpr int CQ = NOUT < 64 ? NOUT : 64;              // accumulator columns per round trip
 #pragma unroll
-            for (int cq = 0; cq < NOUT; cq += 64) {
+            for (int cq = 0; cq < NOUT; cq += CQ) {
                 uint32_t racc[4][16];
                 if (cq > 0) bn_prefetch(cq, tile);
 #pragma unroll
-                for (int q = 0; q < 4; ++q) tmem_ld16(taddr + cq + q * 16, racc[q]);
+                for (int q = 0; q < CQ / 16; ++q) tmem_ld16(taddr + cq + q * 16, racc[q]);
                 tmem_ld_wait();
-                if (cq + 64 == NOUT) {
+                if (cq + CQ == NOUT) {
                     tc_fence_before();
                     __syncwarp();
                     if (lane == 0) {
@@ -709,7 +741,7 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constant__
                     }
                 }
 #pragma unroll
-                for (int q = 0; q < 4; ++q) {
+                for (int q = 0; q < CQ / 16; ++q) {
                     const uint32_t* r = racc[q];
                     const int cb = cq + q * 16;
                     float v[16];
@@ -724,6 +756,12 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constant__
                     if (p.relu) {
 #pragma unroll
                         for (int j = 0; j < 16; ++j) v[j] = fmaxf(v[j], 0.f);
+                    }
+                    if (TF32 && p.relu) {
+                        // inference: this activation is the operand of the next TF32 convolution -- store the nearest
+                        // TF32 value instead of letting the tensor core truncate it
+#pragma unroll
+                        for (int j = 0; j < 16; ++j) v[j] = tf32_rn(v[j]);
                     }
                     if (EPI == 2) {
 #pragma unroll
@@ -941,14 +979,15 @@ inline bool available() { return state().ok && state().enabled; }
 template <typename T> struct TmType;
 template <> struct TmType<__half> { static constexpr CUtensorMapDataType v = CU_TENSOR_MAP_DATA_TYPE_FLOAT16; };
 template <> struct TmType<__nv_bfloat16> { static constexpr CUtensorMapDataType v = CU_TENSOR_MAP_DATA_TYPE_BFLOAT16; };
+template <> struct TmType<float> { static constexpr CUtensorMapDataType v = CU_TENSOR_MAP_DATA_TYPE_FLOAT32; };
 
-// 2-D map over a row-major [rows][cols] matrix of 16-bit elements, box = 64 columns x box_rows, 128B swizzle
+// 2-D map over a row-major [rows][cols] matrix, box = 128 bytes of columns (64 16-bit / 32 FP32 elements) x box_rows, 128B swizzle
 template <typename T>
 CUtensorMap make_map_2d(const void* base, uint64_t rows, uint64_t cols, uint32_t box_rows) {
     CUtensorMap m;
     cuuint64_t gdim[2] = {cols, rows};
     cuuint64_t gstride[1] = {cols * sizeof(T)};
-    cuuint32_t box[2] = {64, box_rows};
+    cuuint32_t box[2] = {(cuuint32_t)(128 / sizeof(T)), box_rows};
     cuuint32_t estr[2] = {1, 1};
     CUresult r = state().encode(&m, TmType<T>::v, 2, const_cast<void*>(base), gdim, gstride, box, estr,
                                 CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
@@ -964,12 +1003,12 @@ CUtensorMap make_map_2d(const void* base, uint64_t rows, uint64_t cols, uint32_t
 template <int TAPS, int CHUNKS, int NOUT, int WP, int EPI, int TMAST, typename TIn, typename TOut, int CG = 1, int BNS = 0>
 void launch(cudaStream_t st, const CUtensorMap& a0, const CUtensorMap& a1, const CUtensorMap& w, const CUtensorMap& o,
             const TcParams& p, int n_blocks_y) {
-    constexpr int STAGES = pick_stages<TAPS, CHUNKS, NOUT, WP, EPI, TMAST, CG>();
+    constexpr int STAGES = pick_stages<TAPS, CHUNKS, NOUT, WP, EPI, TMAST, CG, (int)sizeof(TOut)>();
     static_assert(STAGES >= 2, "not enough shared memory for a 2-stage pipeline");
     constexpr int HALO = (TAPS == 9) ? (WP + 1) : 0;
     constexpr int R = ((TC_BM + 2 * HALO + 7) / 8) * 8;
     constexpr size_t smem = 1024 + (size_t)TAPS * CHUNKS * (NOUT / CG) * 128 + (size_t)STAGES * R * 128 +
-                            (size_t)epi_smem_bytes<TAPS, CHUNKS, NOUT, WP, EPI, TMAST, CG>() + 1280;
+                            (size_t)epi_smem_bytes<TAPS, CHUNKS, NOUT, WP, EPI, TMAST, CG, (int)sizeof(TOut)>() + 1280;
     DDPM_CHECK(p.g.Wp == WP && p.g.Hs == WP - 1 && p.g.npos + 2 * TC_BM < (1ll << 31),
                "conv_tc: geometry does not match the kernel's compile-time row width");
     auto kern = conv_tc_kernel<TAPS, CHUNKS, NOUT, WP, STAGES, EPI, TMAST, CG, BNS, TIn, TOut>;
@@ -1043,7 +1082,45 @@ bool conv3x3(cudaStream_t st, const TIn* s0, int C0, const TIn* s1, int C1, cons
              const Geo& g, const float* shift, int relu, const BnFuse* bn = nullptr, bool* bn_done = nullptr) {
     if (bn_done) *bn_done = false;
     if (!available()) return false;
-    if constexpr (sizeof(TIn) != 2 || sizeof(TOut) != 2) {
+    if constexpr (std::is_same<TIn, float>::value && std::is_same<TOut, float>::value) {
+        // TF32 mode: FP32 activations and weights in HBM, tcgen05.mma.kind::tf32, FP32 accumulate and output.  A 128-byte
+        // K chunk is 32 channels; the resident weights of one CTA are capped at 147 KB, so wide layers split Cout
+        // over blockIdx.y (each N-slice re-reads the slab from L2 -- this is the parity mode, not the fast one).
+        const int Cin = C0 + C1, WP = g.Wp;
+        if (s1 && C0 != C1) return false;
+        const uint64_t rows = (uint64_t)g.alloc_positions();
+        TcParams p{};
+        p.out = out; p.out_cs = Cout; p.g = g; p.g_out = g; p.shift = shift; p.relu = relu;
+        p.num_m_tiles = cdiv(g.npos, TC_BM);
+        p.chunk1_src1 = (s1 != nullptr) ? 1 : 0;
+        p.dbg = nullptr;
+        constexpr int R32 = ((TC_BM + 2 * 35 + 7) / 8) * 8, R16 = ((TC_BM + 2 * 19 + 7) / 8) * 8;
+        CUtensorMap a0 = make_map_2d<float>(s0 - (size_t)g.guard * C0, rows, C0, WP == 34 ? R32 : R16);
+        CUtensorMap a1 = a0;
+        if (s1) a1 = make_map_2d<float>(s1 - (size_t)g.guard * C1, rows, C1, WP == 34 ? R32 : R16);
+        if (WP == 34 && Cin == 64 && Cout == 64) {
+            CUtensorMap w = make_map_2d<float>(Wt, 64, 9 * 64, 64);
+            launch<9, 2, 64, 34, 0, 0, float, float>(st, a0, a1, w, a0, p, 1);
+        } else if (WP == 34 && Cin == 128 && Cout == 64) {
+            CUtensorMap w = make_map_2d<float>(Wt, 64, 9 * 128, 32);
+            launch<9, 4, 32, 34, 0, 0, float, float>(st, a0, a1, w, a0, p, 2);
+        } else if (WP == 34 && Cin == 64 && Cout == 128) {
+            CUtensorMap w = make_map_2d<float>(Wt, 128, 9 * 64, 64);
+            launch<9, 2, 64, 34, 0, 0, float, float>(st, a0, a1, w, a0, p, 2);
+        } else if (WP == 18 && Cin == 64 && Cout == 128) {
+            CUtensorMap w = make_map_2d<float>(Wt, 128, 9 * 64, 64);
+            launch<9, 2, 64, 18, 0, 0, float, float>(st, a0, a1, w, a0, p, 2);
+        } else if (WP == 18 && Cin == 128 && Cout == 128) {
+            CUtensorMap w = make_map_2d<float>(Wt, 128, 9 * 128, 32);
+            launch<9, 4, 32, 18, 0, 0, float, float>(st, a0, a1, w, a0, p, 4);
+        } else if (WP == 18 && Cin == 128 && Cout == 64) {
+            CUtensorMap w = make_map_2d<float>(Wt, 64, 9 * 128, 32);
+            launch<9, 4, 32, 18, 0, 0, float, float>(st, a0, a1, w, a0, p, 2);
+        } else {
+            return false;
+        }
+        return true;
+    } else if constexpr (sizeof(TIn) != 2 || sizeof(TOut) != 2) {
         return false;
     } else {
     const int Cin = C0 + C1;

@@ -208,7 +208,7 @@ struct Engine {
     // multiplied by 1/S.  Powers of two when B is: exact.  Keeps FP16 gradients ~3 decades below overflow
     // and the bulk above the subnormal range (measured ranges in DESIGN.md).  1 in FP32 mode.
     float grad_scale(int B) const {
-        const float base = prec == 0 ? 1.f : (float)B * (float)world * (float)HW / 8.f;
+        const float base = (prec == 0 || prec == 3) ? 1.f : (float)B * (float)world * (float)HW / 8.f;
         return std::ldexp(base, (int)opt_loss_scale_log2);
     }
 
@@ -269,8 +269,8 @@ struct Engine {
     ~Engine();
 
     // ---- helpers
-    size_t esz_a() const { return prec == 0 ? 4 : 2; }
-    size_t esz_g() const { return prec == 0 ? 4 : 2; }
+    size_t esz_a() const { return (prec == 0 || prec == 3) ? 4 : 2; }
+    size_t esz_g() const { return (prec == 0 || prec == 3) ? 4 : 2; }
     float* arr(int k) const { return P + offs[k]; }
     float* garr(int k) const { return G + offs[k]; }
     double* lsum(int l) const { return sums + (size_t)l * 384; }
@@ -342,7 +342,7 @@ struct Engine {
 
 #define DDPM_DISPATCH(prec, ...)                                                         \
     do {                                                                                 \
-        if ((prec) == 0) { using TA = float; using TG = float; __VA_ARGS__; }            \
+        if ((prec) == 0 || (prec) == 3) { using TA = float; using TG = float; __VA_ARGS__; } \
         else if ((prec) == 1) { using TA = __half; using TG = __half; __VA_ARGS__; }     \
         else { using TA = __nv_bfloat16; using TG = __nv_bfloat16; __VA_ARGS__; }        \
     } while (0)
@@ -352,7 +352,7 @@ inline Engine::Engine(int T_, int D_, int H_, int W_, int prec_, int dev_)
     DDPM_CHECK(T >= 2 && T <= 100000, "T out of range");
     DDPM_CHECK(D == 128, "only D=128 (the reference's embedding width) is supported");
     DDPM_CHECK(H == 32 && W == 32, "only 32x32 images (the reference's data) are supported");
-    DDPM_CHECK(prec >= 0 && prec <= 2, "precision must be 0 (fp32), 1 (fp16) or 2 (bf16)");
+    DDPM_CHECK(prec >= 0 && prec <= 3, "precision must be 0 (fp32), 1 (fp16), 2 (bf16) or 3 (tf32)");
     int ndev = 0;
     cudaError_t e = cudaGetDeviceCount(&ndev);
     if (e != cudaSuccess || ndev == 0) throw Error("no CUDA device: libddpm has no CPU fallback");
@@ -622,6 +622,7 @@ void Engine::pack_weights_t() {
         const ConvSpec& c = kConv[l];
         J.w[l - 2] = arr(c.w); J.cin[l - 2] = c.cin; J.cout[l - 2] = c.cout;
         J.out_f[l - 2] = Wf[l]; J.out_d[l - 2] = Wd[l]; J.row_scale[l - 2] = nullptr;
+        J.tf32_round = (prec == 3) ? 1 : 0;
         nmax = std::max(nmax, 9LL * c.cin * c.cout);
     }
     pack_conv3_batch_kernel<TA, TG><<<dim3(cdiv(nmax, 256), NUM_CONV - 1, 2), 256, 0, stream>>>(J);
@@ -661,6 +662,7 @@ void Engine::pack_infer_weights_t() {
         const ConvSpec& c = kConv[l];
         J.w[l - 2] = arr(c.w); J.cin[l - 2] = c.cin; J.cout[l - 2] = c.cout;
         J.out_f[l - 2] = Wfi[l]; J.out_d[l - 2] = nullptr; J.row_scale[l - 2] = inf_scale[l];
+        J.tf32_round = (prec == 3) ? 1 : 0;
         nmax = std::max(nmax, 9LL * c.cin * c.cout);
     }
     pack_conv3_batch_kernel<TA, TG><<<dim3(cdiv(nmax, 256), NUM_CONV - 1, 1), 256, 0, stream>>>(J);

@@ -1233,6 +1233,7 @@ struct PackJobs {
     void* out_f[9];
     void* out_d[9];
     const float* row_scale[9];
+    int tf32_round;      // FP32 outputs rounded to the nearest TF32 value (DDPM_PREC_TF32: operands of kind::tf32 MMAs)
 };
 template <typename TA, typename TG>
 __global__ void pack_conv3_batch_kernel(const PackJobs J) {
@@ -1245,11 +1246,15 @@ __global__ void pack_conv3_batch_kernel(const PackJobs J) {
         const int ci = (int)(i % Cin), tap = (int)((i / Cin) % 9), co = (int)(i / (9LL * Cin));
         const int dy = tap / 3 - 1, dx = tap % 3 - 1;
         const float v = w[(1 - dx) + 3 * (1 - dy) + 9LL * ci + 9LL * Cin * co];
-        reinterpret_cast<TA*>(J.out_f[l])[i] = from_f<TA>(J.row_scale[l] ? v * J.row_scale[l][co] : v);
+        float vs = J.row_scale[l] ? v * J.row_scale[l][co] : v;
+        if (J.tf32_round) vs = tf32_rn(vs);
+        reinterpret_cast<TA*>(J.out_f[l])[i] = from_f<TA>(vs);
     } else {
         const int co = (int)(i % Cout), tap = (int)((i / Cout) % 9), ci = (int)(i / (9LL * Cout));
         const int dy = tap / 3 - 1, dx = tap % 3 - 1;
-        reinterpret_cast<TG*>(J.out_d[l])[i] = from_f<TG>(w[(1 + dx) + 3 * (1 + dy) + 9LL * ci + 9LL * Cin * co]);
+        float vd = w[(1 + dx) + 3 * (1 + dy) + 9LL * ci + 9LL * Cin * co];
+        if (J.tf32_round) vd = tf32_rn(vd);
+        reinterpret_cast<TG*>(J.out_d[l])[i] = from_f<TG>(vd);
     }
 }
 // ConvTranspose weight w[a,b,co,ci]:  Wt[q*Cout+co][ci] (fwd, K = ci)  /  Wtd[ci][q*Cout+co] (dgrad, K = q,co)

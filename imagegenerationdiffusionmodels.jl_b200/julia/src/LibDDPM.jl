@@ -10,6 +10,7 @@ const libddpm = get(ENV, "LIBDDPM", joinpath(@__DIR__, "..", "..", "libddpm.so")
 const PREC_FP32 = Cint(0)
 const PREC_FP16 = Cint(1)
 const PREC_BF16 = Cint(2)
+const PREC_TF32 = Cint(3)
 const NUM_ARRAYS = 64
 
 last_error() = unsafe_string(ccall((:ddpm_last_error, libddpm), Cstring, ()))

@@ -32,7 +32,10 @@ typedef struct ddpm_handle ddpm_handle;
 enum {
     DDPM_PREC_FP32 = 0, /* CUDA-core FP32 everywhere (parity/debug mode)                                   */
     DDPM_PREC_FP16 = 1, /* tcgen05 kind::f16, FP16 activations+weights+gradients (loss-scaled), FP32 accum */
-    DDPM_PREC_BF16 = 2  /* tcgen05 kind::f16, BF16 activations+weights+gradients, FP32 accumulate           */
+    DDPM_PREC_BF16 = 2, /* tcgen05 kind::f16, BF16 activations+weights+gradients, FP32 accumulate           */
+    DDPM_PREC_TF32 = 3  /* tcgen05 kind::tf32: FP32 activations+weights in HBM read as TF32 by the 3x3 convolutions
+                           (forward and data gradient), FP32 accumulate; everything else as in FP32 mode: the
+                           tensor-core parity mode (eps_hat within 2e-3 of the FP32 reference)                */
 };
 
 /* number of Float32 arrays ddpm_set_weights / ddpm_get_weights exchange */

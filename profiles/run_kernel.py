@@ -10,7 +10,7 @@ from igdm_b200 import api, capi, tables  # noqa: E402
 
 name, n = sys.argv[1], int(sys.argv[2])
 iters = int(sys.argv[3]) if len(sys.argv) > 3 else 5
-prec = {"fp32": 0, "fp16": 1, "bf16": 2}[sys.argv[4] if len(sys.argv) > 4 else "fp16"]
+prec = {"fp32": 0, "fp16": 1, "bf16": 2, "tf32": 3}[sys.argv[4] if len(sys.argv) > 4 else "fp16"]
 h = capi.Handle(T=500, precision=prec)
 beta, _, acum = tables.beta_schedule(500)
 h.set_tables(beta, acum, tables.embedding_table(500))

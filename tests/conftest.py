@@ -67,7 +67,7 @@ def gpu_handles(model_arrays, tabs):
     if capi.device_count() < 1:
         pytest.skip("no CUDA device")
     hs = {}
-    for name, prec in (("fp32", capi.PREC_FP32), ("fp16", capi.PREC_FP16), ("bf16", capi.PREC_BF16)):
+    for name, prec in (("fp32", capi.PREC_FP32), ("fp16", capi.PREC_FP16), ("bf16", capi.PREC_BF16), ("tf32", capi.PREC_TF32)):
         h = capi.Handle(T=500, precision=prec)
         h.set_tables(tabs["beta"], tabs["acum"], tabs["pe"])
         h.set_weights(model_arrays)

@@ -84,10 +84,11 @@ def test_apply_noise_bit_exact(oracle):
 # ------------------------------------------------------------------------------ forward parity
 # north_star: rel-L2 <= 1e-2.  Bounds are <= 5x what round 1 measured on B200 (fp32 9e-7, fp16 6.6e-4 test / 8.2e-4 train
 # BatchNorm, bf16 5.2e-3 / 6.6e-3): a regression of one order of magnitude fails, and bf16 sits on the north_star bar.
-TOL_EPS = {"fp32": 5e-6, "fp16": 4e-3, "bf16": 1e-2}
+# tf32 = the tensor-core parity mode (tcgen05 kind::tf32 on FP32 tensors): bar 2e-3 (SURVEY.md App. D emulation: 1.1e-3)
+TOL_EPS = {"fp32": 5e-6, "fp16": 4e-3, "bf16": 1e-2, "tf32": 2e-3}
 
 
-@pytest.mark.parametrize("mode", ["fp32", "fp16", "bf16"])
+@pytest.mark.parametrize("mode", ["fp32", "fp16", "bf16", "tf32"])
 @pytest.mark.parametrize("train", [False, True])
 def test_predict_eps_parity(gpu_handles, oracle, model_arrays, dataset, tabs, mode, train):
     h = gpu_handles[mode]
@@ -143,11 +144,11 @@ def test_known_answer_through_abi(gpu_handles, model_arrays, tabs):
 
 # ------------------------------------------------------------------------------ backward parity
 # measured worst per-array rel-L2 (round 1, B200): fp32 8.4e-4, fp16 3.3e-2, bf16 9.1e-2 (forward rounding dominates)
-GRAD_TOL = {"fp32": 2e-3, "fp16": 6e-2, "bf16": 1.5e-1}
-LOSS_TOL = {"fp32": 2e-6, "fp16": 2e-5, "bf16": 1e-3}    # measured 7e-8 / 2e-6 / 1.4e-4 relative
+GRAD_TOL = {"fp32": 2e-3, "fp16": 6e-2, "bf16": 1.5e-1, "tf32": 6e-2}
+LOSS_TOL = {"fp32": 2e-6, "fp16": 2e-5, "bf16": 1e-3, "tf32": 2e-4}    # measured 7e-8 / 2e-6 / 1.4e-4 relative
 
 
-@pytest.mark.parametrize("mode", ["fp32", "fp16", "bf16"])
+@pytest.mark.parametrize("mode", ["fp32", "fp16", "bf16", "tf32"])
 def test_loss_and_grad_parity(gpu_handles, oracle, model_arrays, dataset, tabs, mode):
     h = gpu_handles[mode]
     h.set_weights(model_arrays)

@@ -129,6 +129,21 @@ def test_predict_eps_at_sampler_chunk_size(gpu_handles, oracle, model_arrays, ta
     assert rep["random_t_worst_image"] <= 8e-3 and rep["shared_t_worst_image"] <= 2e-3, rep
 
 
+def test_predict_eps_tf32_at_chunk_size(gpu_handles, oracle, model_arrays, tabs):
+    """TF32 mode at B = 1300 (many tile rounds, every N-split grid) against the CPU oracle: north_star's TF32 bar."""
+    h = gpu_handles["tf32"]
+    h.set_weights(model_arrays)
+    B = 1300
+    rng = np.random.default_rng(13)
+    x = rng.standard_normal((B, 1, 32, 32)).astype(np.float32)
+    ts = rng.integers(1, 501, B)
+    with torch.no_grad():
+        want = oracle.unet_forward(oracle.Net(model_arrays), torch.tensor(x), torch.tensor(tabs["pe"][ts - 1])).numpy()
+    r = rel_l2(h.predict_eps(x, ts), want)
+    _dump("eps_parity_tf32_B1300.json", {"rel_l2": r})
+    assert r <= 2e-3, r
+
+
 def test_sampler_steps_at_chunk_size(gpu_handles, oracle, model_arrays, tabs):
     """Three reverse steps (t = 4, 3, 2: the precision-critical end) on 1300 images through the captured graph,
     host noise, against the oracle's generate_image."""

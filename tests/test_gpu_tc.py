@@ -60,6 +60,7 @@ def test_tc_is_the_default_path(gpu_handles):
     h = gpu_handles["fp16"]
     assert h.counter("uses_tc") == 1
     assert gpu_handles["fp32"].counter("uses_tc") == 0
+    assert gpu_handles["tf32"].counter("uses_tc") == 1
 
 
 def test_fused_final_epilogue_matches_unfused(gpu_handles, model_arrays):
@@ -159,3 +160,48 @@ def test_first_conv_on_tensor_cores_matches_cuda_core_kernel(gpu_handles, model_
     # a small output after cancellation may take (tests/test_split_arithmetic.py)
     assert rep["frac_mismatch"] < 0.03 and rep["max_err_ulp"] <= 2.0, rep
     assert rep["sampler_max_abs_diff"] < 1e-3, rep
+
+
+def test_tf32_mode_matches_fp32_mode_per_layer(gpu_handles, oracle, model_arrays, dataset, tabs):
+    """DDPM_PREC_TF32: the 3x3 convolutions on tcgen05 kind::tf32 (FP32 tensors in HBM, 32-channel K chunks, Cout split over
+    blockIdx.y) against the CUDA-core FP32 mode of the same library, every intermediate tensor of a train-mode forward,
+    the sampler and the data gradients (B = 9: ragged last tile)."""
+    hf, ht = gpu_handles["fp32"], gpu_handles["tf32"]
+    for h in (hf, ht):
+        h.set_weights(model_arrays)
+    B = 9
+    x0, ts, eps = config2_batch(dataset, B)
+    xt = oracle.q_sample(x0, ts, eps, tabs["acum"])
+    ref, got = _layers(hf, xt, ts), _layers(ht, xt, ts)
+    rep = {nm: rel_l2(got[nm], ref[nm]) for nm in NAMES}
+    lf, gf = hf.loss_and_grad(x0, ts, eps)
+    lt, gt = ht.loss_and_grad(x0, ts, eps)
+    rep["loss_rel"] = abs(lf - lt) / lf
+    rep["grads"] = {k: rel_l2(gt[k], gf[k]) for k in (0, 6, 12, 18, 24, 30, 36, 38, 44, 50, 56, 62)}
+    xT = np.random.default_rng(0).standard_normal((3, 1, 32, 32)).astype(np.float32)
+    z = np.random.default_rng(1).standard_normal((9, 3, 1, 32, 32)).astype(np.float32)
+    rep["sampler_max_abs_diff"] = float(np.abs(hf.sample(3, x_T=xT, z=z, t_start=10) - ht.sample(3, x_T=xT, z=z, t_start=10)).max())
+    _dump("tf32_vs_fp32.json", rep)
+    assert max(rep[nm] for nm in NAMES) < 3e-3, rep          # TF32 operand rounding: 2^-11 relative per product
+    assert rep["loss_rel"] < 3e-4 and max(rep["grads"].values()) < 8e-2, rep      # measured 6e-5 / 3.2e-2 (B = 9)
+    assert rep["sampler_max_abs_diff"] < 2e-2, rep
+
+
+def test_inference_is_bitwise_repeatable(gpu_handles, model_arrays):
+    """compute-sanitizer is closed on this pool (it left GPUs needing a reset), so data races in the mbarrier / TMEM /
+    cluster pipelines are hunted the cheap way: the inference path has no atomics, so every kernel must be bit-for-bit
+    repeatable -- 12 evaluations of a ragged batch and 3 runs of a 20-step sampler must agree exactly."""
+    h = gpu_handles["fp16"]
+    h.set_weights(model_arrays)
+    rng = np.random.default_rng(8)
+    x = rng.standard_normal((37, 1, 32, 32)).astype(np.float32)
+    ts = rng.integers(1, 501, 37)
+    first = h.predict_eps(x, ts)
+    for _ in range(11):
+        assert np.array_equal(h.predict_eps(x, ts), first)
+    shared = h.predict_eps(x, np.full(37, 250))
+    for _ in range(5):
+        assert np.array_equal(h.predict_eps(x, np.full(37, 250)), shared)
+    a = h.sample(300, seed=3, first_index=0, t_start=21)
+    for _ in range(2):
+        assert np.array_equal(h.sample(300, seed=3, first_index=0, t_start=21), a)
