@@ -115,27 +115,36 @@ conv1_tc_kernel(const __grid_constant__ CUtensorMap tmO, const C1Params p) {
     if (warp < 4) {
         // ================= A-tile builders: thread r writes row r of every tile this CTA owns =================
         const int r = threadIdx.x;
-        // the nine taps of position (tile, r); halo / out-of-image taps read as zero
-        auto load_taps = [&](int tile, float v[9]) {
-            const int pos = tile * TC_BM + r;
-            const int pr = pos / WP, pc = pos - pr * WP;
-            const int n = pr / HS, prr = pr - n * HS;
-            const int h = prr - 1, w = pc - 1;
-            const bool valid = tile < p.num_tiles && pos < npos && prr != 0 && pc >= 1 && pc <= W && n < p.g.N;
+        // The nine taps of output row r are nine entries of ONE window of the zero-padded position space:
+        //   tap(dy,dx) = Xp[r + 35 + dy*34 + dx],   Xp[j] = padded image value at position tile*128 - 35 + j, j < 198.
+        // The first version fetched them with 9 bounds-checked global loads per thread (1152 per tile); ncu's source
+        // view showed the builders latency-bound on exactly those loads with every other warp idle on its barrier.
+        // Now the 128 builder threads fetch the 198 window entries once (<= 2 loads per thread, two tiles ahead),
+        // publish them in a double-buffered shared-memory window and read their taps from there.
+        float* s_xp = s_E + 9 * 64;                               // [2][208] window buffers
+        auto load_window = [&](int tile, float v[2]) {
 #pragma unroll
-            for (int k = 0; k < 9; ++k) {
-                const int hh = h + k / 3 - 1, ww = w + k % 3 - 1;
-                const bool in = valid && hh >= 0 && hh < H && ww >= 0 && ww < W;
-                v[k] = in ? __ldg(p.x + ((long long)n * H + hh) * W + ww) : 0.f;
+            for (int q = 0; q < 2; ++q) {
+                const int jdx = r + q * TC_BM;
+                const int pos = tile * TC_BM - (WP + 1) + jdx;
+                const int pr = pos / WP, pc = pos - pr * WP;
+                const int n = pr / HS, prr = pr - n * HS;
+                const bool in = jdx < TC_BM + 2 * (WP + 1) && tile < p.num_tiles && pos >= 0 && pos < npos && prr != 0 && pc >= 1 &&
+                                pc <= W && n < p.g.N;
+                v[q] = in ? __ldg(p.x + ((long long)n * H + (prr - 1)) * W + (pc - 1)) : 0.f;
             }
         };
-        // The builders are the critical path of this kernel and they are latency-bound on the tap loads (ncu source
-        // view, round 2: 31 % of all stall samples on the first use of a prefetched tap, epilogue and MMA warps idle on
-        // their barriers): the taps of TWO tiles ahead are kept in flight, in three register sets that rotate through a
-        // 3x unrolled loop (a register copy of a pending load would stall on it just like its first use).
-        float vs[3][9];
-        load_taps(blockIdx.x, vs[0]);
-        load_taps(blockIdx.x + gridDim.x, vs[1]);
+        auto load_taps_from_window = [&](const float w2[2], int it, float v[9]) {
+            float* xp = s_xp + (it & 1) * 208;
+            xp[r] = w2[0];
+            if (r + TC_BM < 208) xp[r + TC_BM] = w2[1];
+            named_bar_sync(4, 128);                                // the four builder warps only
+#pragma unroll
+            for (int k = 0; k < 9; ++k) v[k] = xp[r + (WP + 1) + (k / 3 - 1) * WP + (k % 3 - 1)];
+        };
+        float ws[3][2];
+        load_window(blockIdx.x, ws[0]);
+        load_window(blockIdx.x + gridDim.x, ws[1]);
         auto pack_tile = [&](const float v[9], int it) {
             const int stage = it % C1_STAGES;
             const uint32_t phase = (uint32_t)(it / C1_STAGES) & 1u;
@@ -163,8 +172,10 @@ conv1_tc_kernel(const __grid_constant__ CUtensorMap tmO, const C1Params p) {
 #pragma unroll
             for (int u = 0; u < 3; ++u) {
                 if (tile < p.num_tiles) {
-                    load_taps(tile + 2 * gridDim.x, vs[(u + 2) % 3]);      // in flight while this tile and the next are packed
-                    pack_tile(vs[u], it);
+                    load_window(tile + 2 * gridDim.x, ws[(u + 2) % 3]);     // in flight while this tile and the next are packed
+                    float v[9];
+                    load_taps_from_window(ws[u], it, v);
+                    pack_tile(v, it);
                     tile += gridDim.x; ++it;
                 }
             }
@@ -273,7 +284,7 @@ bool conv1_shared_t(cudaStream_t st, const float* x, const float* Wimg, const fl
     p.x = x; p.Wimg = Wimg; p.Ecls_t = Ecls_t; p.scale = scale; p.shift = shift; p.relu = relu; p.g = g;
     p.num_tiles = cdiv(g.npos, TC_BM);
     CUtensorMap o = make_map_2d<TOut>(out - (size_t)g.guard * 64, (uint64_t)g.alloc_positions(), 64, TC_BM);
-    constexpr size_t smem = 1024 + 64 * 128 + (size_t)C1_STAGES * TC_BM * 128 + 2 * TC_BM * 64 * 2 + 256 + 9 * 64 * 4 + 256;
+    constexpr size_t smem = 1024 + 64 * 128 + (size_t)C1_STAGES * TC_BM * 128 + 2 * TC_BM * 64 * 2 + 256 + 9 * 64 * 4 + 2 * 208 * 4 + 256;
     auto kern = conv1_tc_kernel<TOut>;
     ensure_smem_attr(kern, smem);
     int ctas = state().num_sms;

@@ -11,6 +11,7 @@
 #include <cstring>
 #include <dlfcn.h>
 #include <nccl.h>
+#include <nvtx3/nvToolsExt.h>      // header-only NVTX v3: ranges cost ~nothing unless a profiler is attached
 #include "common.cuh"
 #include "kernels.cuh"
 #include "igemm_simt.cuh"
@@ -19,6 +20,19 @@
 #include "l1_bwd.cuh"
 
 namespace ddpm {
+
+// NVTX range around the launches of one layer / phase (visible in Nsight Systems / ncu --nvtx as fwd.L3, bwd.L7, ...)
+struct NvtxRange {
+    explicit NvtxRange(const char* name) { nvtxRangePushA(name); }
+    NvtxRange(const char* prefix, int l) {
+        char buf[32];
+        snprintf(buf, sizeof buf, "%s%d", prefix, l);
+        nvtxRangePushA(buf);
+    }
+    ~NvtxRange() { nvtxRangePop(); }
+    NvtxRange(const NvtxRange&) = delete;
+    NvtxRange& operator=(const NvtxRange&) = delete;
+};
 
 constexpr int NUM_ARRAYS = 64;
 constexpr int NUM_CONV = 10;  // 3x3 convs followed by BatchNorm(relu)
@@ -738,6 +752,7 @@ inline tc::BnFuse Engine::bn_bwd_fuse(ActSet& s, int bn_layer) {
 // layer; the epilogue then also accumulates the first pass of that BatchNorm's backward (*bn_done reports it).
 template <typename TA, typename TG>
 void Engine::dgrad3(ActSet& s, const Tensor& dy, int l, Tensor& out, int out_c_total, int bn_layer, bool* bn_done) {
+    NvtxRange r("bwd.dgrad.L", l);
     const ConvSpec& c = kConv[l];
     const Geo& g = out.g;
     if (bn_done) *bn_done = false;
@@ -804,6 +819,7 @@ void Engine::forward_t(ActSet& s, const float* x_dev, const int* ts_dev, int t_f
         cnt_launches += 2;
     };
     auto layer = [&](int l, const Tensor& in0, const Tensor* in1) {
+        NvtxRange r(train ? "fwd.train.L" : "fwd.infer.L", l);
         const ConvSpec& c = kConv[l];
         if (train) {
             conv3<TA, TG>(in0, in1, l, s.y[l], false, arr(c.b), 0, lsum(l));
@@ -815,6 +831,7 @@ void Engine::forward_t(ActSet& s, const float* x_dev, const int* ts_dev, int t_f
 
     // ---- down1.conv1 (+ folded embedding)
     {
+        NvtxRange r(train ? "fwd.train.L" : "fwd.infer.L", 1);
         const ConvSpec& c = kConv[1];
         long long pixels = (long long)N * HW;
         Tensor& o = train ? s.y[1] : s.a[1];
@@ -845,6 +862,7 @@ void Engine::forward_t(ActSet& s, const float* x_dev, const int* ts_dev, int t_f
     layer(6, s.a[5], nullptr);
     // ---- ConvTranspose((2,2), 128=>64, stride=2): GEMM [pos16][128] x [128][4*64] + pixel shuffle
     {
+        NvtxRange r("fwd.convT");
         const Geo& gi = s.a[6].g;
         const Geo& go = s.u.g;
         bool done = false;
@@ -948,6 +966,7 @@ void Engine::backward_t(ActSet& s, const float* xt_dev, const int* ts_dev, const
     // BatchNorm(relu) backward of layer l: da (view) -> dy tensor
     // have_sums: the kernel that produced da already accumulated sum g, sum g*xhat into lsum(l) (fused epilogue)
     auto bn_bwd = [&](int l, View<const TG> da, Tensor& dy, bool have_sums) {
+        NvtxRange r("bwd.bn.L", l);
         const ConvSpec& c = kConv[l];
         const Geo& g = s.y[l].g;
         long long pixels = (long long)N * c.hw * c.hw;
@@ -991,6 +1010,7 @@ void Engine::backward_t(ActSet& s, const float* xt_dev, const int* ts_dev, const
     };
     // weight gradient of a 3x3 conv: dW[co][tap][ci] = sum_p dy[p][co] * x[p + shift(tap)][ci]
     auto wgrad = [&](int l, const Tensor& dy, const Tensor& x, int ci_off) {
+        NvtxRange r("bwd.wgrad.L", l);
         const ConvSpec& c = kConv[l];
         const Geo& g = dy.g;
         bool done = false;
@@ -1134,6 +1154,7 @@ void Engine::backward_t(ActSet& s, const float* xt_dev, const int* ts_dev, const
 // gathered through s.idx), s.ts, s.eps -- host-supplied, or drawn here from Philox keyed by d_trng = [seed, first
 // global image index, step].  Nothing in here depends on a host-side per-step scalar, so the sequence can be captured.
 inline void Engine::train_enqueue(ActSet& s, bool gather, bool device_draws, bool update) {
+    NvtxRange r("train_step");
     const int B = s.N;
     const float* x0 = gather ? d_dataset.as<float>() : s.x0.as<float>();
     const int* idx = gather ? s.idx.as<int>() : nullptr;
@@ -1159,6 +1180,7 @@ inline void Engine::train_enqueue(ActSet& s, bool gather, bool device_draws, boo
     cnt_launches += 1;
     DDPM_DISPATCH(prec, (backward_t<TA, TG>(s, s.xt.as<float>(), s.ts.as<int>(), s.deps.as<float>(), 1.f / gs)));
     if (update) {
+        NvtxRange ra("adam");
         // overflow guard of the 16-bit gradient tensors: a non-finite value anywhere in the (all-reduced) gradient
         // skips the update (weights and moments untouched, beta^t not advanced) and bumps a counter
         grad_check_kernel<<<cdiv(n_params, 1024), 256, 0, stream>>>(G, n_params, d_tstate);
@@ -1240,6 +1262,7 @@ inline void Engine::train_core(ActSet& s, bool gather, bool device_draws, bool u
 template <typename TA, typename TG>
 void Engine::sample_steps_t(ActSet& s, float* x_dev, const float* z_dev, int N, int t_start) {
     for (int t = t_start, k = 0; t >= 2; --t, ++k) {
+        NvtxRange r("reverse_step");
         const float* zstep = z_dev ? z_dev + (size_t)k * N * HW : nullptr;
         if (!zstep) {
             // fresh noise of this step, Philox keyed by (seed, global image index, t): one fully parallel
