@@ -592,17 +592,20 @@ int ddpm_time_kernel(ddpm_handle* h, const char* name, int64_t n_images, int ite
             time_it([&] { e.forward(s, s.x.as<float>(), nullptr, e.T / 2, Mode::Infer, false); });
             fl = 735.31e6 * N;
         } else if (k == "reverse_update") {
+            // the stand-alone final 1x1 conv + reverse update exactly as the sampler launches it when the fused
+            // epilogue is off (FP32 / TF32 modes, option fuse_final=0): noise of the step pre-generated in s.zstep
             const float* sc = &e.h_samp[(size_t)(e.T / 2) * 4];
             unsigned long long rng[2] = {7ull, 0ull};
-            DDPM_CUDA(cudaMemcpyAsync(e.d_rng, rng, sizeof rng, cudaMemcpyHostToDevice, e.stream));
+            DDPM_CUDA(cudaMemcpyAsync(s.rng.p, rng, sizeof rng, cudaMemcpyHostToDevice, e.stream));
+            randn_dev_kernel<<<cdiv(n4, 256), 256, 0, e.stream>>>(s.zstep.as<float>(), N, HW, s.rng.as<unsigned long long>(), 5u);
             DDPM_DISPATCH(e.prec, time_it([&] {
                 long long work = (long long)N * HW * 8;
                 final_conv_kernel<TA><<<cdiv(work, 256), 256, 0, e.stream>>>(
-                    s.a[10].cview<TA>(), s.a[10].g, e.arr(kFinalW), e.arr(kFinalB), nullptr, 1, s.x.as<float>(), nullptr,
-                    make_float4(sc[0], sc[1], sc[2], sc[3]), e.d_rng, 5u, 0);
+                    s.a[10].cview<TA>(), s.a[10].g, e.arr(kFinalW), e.arr(kFinalB), nullptr, 1, s.x.as<float>(), s.zstep.as<float>(),
+                    make_float4(sc[0], sc[1], sc[2], sc[3]), s.rng.as<unsigned long long>(), 5u, 0);
             }));
-            // reads a10 (64 ch) + x, writes x; z is generated in registers
-            by = (double)N * HW * (64.0 * e.esz_a() + 8.0);
+            // reads a10 (64 ch), x and z, writes x
+            by = (double)N * HW * (64.0 * e.esz_a() + 12.0);
         } else if (k == "conv1" || k == "pool" || k == "up2") {
             DDPM_DISPATCH(e.prec, time_it([&] {
                 if (k == "conv1") {
