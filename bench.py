@@ -287,10 +287,9 @@ def run_workload(args, workload, h, td, rank, world, local, peaks, N, t_start, e
         o_host = torch.empty((NE, 1024), dtype=torch.float32, pin_memory=True)
         x_host.normal_(generator=torch.Generator().manual_seed(1 + rank))
         xin, oout = x_host.numpy(), o_host.numpy()
-        # warm-up: same balanced chunk size as the big call (ceil(NE / ceil(NE / chunk))), two chunks of it
-        kch = -(-NE // args.chunk)
-        bal = -(-NE // kch)
-        nw = min(NE, 2 * bal)
+        # warm-up: the chunk sizes of the big call (full chunks + the remainder chunk, see sample_impl in csrc/libddpm.cu)
+        rem = NE % args.chunk
+        nw = min(NE, args.chunk + rem) if (NE > args.chunk and rem * 4 >= args.chunk) else min(NE, 2 * args.chunk)
         h.sample(nw, x_T=xin[:nw], seed=args.seed, first_index=0, t_start=t_start, out=oout[:nw])
         barrier(td, local)
         t0 = time.perf_counter()

@@ -302,13 +302,15 @@ static void sample_impl(Engine& e, const float* x_T, const float* z, uint64_t se
     DDPM_CHECK(t_start >= 1 && t_start <= e.T, "t_start out of range 1..T");
     const int HW = e.HW;
     const int steps = t_start - 1;
-    // balanced chunks: ceil(N / ceil(N / sample_chunk)) images each, so a batch slightly over the chunk size does not
-    // leave a small, poorly filled last chunk (Philox noise is keyed by the global image index: chunking never
-    // changes the images)
+    // Chunking (Philox noise is keyed by the global image index: chunking never changes the images).  The chunk size
+    // is chosen so that the persistent conv kernels' tile rounds come out even (1300 images), so a large batch is cut
+    // into FULL chunks plus one remainder chunk; only when the remainder would be small (< 1/4 chunk: poorly filled
+    // launches) the batch is cut into equal chunks instead.
     long long chunk = std::max<long long>(1, std::min<long long>(e.opt_sample_chunk, N));
     {
         const long long k = (N + chunk - 1) / chunk;
-        chunk = (N + k - 1) / k;
+        const long long rem = N - (k - 1) * chunk;
+        if (k > 1 && rem * 4 < chunk) chunk = (N + k - 1) / k;
     }
     if (keep_on_device) e.d_sample_out.ensure((size_t)N * HW * 4);
     // derived weights / tables are refreshed once on the main stream; the chunk streams wait for that
