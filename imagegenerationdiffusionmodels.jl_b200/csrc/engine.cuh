@@ -271,7 +271,8 @@ struct Engine {
 
     // options / counters
     long long opt_sample_streams = 1;
-    long long opt_conv1_tc = 1;    // sampler: first conv on tensor cores (hi/lo split operands) when the batch shares one timestep
+    long long opt_conv1_tc = 2;    // sampler: first conv on tensor cores (hi/lo split operands) when the batch shares one timestep;
+                                   // 2 = (timestep, border class) constants folded into the contraction as well, 1 = added in the epilogue
     // images per captured reverse-loop graph.  1300 images fill the persistent conv kernels' tile rounds exactly
     // (32x32 layers: 77.0 rounds of 74 CTA-pair tiles, 16x16 layers: 21.0) -- 512 left the 16x16 layers at 92 %
     long long opt_sample_chunk = 1300, opt_use_graph = 1, opt_conv_impl = 0 /*0 auto, 1 simt, 2 tc*/, opt_fuse_final = 1;
@@ -838,7 +839,7 @@ void Engine::forward_t(ActSet& s, const float* x_dev, const int* ts_dev, int t_f
         bool done = false;
         if (!train && !ts_dev && opt_conv1_tc && use_tc())
             done = tc::conv1_shared_t<TA>(stream, x_dev, Wimg, Ecls + (long long)(t_fixed - 1) * 9 * 64, inf_scale[1],
-                                          inf_shift[1], 1, o.pos0<TA>(), o.g);
+                                          inf_shift[1], 1, o.pos0<TA>(), o.g, opt_conv1_tc >= 2);
         if (!done) {
             conv1_kernel<TA><<<cdiv(pixels, CONV1_PIX_PER_BLOCK), 256, 0, stream>>>(x_dev, ts_dev, t_fixed, Wimg, Ecls,
                                                               train ? nullptr : inf_scale[1], train ? arr(c.b) : inf_shift[1],

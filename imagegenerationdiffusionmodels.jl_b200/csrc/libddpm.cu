@@ -530,6 +530,19 @@ int ddpm_timer_stop(ddpm_handle* h, float* ms) {
     API_END
 }
 
+static __global__ void probe_fill_kernel(uint4* p, long long n16, uint32_t v) {
+    for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < n16; i += (long long)gridDim.x * blockDim.x)
+        p[i] = make_uint4(v, v, v, v);
+}
+static __global__ void probe_read_kernel(const uint4* p, long long n16, double* sink) {
+    uint32_t acc = 0;
+    for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < n16; i += (long long)gridDim.x * blockDim.x) {
+        const uint4 v = __ldcs(p + i);
+        acc ^= v.x ^ v.y ^ v.z ^ v.w;
+    }
+    if (acc == 0x12345678u) *sink = 1.0;      // never true for the fill pattern; keeps the loads alive
+}
+
 int ddpm_time_kernel(ddpm_handle* h, const char* name, int64_t n_images, int iters, float* ms, double* bytes, double* flops) {
     API_BEGIN
     Engine& e = E(h);
@@ -608,6 +621,19 @@ int ddpm_time_kernel(ddpm_handle* h, const char* name, int64_t n_images, int ite
             }));
             // reads a10 (64 ch), x and z, writes x
             by = (double)N * HW * (64.0 * e.esz_a() + 12.0);
+        } else if (k == "probe_fill" || k == "probe_read") {
+            // bandwidth probes on a scratch buffer of the size of one 32x32x64 activation tensor: a pure write stream and
+            // a pure read stream (what a write-bound / read-bound kernel of the sampler can reach at best)
+            DevBuf sc;
+            const size_t nb = s.a[1].bytes;
+            sc.ensure(nb);
+            const long long n16 = (long long)(nb / 16);
+            const int blocks = tc::state().num_sms * 8;
+            if (k == "probe_fill") time_it([&] { probe_fill_kernel<<<blocks, 512, 0, e.stream>>>(sc.as<uint4>(), n16, 0x3c003c00u); });
+            else time_it([&] { probe_read_kernel<<<blocks, 512, 0, e.stream>>>(sc.as<uint4>(), n16, e.misc_sums); });
+            DDPM_CUDA(cudaStreamSynchronize(e.stream));
+            sc.release();
+            by = (double)nb;
         } else if (k == "conv1" || k == "pool" || k == "up2") {
             DDPM_DISPATCH(e.prec, time_it([&] {
                 if (k == "conv1") {
@@ -616,7 +642,7 @@ int ddpm_time_kernel(ddpm_handle* h, const char* name, int64_t n_images, int ite
                     if (e.opt_conv1_tc && e.use_tc())
                         done = tc::conv1_shared_t<TA>(e.stream, s.x.as<float>(), e.Wimg,
                                                       e.Ecls + (long long)(e.T / 2 - 1) * 9 * 64, e.inf_scale[1], e.inf_shift[1],
-                                                      1, s.a[1].pos0<TA>(), s.a[1].g);
+                                                      1, s.a[1].pos0<TA>(), s.a[1].g, e.opt_conv1_tc >= 2);
                     if (!done)
                         conv1_kernel<TA><<<cdiv(pixels, CONV1_PIX_PER_BLOCK), 256, 0, e.stream>>>(
                             s.x.as<float>(), nullptr, e.T / 2, e.Wimg, e.Ecls, e.inf_scale[1], e.inf_shift[1], 1,

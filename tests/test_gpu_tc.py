@@ -126,8 +126,10 @@ def test_cta_pair_convs_match_single_cta_convs(gpu_handles, oracle, model_arrays
     assert rep["sampler_max_abs_diff"] == 0.0, rep
 
 
-def test_first_conv_on_tensor_cores_matches_cuda_core_kernel(gpu_handles, model_arrays):
-    """conv1_tc.cuh (BF16 hi/lo split operands on tcgen05, FP32 accumulate) against the FP32 CUDA-core first conv on
+@pytest.mark.parametrize("mode", [2, 1])
+def test_first_conv_on_tensor_cores_matches_cuda_core_kernel(gpu_handles, model_arrays, mode):
+    """conv1_tc.cuh (BF16 hi/lo split operands on tcgen05, FP32 accumulate; mode 2 = default: the timestep constants ride
+    on the contraction as three BF16 parts, mode 1: added in the epilogue) against the FP32 CUDA-core first conv on
     the same device-resident input: the stored FP16 activation may differ by one rounding step in a few elements
     (the split keeps 16 significand bits per operand), never by more; the sampler output moves by < 1e-3."""
     h = gpu_handles["fp16"]
@@ -139,22 +141,22 @@ def test_first_conv_on_tensor_cores_matches_cuda_core_kernel(gpu_handles, model_
     rep = {}
     try:
         out = {}
-        for m in (0, 1):
+        for m in (0, mode):
             h.set_option("conv1_tc", m)
             out[m] = h.sample(n, x_T=xT, z=z, t_start=6)
         # the layer alone: ddpm_time_kernel("conv1") refills the set's x with the same Philox normals on every call and
         # leaves the first conv's output in the (otherwise aliased) a1 buffer
         h.set_option("conv1_tc", 0); h.time_kernel("conv1", n, 1); ref = h.debug_fetch("infer:a1")
-        h.set_option("conv1_tc", 1); h.time_kernel("conv1", n, 1); got = h.debug_fetch("infer:a1")
+        h.set_option("conv1_tc", mode); h.time_kernel("conv1", n, 1); got = h.debug_fetch("infer:a1")
         d = np.abs(got - ref)
         # one FP16 rounding step of the reference value, floored at 2e-5 absolute (values that straddle the ReLU zero)
         ulp = np.maximum(2.0 ** (np.floor(np.log2(np.maximum(np.abs(ref), 2.0 ** -14))) - 10), 2e-5)
         rep = {"frac_mismatch": float(np.mean(d > 0)), "max_err_ulp": float((d / ulp).max()),
                "max_abs_a1": float(np.abs(ref).max()), "frac_nonzero": float(np.mean(ref != 0)),
-               "sampler_max_abs_diff": float(np.abs(out[0] - out[1]).max())}
+               "sampler_max_abs_diff": float(np.abs(out[0] - out[mode]).max())}
     finally:
-        h.set_option("conv1_tc", 1)
-        _dump("conv1_tc_vs_simt.json", rep)
+        h.set_option("conv1_tc", 2)
+        _dump(f"conv1_tc{mode}_vs_simt.json", rep)
     assert rep["max_abs_a1"] > 0.1 and rep["frac_nonzero"] > 0.2, rep     # the layer really ran on real data
     # measured: 0.27 % of the elements differ, all by exactly one rounding step; the bound allows the second step that
     # a small output after cancellation may take (tests/test_split_arithmetic.py)
