@@ -271,6 +271,7 @@ struct Engine {
 
     // options / counters
     long long opt_sample_streams = 1;
+    long long opt_bnbwd_blocks = 4; // resident blocks per SM of the second BatchNorm-backward pass
     long long opt_conv1_tc = 2;    // sampler: first conv on tensor cores (hi/lo split operands) when the batch shares one timestep;
                                    // 2 = (timestep, border class) constants folded into the contraction as well, 1 = added in the epilogue
     // images per captured reverse-loop graph.  1300 images fill the persistent conv kernels' tile rounds exactly
@@ -971,7 +972,7 @@ void Engine::backward_t(ActSet& s, const float* xt_dev, const int* ts_dev, const
         const ConvSpec& c = kConv[l];
         const Geo& g = s.y[l].g;
         long long pixels = (long long)N * c.hw * c.hw;
-        int blocks = stride_blocks(pixels, BNB_PIX_PER_BLOCK, tc::state().num_sms, 3);
+        int blocks = stride_blocks(pixels, BNB_PIX_PER_BLOCK, tc::state().num_sms, (int)opt_bnbwd_blocks);
         double m = count_local * c.hw * c.hw;
         if (!have_sums) {
             bn_reduce_linear_kernel<TA, TG, 1><<<lin_reduce_blocks(g.npos, tc::state().num_sms), 256, 0, stream>>>(

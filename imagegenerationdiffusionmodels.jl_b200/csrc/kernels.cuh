@@ -601,7 +601,7 @@ static inline int stride_blocks(long long items, int per_block, int num_sms, int
 }
 
 template <typename TA, typename TG, int PASS>
-__global__ void __launch_bounds__(256)
+__global__ void __launch_bounds__(256, PASS == 2 ? 4 : 2)
 bn_bwd_kernel(View<const TA> y, View<const TG> da, View<TG> dy, Geo g, int C, const float* __restrict__ scale,
               const float* __restrict__ shift, const float* __restrict__ mean, const float* __restrict__ istd,
               const float* __restrict__ mg, const float* __restrict__ mgx, double* __restrict__ sums) {
@@ -613,12 +613,20 @@ bn_bwd_kernel(View<const TA> y, View<const TG> da, View<TG> dy, Geo g, int C, co
     const int lanes = 256 / groups;
     const int c0 = (t % groups) * 8, pl = t / groups;
     const long long total = (long long)g.N * g.H * g.W;
-    float sc[8], sh[8], mu[8], is[8], a0[8], a1[8], r0[8], r1[8];
+    // PASS 2 keeps four blocks per SM resident (<= 64 registers): dy = scale*(g - mg - xhat*mgx) with xhat = (y - mean)*istd
+    // is evaluated as  g*scale + (y*k1 + k0),  k1 = -scale*istd*mgx,  k0 = scale*(mean*istd*mgx - mg)
+    float sc[8], sh[8], mu[8], is[8], r0[8], r1[8];
 #pragma unroll
     for (int j = 0; j < 8; ++j) {
-        sc[j] = scale[c0 + j]; sh[j] = shift[c0 + j]; mu[j] = mean[c0 + j]; is[j] = istd[c0 + j];
+        sc[j] = scale[c0 + j]; sh[j] = shift[c0 + j];
         r0[j] = 0.f; r1[j] = 0.f;
-        if (PASS == 2) { a0[j] = mg[c0 + j]; a1[j] = mgx[c0 + j]; }
+        if (PASS == 2) {
+            const float m_ = mean[c0 + j], i_ = istd[c0 + j], a0 = mg[c0 + j], a1 = mgx[c0 + j];
+            mu[j] = -sc[j] * i_ * a1;                        // k1
+            is[j] = sc[j] * (m_ * i_ * a1 - a0);             // k0
+        } else {
+            mu[j] = mean[c0 + j]; is[j] = istd[c0 + j];
+        }
     }
     const int HW = g.H * g.W;
     const long long nchunks = (total + BNB_PIX_PER_BLOCK - 1) / BNB_PIX_PER_BLOCK;
@@ -638,11 +646,11 @@ bn_bwd_kernel(View<const TA> y, View<const TG> da, View<TG> dy, Geo g, int C, co
             for (int j = 0; j < 8; ++j) {
                 float z = fmaf(yv[j], sc[j], sh[j]);
                 float gg = z > 0.f ? gv[j] : 0.f;
-                float xh = (yv[j] - mu[j]) * is[j];
                 if (PASS == 1) {
+                    float xh = (yv[j] - mu[j]) * is[j];
                     r0[j] += gg; r1[j] += gg * xh;
                 } else {
-                    float d = sc[j] * (gg - a0[j] - xh * a1[j]);
+                    float d = fmaf(gg, sc[j], fmaf(yv[j], mu[j], is[j]));
                     o[j] = d; r0[j] += d;
                 }
             }
