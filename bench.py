@@ -363,7 +363,8 @@ def run_workload(args, workload, h, td, rank, world, local, peaks, N, t_start, e
     #      51% of the U-Net FLOPs), timed alone with CUDA events on the engine's stream
     chunk = min(args.chunk, N)
     kern = {}
-    for name in ("conv_l2", "conv_l4", "conv_l9", "conv_l3", "conv1", "pool", "up2", "reverse_update", "qsample", "mse", "adam"):
+    for name in ("conv_l2", "conv_l4", "conv_l9", "conv_l3", "conv1", "pool", "up2", "reverse_update", "qsample", "mse", "adam",
+                 "probe_fill", "probe_read"):
         if workload == "train" and args.workload == "both":
             break   # already measured in the sampling pass of this run
         try:
@@ -383,9 +384,14 @@ def run_workload(args, workload, h, td, rank, world, local, peaks, N, t_start, e
                 "peak_source": peaks["source"], "note": peak_note,
                 "whole_step_tflops": value * flop_per_unit / 1e12 / world,
                 "whole_step_frac_of_sustained": value * flop_per_unit / 1e12 / world / peaks["bf16_tflops_sustained"]}
-    rev = kern.get("reverse_update", {})
-    roofline_hbm = {"bound": "hbm", "kernel": "final 1x1 conv + reverse update", "achieved": rev.get("gbs"),
-                    "peak": peaks["hbm_gbs"], "unit": "GB/s", "frac": (rev.get("gbs") or 0.0) / peaks["hbm_gbs"]}
+    # largest HBM-side kernel of the default sampler path: the first conv (writes one 32x32x64 tensor per launch).  Peak =
+    # the copy figure of MEASURED_PEAKS; the pure write / read stream rates of this box and run are listed beside it
+    # (probe_fill / probe_read in the kernel table: a write-only kernel cannot exceed the former)
+    c1 = kern.get("conv1", {})
+    roofline_hbm = {"bound": "hbm", "kernel": "first conv of the sampler (tcgen05, writes 64 ch per pixel)", "achieved": c1.get("gbs"),
+                    "peak": peaks["hbm_gbs"], "unit": "GB/s", "frac": (c1.get("gbs") or 0.0) / peaks["hbm_gbs"],
+                    "stream_write_gbs": kern.get("probe_fill", {}).get("gbs"), "stream_read_gbs": kern.get("probe_read", {}).get("gbs"),
+                    "frac_of_stream_write": ((c1.get("gbs") or 0.0) / kern["probe_fill"]["gbs"]) if kern.get("probe_fill", {}).get("gbs") else None}
 
     # ---- CPU baseline on the box's host cores, bounded sample
     cpu = None

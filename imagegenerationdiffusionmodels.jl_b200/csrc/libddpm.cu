@@ -657,7 +657,10 @@ int ddpm_time_kernel(ddpm_handle* h, const char* name, int64_t n_images, int ite
                     tc::up2<TA>(e.stream, s.a[6].pos0<TA>(), (const TA*)e.Wt, s.u.pos0<TA>(), s.a[6].g, s.u.g, e.arr(kUpB));
                 }
             }));
-            by = (double)N * HW * 64.0 * e.esz_a();
+            // algorithmic bytes: first conv reads x (4 B/pixel) and writes 64 channels; the pool reads 64 channels at 32x32 and
+            // writes them at 16x16; the ConvTranspose reads 128 channels at 16x16 and writes 64 at 32x32
+            const double t64 = (double)N * HW * 64.0 * e.esz_a();
+            by = (k == "conv1") ? t64 + 4.0 * N * HW : (k == "pool") ? 1.25 * t64 : 1.5 * t64;
         } else if (k.rfind("conv_l", 0) == 0) {
             int l = std::atoi(k.c_str() + 6);
             DDPM_CHECK(l >= 2 && l <= NUM_CONV, "conv layer index must be 2..10");
