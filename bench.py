@@ -248,8 +248,8 @@ def run_ours(args):
             line["train"]["per_gpu_value"] = tl["value"] / world
             try:
                 one = json.load(open(os.path.join(ROOT, "profiles", "r2", "train_1gpu.json")))
-                line["train"]["efficiency_vs_1gpu"] = tl["value"] / (world * one["value"])
-                line["train"]["one_gpu_value"] = one["value"]
+                line["train"]["efficiency_vs_1gpu"] = 1.0 if world == 1 else tl["value"] / (world * one["value"])
+                line["train"]["one_gpu_value"] = tl["value"] if world == 1 else one["value"]
             except Exception:
                 line["train"]["efficiency_vs_1gpu"] = 1.0 if world == 1 else None
     if rank == 0:
