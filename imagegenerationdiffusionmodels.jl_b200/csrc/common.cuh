@@ -51,9 +51,11 @@ struct Error : std::runtime_error {
 // producers only ever write valid positions, halos stay zero from allocation time.
 // `guard` zero positions precede position 0 and follow the last one so shifted tile reads and the
 // overhang of the last 128-row tile stay inside the allocation.
+constexpr int WP_32 = 33, WP_16 = 17;      // Geo::Wp of the 32x32 and 16x16 levels (kernel template arguments)
+
 struct Geo {
     int N, H, W;
-    int Wp;        // W + 2
+    int Wp;        // W + 1  (row stride in positions: ONE zero column per row, see make())
     int Hs;        // H + 1  (image stride in rows)
     int L;         // N*(H+1) + 1 rows
     long long npos;  // L * Wp
@@ -62,7 +64,9 @@ struct Geo {
     __host__ __device__ static Geo make(int N, int H, int W) {
         Geo g;
         g.N = N; g.H = H; g.W = W;
-        g.Wp = W + 2; g.Hs = H + 1; g.L = N * (H + 1) + 1;
+        // one zero column per row: position (r, 0) is the right pad of row r-1 and the left pad of row r, exactly like the
+        // shared separator row between images (33x33 instead of 34x33 positions per 32x32 image: fewer MMA rows and bytes)
+        g.Wp = W + 1; g.Hs = H + 1; g.L = N * (H + 1) + 1;
         g.npos = (long long)g.L * g.Wp;
         g.guard = 2 * g.Wp + 160;
         return g;

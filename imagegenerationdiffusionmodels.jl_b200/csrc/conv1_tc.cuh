@@ -49,7 +49,7 @@ __device__ __forceinline__ void split2(float v, float& hi, float& lo) {
 template <typename TOut>
 __global__ void __launch_bounds__(C1_THREADS, 1)
 conv1_tc_kernel(const __grid_constant__ CUtensorMap tmO, const C1Params p) {
-    constexpr int WP = 34, HS = 33, H = 32, W = 32;
+    constexpr int WP = WP_32, HS = 33, H = 32, W = 32;
     constexpr int ACC_BUFS = 4, NOUT = 64;
     constexpr uint32_t A_STAGE_BYTES = TC_BM * 128;
     constexpr uint32_t B_BYTES = NOUT * 128;
@@ -116,7 +116,7 @@ conv1_tc_kernel(const __grid_constant__ CUtensorMap tmO, const C1Params p) {
         // ================= A-tile builders: thread r writes row r of every tile this CTA owns =================
         const int r = threadIdx.x;
         // The nine taps of output row r are nine entries of ONE window of the zero-padded position space:
-        //   tap(dy,dx) = Xp[r + 35 + dy*34 + dx],   Xp[j] = padded image value at position tile*128 - 35 + j, j < 198.
+        //   tap(dy,dx) = Xp[r + (WP+1) + dy*WP + dx],   Xp[j] = padded image value at position tile*128 - (WP+1) + j, j < 128 + 2*(WP+1).
         // The first version fetched them with 9 bounds-checked global loads per thread (1152 per tile); ncu's source
         // view showed the builders latency-bound on exactly those loads with every other warp idle on its barrier.
         // Now the 128 builder threads fetch the 198 window entries once (<= 2 loads per thread, two tiles ahead),
@@ -319,8 +319,8 @@ __device__ __forceinline__ void sts128(uint32_t a, uint32_t x, uint32_t y, uint3
 template <typename TOut>
 __global__ void __launch_bounds__(C1F_THREADS, 1)
 conv1f_tc_kernel(const __grid_constant__ CUtensorMap tmO, const C1Params p) {
-    constexpr int WP = 34, HS = 33, H = 32, W = 32;
-    constexpr int ACC_BUFS = 4, NOUT = 64, WIN = 208;                  // window: 128 + 2*35 = 198 entries, padded
+    constexpr int WP = WP_32, HS = 33, H = 32, W = 32;
+    constexpr int ACC_BUFS = 4, NOUT = 64, WIN = 208;                  // window: 128 + 2*(WP+1) = 196 entries, padded
     constexpr uint32_t A_STAGE_BYTES = TC_BM * 128;
     constexpr uint32_t B_BYTES = NOUT * 128;
     constexpr uint32_t O_TILE = TC_BM * NOUT * 2;
@@ -406,7 +406,7 @@ conv1f_tc_kernel(const __grid_constant__ CUtensorMap tmO, const C1Params p) {
         const int r = threadIdx.x & 127;
         const uint32_t sw = (uint32_t)r & 7u;
         // The nine taps of output row r are nine entries of ONE window of the zero-padded position space:
-        //   tap(dy,dx) = Xp[r + 35 + dy*34 + dx],   Xp[j] = padded image value at position tile*128 - 35 + j, j < 198;
+        //   tap(dy,dx) = Xp[r + (WP+1) + dy*WP + dx],   Xp[j] = padded image value at position tile*128 - (WP+1) + j, j < 128 + 2*(WP+1);
         // entry r + 35 is the row's own position.  The 128 threads of a set fetch the 198 entries once (<= 2 loads per
         // thread, two of the set's tiles ahead), split them and publish (hi | lo << 16, border-class code).
         auto load_window = [&](int tile, float v[2], int code[2]) {
@@ -567,7 +567,7 @@ bool conv1_shared_t(cudaStream_t st, const float* x, const float* Wimg, const fl
     if constexpr (sizeof(TOut) != 2) {
         return false;
     } else {
-    if (g.Wp != 34 || g.Hs != 33 || g.npos + 2 * TC_BM >= (1ll << 31)) return false;
+    if (g.Wp != WP_32 || g.Hs != 33 || g.npos + 2 * TC_BM >= (1ll << 31)) return false;
     C1Params p{};
     p.x = x; p.Wimg = Wimg; p.Ecls_t = Ecls_t; p.scale = scale; p.shift = shift; p.relu = relu; p.g = g;
     p.num_tiles = cdiv(g.npos, TC_BM);

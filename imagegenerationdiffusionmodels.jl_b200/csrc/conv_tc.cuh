@@ -340,7 +340,7 @@ struct TcParams {
 };
 
 // TAPS: 9 (3x3 conv, halo'ed slab) or 1 (plain GEMM rows); CHUNKS: 64-channel K chunks (1|2);
-// NOUT: output channels handled by this CTA (64|128); WP: padded row width (W+2) for TAPS==9
+// NOUT: output channels handled by this CTA (64|128); WP: padded row width (W+1, Geo::Wp) for TAPS==9
 // EPI: 0 = conv store on the same geometry, 1 = ConvTranspose 2x2 pixel shuffle (blockIdx.y = q),
 //      2 = no activation store: eps_hat = <relu(acc+shift), wf> + bf per pixel, then the reverse-diffusion update
 //          x <- sqrt(a_prev)*clamp((x - sigma*eps_hat)/sqrt(a_t)) + sqrt(pv)*z   (generate_images.jl:196-208)
@@ -696,12 +696,12 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constant__
             const int buf = seq % ACC_BUFS;
             const uint32_t acc_phase = (uint32_t)(seq / ACC_BUFS) & 1u;
             const int tile = ut * CG + (int)rank;
-            // position -> (image, row, column) with compile-time divisors (square images: Hs = WP - 1)
+            // position -> (image, row, column) with compile-time divisors (square images: Hs = H + 1 = W + 1 = WP)
             const int pos = tile * TC_BM + row;
             const int pr = pos / WP, pc = pos - pr * WP;
-            const int n_img = pr / (WP - 1), prr = pr - n_img * (WP - 1);
+            const int n_img = pr / WP, prr = pr - n_img * WP;
             const int hh = prr - 1, ww = pc - 1;
-            const bool valid = pos < npos && prr != 0 && pc >= 1 && pc <= WP - 2 && n_img < p.g.N;
+            const bool valid = pos < npos && prr != 0 && pc >= 1 && n_img < p.g.N;
             long long opos = pos;
             int ch_off = n_blk * NOUT;
             if (EPI == 1) {
@@ -1009,7 +1009,7 @@ void launch(cudaStream_t st, const CUtensorMap& a0, const CUtensorMap& a1, const
     constexpr int R = ((TC_BM + 2 * HALO + 7) / 8) * 8;
     constexpr size_t smem = 1024 + (size_t)TAPS * CHUNKS * (NOUT / CG) * 128 + (size_t)STAGES * R * 128 +
                             (size_t)epi_smem_bytes<TAPS, CHUNKS, NOUT, WP, EPI, TMAST, CG, (int)sizeof(TOut)>() + 1280;
-    DDPM_CHECK(p.g.Wp == WP && p.g.Hs == WP - 1 && p.g.npos + 2 * TC_BM < (1ll << 31),
+    DDPM_CHECK(p.g.Wp == WP && p.g.Hs == WP && p.g.npos + 2 * TC_BM < (1ll << 31),
                "conv_tc: geometry does not match the kernel's compile-time row width");
     auto kern = conv_tc_kernel<TAPS, CHUNKS, NOUT, WP, STAGES, EPI, TMAST, CG, BNS, TIn, TOut>;
     ensure_smem_attr(kern, smem);
@@ -1094,28 +1094,28 @@ bool conv3x3(cudaStream_t st, const TIn* s0, int C0, const TIn* s1, int C1, cons
         p.num_m_tiles = cdiv(g.npos, TC_BM);
         p.chunk1_src1 = (s1 != nullptr) ? 1 : 0;
         p.dbg = nullptr;
-        constexpr int R32 = ((TC_BM + 2 * 35 + 7) / 8) * 8, R16 = ((TC_BM + 2 * 19 + 7) / 8) * 8;
-        CUtensorMap a0 = make_map_2d<float>(s0 - (size_t)g.guard * C0, rows, C0, WP == 34 ? R32 : R16);
+        constexpr int R32 = ((TC_BM + 2 * (WP_32 + 1) + 7) / 8) * 8, R16 = ((TC_BM + 2 * (WP_16 + 1) + 7) / 8) * 8;
+        CUtensorMap a0 = make_map_2d<float>(s0 - (size_t)g.guard * C0, rows, C0, WP == WP_32 ? R32 : R16);
         CUtensorMap a1 = a0;
-        if (s1) a1 = make_map_2d<float>(s1 - (size_t)g.guard * C1, rows, C1, WP == 34 ? R32 : R16);
-        if (WP == 34 && Cin == 64 && Cout == 64) {
+        if (s1) a1 = make_map_2d<float>(s1 - (size_t)g.guard * C1, rows, C1, WP == WP_32 ? R32 : R16);
+        if (WP == WP_32 && Cin == 64 && Cout == 64) {
             CUtensorMap w = make_map_2d<float>(Wt, 64, 9 * 64, 64);
-            launch<9, 2, 64, 34, 0, 0, float, float>(st, a0, a1, w, a0, p, 1);
-        } else if (WP == 34 && Cin == 128 && Cout == 64) {
+            launch<9, 2, 64, WP_32, 0, 0, float, float>(st, a0, a1, w, a0, p, 1);
+        } else if (WP == WP_32 && Cin == 128 && Cout == 64) {
             CUtensorMap w = make_map_2d<float>(Wt, 64, 9 * 128, 32);
-            launch<9, 4, 32, 34, 0, 0, float, float>(st, a0, a1, w, a0, p, 2);
-        } else if (WP == 34 && Cin == 64 && Cout == 128) {
+            launch<9, 4, 32, WP_32, 0, 0, float, float>(st, a0, a1, w, a0, p, 2);
+        } else if (WP == WP_32 && Cin == 64 && Cout == 128) {
             CUtensorMap w = make_map_2d<float>(Wt, 128, 9 * 64, 64);
-            launch<9, 2, 64, 34, 0, 0, float, float>(st, a0, a1, w, a0, p, 2);
-        } else if (WP == 18 && Cin == 64 && Cout == 128) {
+            launch<9, 2, 64, WP_32, 0, 0, float, float>(st, a0, a1, w, a0, p, 2);
+        } else if (WP == WP_16 && Cin == 64 && Cout == 128) {
             CUtensorMap w = make_map_2d<float>(Wt, 128, 9 * 64, 64);
-            launch<9, 2, 64, 18, 0, 0, float, float>(st, a0, a1, w, a0, p, 2);
-        } else if (WP == 18 && Cin == 128 && Cout == 128) {
+            launch<9, 2, 64, WP_16, 0, 0, float, float>(st, a0, a1, w, a0, p, 2);
+        } else if (WP == WP_16 && Cin == 128 && Cout == 128) {
             CUtensorMap w = make_map_2d<float>(Wt, 128, 9 * 128, 32);
-            launch<9, 4, 32, 18, 0, 0, float, float>(st, a0, a1, w, a0, p, 4);
-        } else if (WP == 18 && Cin == 128 && Cout == 64) {
+            launch<9, 4, 32, WP_16, 0, 0, float, float>(st, a0, a1, w, a0, p, 4);
+        } else if (WP == WP_16 && Cin == 128 && Cout == 64) {
             CUtensorMap w = make_map_2d<float>(Wt, 64, 9 * 128, 32);
-            launch<9, 4, 32, 18, 0, 0, float, float>(st, a0, a1, w, a0, p, 2);
+            launch<9, 4, 32, WP_16, 0, 0, float, float>(st, a0, a1, w, a0, p, 2);
         } else {
             return false;
         }
@@ -1138,51 +1138,51 @@ bool conv3x3(cudaStream_t st, const TIn* s0, int C0, const TIn* s1, int C1, cons
     }
     auto done = [&]() { if (bn_done) *bn_done = true; };
     const TIn* base0 = s0 - (size_t)g.guard * C0;
-    constexpr int R32 = ((TC_BM + 2 * 35 + 7) / 8) * 8, R16 = ((TC_BM + 2 * 19 + 7) / 8) * 8;
-    CUtensorMap a0 = make_map_2d<TIn>(base0, rows, C0, WP == 34 ? R32 : R16);
+    constexpr int R32 = ((TC_BM + 2 * (WP_32 + 1) + 7) / 8) * 8, R16 = ((TC_BM + 2 * (WP_16 + 1) + 7) / 8) * 8;
+    CUtensorMap a0 = make_map_2d<TIn>(base0, rows, C0, WP == WP_32 ? R32 : R16);
     CUtensorMap a1 = a0;
-    if (s1) a1 = make_map_2d<TIn>(s1 - (size_t)g.guard * C1, rows, C1, WP == 34 ? R32 : R16);
-    if (WP == 34 && Cin == 64 && Cout == 64 && !s1) {
+    if (s1) a1 = make_map_2d<TIn>(s1 - (size_t)g.guard * C1, rows, C1, WP == WP_32 ? R32 : R16);
+    if (WP == WP_32 && Cin == 64 && Cout == 64 && !s1) {
         const bool pair = (state().pair_mask & 2) != 0;
         CUtensorMap w = make_map_2d<TIn>(Wt, 64, 9 * 64, pair ? 32 : 64);
         CUtensorMap o = make_map_2d<TOut>(out - (size_t)g.guard * Cout, rows, Cout, TC_BM);
-        if (pair && bm == 1) { launch<9, 1, 64, 34, 0, 1, TIn, TOut, 2, 1>(st, a0, a1, w, o, p, 1); done(); }
-        else if (pair && bm == 2) { launch<9, 1, 64, 34, 0, 1, TIn, TOut, 2, 2>(st, a0, a1, w, o, p, 1); done(); }
-        else if (pair) launch<9, 1, 64, 34, 0, 1, TIn, TOut, 2>(st, a0, a1, w, o, p, 1);
-        else if (state().tma_store) launch<9, 1, 64, 34, 0, 1, TIn, TOut>(st, a0, a1, w, o, p, 1);
-        else launch<9, 1, 64, 34, 0, 0, TIn, TOut>(st, a0, a1, w, o, p, 1);
-    } else if (WP == 34 && Cin == 128 && Cout == 64) {
+        if (pair && bm == 1) { launch<9, 1, 64, WP_32, 0, 1, TIn, TOut, 2, 1>(st, a0, a1, w, o, p, 1); done(); }
+        else if (pair && bm == 2) { launch<9, 1, 64, WP_32, 0, 1, TIn, TOut, 2, 2>(st, a0, a1, w, o, p, 1); done(); }
+        else if (pair) launch<9, 1, 64, WP_32, 0, 1, TIn, TOut, 2>(st, a0, a1, w, o, p, 1);
+        else if (state().tma_store) launch<9, 1, 64, WP_32, 0, 1, TIn, TOut>(st, a0, a1, w, o, p, 1);
+        else launch<9, 1, 64, WP_32, 0, 0, TIn, TOut>(st, a0, a1, w, o, p, 1);
+    } else if (WP == WP_32 && Cin == 128 && Cout == 64) {
         const bool pair = (state().pair_mask & 4) != 0;
         CUtensorMap w = make_map_2d<TIn>(Wt, 64, 9 * 128, pair ? 32 : 64);
-        if (pair && bm == 1) { launch<9, 2, 64, 34, 0, 0, TIn, TOut, 2, 1>(st, a0, a1, w, a0, p, 1); done(); }
-        else if (pair) launch<9, 2, 64, 34, 0, 0, TIn, TOut, 2>(st, a0, a1, w, a0, p, 1);
-        else launch<9, 2, 64, 34, 0, 0, TIn, TOut>(st, a0, a1, w, a0, p, 1);
-    } else if (WP == 18 && Cin == 64 && Cout == 128 && !s1) {
+        if (pair && bm == 1) { launch<9, 2, 64, WP_32, 0, 0, TIn, TOut, 2, 1>(st, a0, a1, w, a0, p, 1); done(); }
+        else if (pair) launch<9, 2, 64, WP_32, 0, 0, TIn, TOut, 2>(st, a0, a1, w, a0, p, 1);
+        else launch<9, 2, 64, WP_32, 0, 0, TIn, TOut>(st, a0, a1, w, a0, p, 1);
+    } else if (WP == WP_16 && Cin == 64 && Cout == 128 && !s1) {
         const bool pair = (state().pair_mask & 8) != 0;
         CUtensorMap w = make_map_2d<TIn>(Wt, 128, 9 * 64, pair ? 64 : 128);
-        if (pair && bm == 1) { launch<9, 1, 128, 18, 0, 0, TIn, TOut, 2, 1>(st, a0, a1, w, a0, p, 1); done(); }
-        else if (pair) launch<9, 1, 128, 18, 0, 0, TIn, TOut, 2>(st, a0, a1, w, a0, p, 1);
-        else launch<9, 1, 128, 18, 0, 0, TIn, TOut>(st, a0, a1, w, a0, p, 1);
-    } else if (WP == 18 && Cin == 128 && Cout == 128 && !s1) {
+        if (pair && bm == 1) { launch<9, 1, 128, WP_16, 0, 0, TIn, TOut, 2, 1>(st, a0, a1, w, a0, p, 1); done(); }
+        else if (pair) launch<9, 1, 128, WP_16, 0, 0, TIn, TOut, 2>(st, a0, a1, w, a0, p, 1);
+        else launch<9, 1, 128, WP_16, 0, 0, TIn, TOut>(st, a0, a1, w, a0, p, 1);
+    } else if (WP == WP_16 && Cin == 128 && Cout == 128 && !s1) {
         CUtensorMap w = make_map_2d<TIn>(Wt, 128, 9 * 128, 64);
         const bool pair = (state().pair_mask & 1) != 0;
-        if (pair && bm == 1) { launch<9, 2, 128, 18, 0, 0, TIn, TOut, 2, 1>(st, a0, a1, w, a0, p, 1); done(); }
-        else if (pair && bm == 2) { launch<9, 2, 128, 18, 0, 0, TIn, TOut, 2, 2>(st, a0, a1, w, a0, p, 1); done(); }
+        if (pair && bm == 1) { launch<9, 2, 128, WP_16, 0, 0, TIn, TOut, 2, 1>(st, a0, a1, w, a0, p, 1); done(); }
+        else if (pair && bm == 2) { launch<9, 2, 128, WP_16, 0, 0, TIn, TOut, 2, 2>(st, a0, a1, w, a0, p, 1); done(); }
         else if (pair)
-            launch<9, 2, 128, 18, 0, 0, TIn, TOut, 2>(st, a0, a1, w, a0, p, 1);  // CTA pair: each CTA stages 64 of the 128 weight rows
+            launch<9, 2, 128, WP_16, 0, 0, TIn, TOut, 2>(st, a0, a1, w, a0, p, 1);  // CTA pair: each CTA stages 64 of the 128 weight rows
         else
-            launch<9, 2, 64, 18, 0, 0, TIn, TOut>(st, a0, a1, w, a0, p, 2);      // Cout split over blockIdx.y so the weights fit
-    } else if (WP == 18 && Cin == 128 && Cout == 64 && !s1) {
+            launch<9, 2, 64, WP_16, 0, 0, TIn, TOut>(st, a0, a1, w, a0, p, 2);      // Cout split over blockIdx.y so the weights fit
+    } else if (WP == WP_16 && Cin == 128 && Cout == 64 && !s1) {
         const bool pair = (state().pair_mask & 16) != 0;
         CUtensorMap w = make_map_2d<TIn>(Wt, 64, 9 * 128, pair ? 32 : 64);         // dgrad of down2.conv1
-        if (pair) launch<9, 2, 64, 18, 0, 0, TIn, TOut, 2>(st, a0, a1, w, a0, p, 1);
-        else launch<9, 2, 64, 18, 0, 0, TIn, TOut>(st, a0, a1, w, a0, p, 1);
-    } else if (WP == 34 && Cin == 64 && Cout == 128 && !s1) {
+        if (pair) launch<9, 2, 64, WP_16, 0, 0, TIn, TOut, 2>(st, a0, a1, w, a0, p, 1);
+        else launch<9, 2, 64, WP_16, 0, 0, TIn, TOut>(st, a0, a1, w, a0, p, 1);
+    } else if (WP == WP_32 && Cin == 64 && Cout == 128 && !s1) {
         const bool pair = (state().pair_mask & 16) != 0;
         CUtensorMap w = make_map_2d<TIn>(Wt, 128, 9 * 64, pair ? 64 : 128);        // dgrad of up1.conv1 (d cat)
-        if (pair && bm == 2) { launch<9, 1, 128, 34, 0, 0, TIn, TOut, 2, 2>(st, a0, a1, w, a0, p, 1); done(); }
-        else if (pair) launch<9, 1, 128, 34, 0, 0, TIn, TOut, 2>(st, a0, a1, w, a0, p, 1);
-        else launch<9, 1, 128, 34, 0, 0, TIn, TOut>(st, a0, a1, w, a0, p, 1);
+        if (pair && bm == 2) { launch<9, 1, 128, WP_32, 0, 0, TIn, TOut, 2, 2>(st, a0, a1, w, a0, p, 1); done(); }
+        else if (pair) launch<9, 1, 128, WP_32, 0, 0, TIn, TOut, 2>(st, a0, a1, w, a0, p, 1);
+        else launch<9, 1, 128, WP_32, 0, 0, TIn, TOut>(st, a0, a1, w, a0, p, 1);
     } else {
         return false;
     }
@@ -1198,7 +1198,7 @@ bool conv3x3_final(cudaStream_t st, const TIn* s0, const TIn* Wt, const Geo& g, 
     if constexpr (sizeof(TIn) != 2) {
         return false;
     } else {
-    if (g.Wp != 34) return false;
+    if (g.Wp != WP_32) return false;
     TcParams p{};
     p.out = nullptr; p.out_cs = 64; p.g = g; p.g_out = g; p.shift = shift; p.relu = 1;
     p.num_m_tiles = cdiv(g.npos, TC_BM);
@@ -1207,12 +1207,12 @@ bool conv3x3_final(cudaStream_t st, const TIn* s0, const TIn* Wt, const Geo& g, 
     p.x = x; p.z = z; p.wf = wf; p.bf = bf;
     p.sig = scal[0]; p.sqa = scal[1]; p.sqp = scal[2]; p.sqv = scal[3];
     p.final_clamp = final_clamp;
-    constexpr int R32 = ((TC_BM + 2 * 35 + 7) / 8) * 8;
+    constexpr int R32 = ((TC_BM + 2 * (WP_32 + 1) + 7) / 8) * 8;
     CUtensorMap a0 = make_map_2d<TIn>(s0 - (size_t)g.guard * 64, (uint64_t)g.alloc_positions(), 64, R32);
     const bool pair = (state().pair_mask & 2) != 0;
     CUtensorMap w = make_map_2d<TIn>(Wt, 64, 9 * 64, pair ? 32 : 64);
-    if (pair) launch<9, 1, 64, 34, 2, 0, TIn, TIn, 2>(st, a0, a0, w, a0, p, 1);
-    else launch<9, 1, 64, 34, 2, 0, TIn, TIn>(st, a0, a0, w, a0, p, 1);
+    if (pair) launch<9, 1, 64, WP_32, 2, 0, TIn, TIn, 2>(st, a0, a0, w, a0, p, 1);
+    else launch<9, 1, 64, WP_32, 2, 0, TIn, TIn>(st, a0, a0, w, a0, p, 1);
     return true;
     }
 }
@@ -1230,7 +1230,7 @@ bool up2(cudaStream_t st, const TA* a6, const TA* Wt, TA* u, const Geo& gi, cons
     p.chunk1_src1 = 0;
     CUtensorMap a0 = make_map_2d<TA>(a6 - (size_t)gi.guard * 128, (uint64_t)gi.alloc_positions(), 128, TC_BM);
     CUtensorMap w = make_map_2d<TA>(Wt, 256, 128, 64);
-    launch<1, 2, 64, 18, 1, 0, TA, TA>(st, a0, a0, w, a0, p, 4);
+    launch<1, 2, 64, WP_16, 1, 0, TA, TA>(st, a0, a0, w, a0, p, 4);
     return true;
     }
 }
@@ -1256,10 +1256,10 @@ bool gemm_rows(cudaStream_t st, const T* a, int K, const T* Wt, int Nout, T* out
     if (bn && bn->mode == 2) {
         p.stats = bn->sums; p.stats_C = bn->C; p.stats_nch = bn->nch; p.bn_y = bn->y; p.bn_cs = bn->y_cs;
         p.bn_scale = bn->scale; p.bn_shift = bn->shift; p.bn_mean = bn->mean; p.bn_istd = bn->istd;
-        launch<1, 4, 128, 18, 0, 0, T, T, 1, 2>(st, a0, a0, w, a0, p, 1);
+        launch<1, 4, 128, WP_16, 0, 0, T, T, 1, 2>(st, a0, a0, w, a0, p, 1);
         if (bn_done) *bn_done = true;
     } else {
-        launch<1, 4, 128, 18, 0, 0, T, T>(st, a0, a0, w, a0, p, 1);
+        launch<1, 4, 128, WP_16, 0, 0, T, T>(st, a0, a0, w, a0, p, 1);
     }
     return true;
     }
@@ -1592,7 +1592,7 @@ bool wgrad3x3(cudaStream_t st, WgScratch& sc, const TG* dy, int Cout, const TA* 
     if constexpr (sizeof(TG) != 2 || sizeof(TA) != 2 || !std::is_same<TG, TA>::value) {
         return false;
     } else {
-    if ((Cout != 64 && Cout != 128) || (Cx != 64 && Cx != 128) || (g.Wp != 34 && g.Wp != 18)) return false;
+    if ((Cout != 64 && Cout != 128) || (Cx != 64 && Cx != 128) || (g.Wp != WP_32 && g.Wp != WP_16)) return false;
     const int nco = Cout / 64, nci = Cx / 64, n_sub = nco * nci;
     const int num_kblocks = cdiv(g.npos, WG_KB);
     int ctas_x = state().num_sms / n_sub;
@@ -1610,8 +1610,8 @@ bool wgrad3x3(cudaStream_t st, WgScratch& sc, const TG* dy, int Cout, const TA* 
     const int RDY = ((WG_KB + 2 * g.Wp + 7) / 8) * 8;
     CUtensorMap mdy = make_map_2d<TG>(dy - (size_t)g.guard * Cout, rows, Cout, RDY);
     CUtensorMap mx = make_map_2d<TA>(x - (size_t)g.guard * Cx, rows, Cx, RX);
-    if (g.Wp == 34) launch_wgrad<34, TG, TA>(st, mdy, mx, p, ctas_x, n_sub);
-    else launch_wgrad<18, TG, TA>(st, mdy, mx, p, ctas_x, n_sub);
+    if (g.Wp == WP_32) launch_wgrad<WP_32, TG, TA>(st, mdy, mx, p, ctas_x, n_sub);
+    else launch_wgrad<WP_16, TG, TA>(st, mdy, mx, p, ctas_x, n_sub);
     const int total = n_sub * 36864;
     wgrad_reduce_kernel<<<cdiv(total, 256), 256, 0, st>>>(sc.partial, ctas_x, n_sub, sc.sub + cfg * 8, sc.sub + cfg * 8 + 4,
                                                           Cin_total, ci_off, alpha, dW);

@@ -250,7 +250,7 @@ conv1_kernel(const float* __restrict__ x, const int* __restrict__ ts, int t_fixe
     const float* erow = Ecls + (long long)trow * 9 * 64 + cg;
     __syncthreads();
     float s1[4] = {0.f, 0.f, 0.f, 0.f}, s2[4] = {0.f, 0.f, 0.f, 0.f};
-    TA* obase = out.p + ((long long)(n * (H + 1) + 1 + h0) * (W + 2) + 1) * out.cs + cg;
+    TA* obase = out.p + ((long long)(n * g.Hs + 1 + h0) * g.Wp + 1) * out.cs + cg;
 #pragma unroll 2
     for (int lp = (t >> 4); lp < CONV1_PIX_PER_BLOCK; lp += 16) {
         const int hl = lp >> 5, w = lp & 31, h = h0 + hl;
@@ -271,7 +271,7 @@ conv1_kernel(const float* __restrict__ x, const int* __restrict__ ts, int t_fixe
             s1[j] += v; s2[j] = fmaf(v, v, s2[j]);
             o[j] = relu ? fmaxf(v, 0.f) : v;
         }
-        st4<TA>(obase + (long long)(hl * (W + 2) + w) * out.cs, o);
+        st4<TA>(obase + (long long)(hl * g.Wp + w) * out.cs, o);
     }
     if (stats) {
 #pragma unroll

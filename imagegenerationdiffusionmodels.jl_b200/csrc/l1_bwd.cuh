@@ -8,7 +8,7 @@
 // HBM-bound: the kernel must stream dy once (128 KB per image) while doing 72 FMAs per loaded 16-byte vector.  The
 // first version issued its loads from the FMA loop (one block per SM, eight warps, one dependent global load per row):
 // 331 us for 2048 images = 0.8 TB/s.  Here a block stages dy through shared memory with bulk asynchronous copies
-// (cp.async.bulk, the 1-D TMA path): eight image rows = 272 consecutive padded positions = 34 KB per copy, double
+// (cp.async.bulk, the 1-D TMA path): eight image rows = 264 consecutive padded positions = 33 KB per copy, double
 // buffered on two mbarriers, so the copy of chunk k+1 is in flight while chunk k is consumed from shared memory.
 #pragma once
 #include "conv_tc.cuh"
@@ -22,15 +22,15 @@ __device__ __forceinline__ void bulk_load_1d(uint32_t dst_smem, const void* src,
 }
 
 constexpr int L1B_ROWS = 8;                                  // image rows per staged chunk
-constexpr int L1B_POS = L1B_ROWS * 34;                       // padded positions per chunk
-constexpr int L1B_CHUNK_BYTES = L1B_POS * 64 * 2;            // 34,816
+constexpr int L1B_POS = L1B_ROWS * WP_32;                    // padded positions per chunk
+constexpr int L1B_CHUNK_BYTES = L1B_POS * 64 * 2;            // 33,792
 constexpr size_t L1B_SMEM = 1024 + 2 * (size_t)L1B_CHUNK_BYTES + 34 * 34 * 4 + 32 * 3 * 64 * 4 + 64;
 
 template <typename T>
 __global__ void __launch_bounds__(256, 1)
 l1_bwd_bulk_kernel(const T* __restrict__ dy0 /*position 0, 64 channels per position*/, Geo g, const float* __restrict__ x,
                    float* __restrict__ Ccls, double* __restrict__ wimg_acc) {
-    constexpr int H = 32, W = 32, TW = W + 2, CPI = H / L1B_ROWS;     // chunks per image
+    constexpr int H = 32, W = 32, TW = W + 2, PW = WP_32, CPI = H / L1B_ROWS;     // x window width, position row stride, chunks per image
     extern __shared__ uint8_t smem_raw[];
     uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 127) & ~(uintptr_t)127);
     const uint32_t s_buf = tc::smem_u32(smem);
@@ -49,7 +49,7 @@ l1_bwd_bulk_kernel(const T* __restrict__ dy0 /*position 0, 64 channels per posit
     const int n_chunks = n_mine * CPI;
     auto issue = [&](int k) {                                          // chunk k of this block's sequence -> buffer k&1
         const int n = blockIdx.x + (k / CPI) * gridDim.x, c = k % CPI;
-        const long long p0 = (long long)(n * (H + 1) + 1 + c * L1B_ROWS) * TW;
+        const long long p0 = (long long)(n * (H + 1) + 1 + c * L1B_ROWS) * PW;
         tc::mbar_expect_tx(s_bar + 8 * (k & 1), L1B_CHUNK_BYTES);
         bulk_load_1d(s_buf + (k & 1) * L1B_CHUNK_BYTES, dy0 + p0 * 64, L1B_CHUNK_BYTES, s_bar + 8 * (k & 1));
     };
@@ -81,7 +81,7 @@ l1_bwd_bulk_kernel(const T* __restrict__ dy0 /*position 0, 64 channels per posit
         for (int hl = 0; hl < L1B_ROWS; ++hl) {
             const int h = c * L1B_ROWS + hl;
             float d[8];
-            V8<T>::ld(reinterpret_cast<const T*>(buf + (size_t)(hl * TW + w + 1) * 128) + c0, d);
+            V8<T>::ld(reinterpret_cast<const T*>(buf + (size_t)(hl * PW + w + 1) * 128) + c0, d);
             const float* tp = tile + h * TW + w;
 #pragma unroll
             for (int tap = 0; tap < 9; ++tap) {

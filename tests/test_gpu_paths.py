@@ -370,3 +370,40 @@ def test_demo_runs(tmp_path):
     for f in ("grid.png", "noisy_img.png", "denoised_img.png", "generated_image_1.png"):
         assert (tmp_path / f).stat().st_size > 100
     assert res["generated"].shape == (1, 1, 32, 32) and res["denoised"].shape == (32, 32)
+
+
+@pytest.mark.parametrize("name,T,max_tol,med_tol", [("trained_model.bson", 500, 0.12, 0.035), ("ddpm_epoch_95.bson", 5, 0.12, 0.035)])
+def test_cuda_forward_reproduces_the_running_statistics_flux_wrote(oracle, name, T, max_tol, med_tol):
+    """The CUDA path against numbers the REFERENCE'S OWN RUN produced (no oracle in between): the BatchNorm running means /
+    variances Flux wrote into the shipped checkpoints (train_brain.jl:112-140,295-300) are the per-channel statistics of the
+    ten pre-BatchNorm conv outputs at the checkpoint's weights.  The train-mode forward of libddpm (default FP16 tensor-core
+    mode) on the same dataset, fresh random t and eps, 8 batches of 64, must reproduce all twenty vectors within the band
+    the CPU restatement reproduces them (tests/test_oracle_checkpoint_stats.py: max 7 %, median 1.3-1.8 %)."""
+    from igdm_b200 import api, capi, tables
+    model = api.SimpleUNet.load(os.path.join(ROOT, "fixtures", name))
+    beta, _, acum = tables.beta_schedule(T)
+    data = api.load_dataset() * np.float32(2) - np.float32(1)
+    rng = np.random.default_rng(0)
+    acc = None
+    nb = 8
+    with capi.Handle(T=T, precision=capi.PREC_FP16) as h:
+        h.set_tables(beta, acum, tables.embedding_table(T))
+        h.set_weights(model.arrays)
+        for _ in range(nb):
+            idx = rng.permutation(500)[:64]
+            x0 = data[idx]
+            ts = rng.integers(1, T + 1, 64)
+            eps = rng.standard_normal(x0.shape).astype(np.float32)
+            xt = h.q_sample(x0, ts, eps)
+            h.predict_eps(xt, ts, train_mode=True)
+            cur = []
+            for l in range(1, 11):
+                C = 128 if 3 <= l <= 6 else 64
+                y = h.debug_fetch("y%d" % l).reshape(64, C, -1).astype(np.float64)
+                m = y.mean(axis=(0, 2))
+                cur += [m, ((y - m[None, :, None]) ** 2).sum(axis=(0, 2)) / (y.shape[0] * y.shape[2] - 1)]
+            acc = cur if acc is None else [a + c for a, c in zip(acc, cur)]
+    stored = [model.arrays[i] for i, t in enumerate(oracle.trainable_mask()) if not t]
+    r = [float(np.linalg.norm(a / nb - s) / np.linalg.norm(s)) for a, s in zip(acc, stored)]
+    _dump("running_stats_vs_checkpoint_%s.json" % name.split(".")[0], {"rel_l2_per_vector": r, "max": max(r), "median": float(np.median(r))})
+    assert max(r) < max_tol and float(np.median(r)) < med_tol, r
