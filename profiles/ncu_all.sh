@@ -6,7 +6,7 @@ O=gpurun_out
 T0=$(date +%s)
 if [ "$1" = "sampler" ]; then
   python profiles/run_kernel.py forward_infer 1300 1 > $O/plain_fwd.log 2>&1 &&
-  timeout 300 ncu --set full --clock-control none -f -k regex:'conv_tc_kernel|conv1_tc_kernel|bn_apply_pool' -s 48 -c 12 -o $O/ncu_sampler_eval python profiles/run_kernel.py forward_infer 1300 1 > $O/ncu_fwd.log 2>&1
+  timeout 300 ncu --set full --clock-control none -f -k regex:'conv_tc_kernel|conv1f_tc_kernel|bn_apply_pool' -s 48 -c 12 -o $O/ncu_sampler_eval python profiles/run_kernel.py forward_infer 1300 1 > $O/ncu_fwd.log 2>&1
   ncu -i $O/ncu_sampler_eval.ncu-rep --page raw --csv > $O/ncu_sampler_eval_raw.csv 2>/dev/null; rm -f $O/ncu_sampler_eval.ncu-rep
   echo "sampler eval done at $(( $(date +%s) - T0 )) s"
   python profiles/sample_once.py 1300 3 > $O/plain_sample.log 2>&1 &&
@@ -14,7 +14,7 @@ if [ "$1" = "sampler" ]; then
   ncu -i $O/ncu_sampler_final.ncu-rep --page raw --csv > $O/ncu_sampler_final_raw.csv 2>/dev/null; rm -f $O/ncu_sampler_final.ncu-rep
   echo "sampler final done at $(( $(date +%s) - T0 )) s"
   python profiles/run_kernel.py conv1 1300 3 > $O/plain_c1.log 2>&1 &&
-  timeout 120 ncu --set full --clock-control none --import-source on -f -k regex:conv1_tc_kernel -s 4 -c 1 -o $O/conv1_tc_r2 python profiles/run_kernel.py conv1 1300 3 > $O/ncu_c1.log 2>&1
+  timeout 120 ncu --set full --clock-control none --import-source on -f -k regex:conv1f_tc_kernel -s 4 -c 1 -o $O/conv1f_tc_r2 python profiles/run_kernel.py conv1 1300 3 > $O/ncu_c1.log 2>&1
   echo "conv1 source done at $(( $(date +%s) - T0 )) s"
 else
   python profiles/train_once.py 1024 1 > $O/plain_train.log 2>&1 &&
