@@ -44,10 +44,11 @@ struct Error : std::runtime_error {
 // over a ZERO-PADDED, IMAGE-STACKED position space:
 //   rows  r = 0 .. N*(H+1)      row n*(H+1) is an all-zero separator (bottom pad of image n-1 ==
 //                               top pad of image n), rows n*(H+1)+1+h hold image row h
-//   cols  c = 0 .. W+1          c = 0 and c = W+1 are zero, c = 1+w holds pixel w
-//   pos = r*(W+2) + c
-// so that a 3x3 tap (dy,dx) is the constant row shift dy*(W+2)+dx of that matrix and the zero halo
-// implements pad=1.  The implicit-GEMM kernels therefore never test bounds on the input side;
+//   cols  c = 0 .. W            c = 0 is zero, c = 1+w holds pixel w; the right neighbour of pixel W-1 is position
+//                               (r+1, 0): ONE zero column serves as the right pad of row r and the left pad of row r+1
+//   pos = r*(W+1) + c
+// so that a 3x3 tap (dy,dx) is the constant row shift dy*(W+1)+dx of that matrix and the zero halo
+// implements pad=1 (tests/test_layout_host.py checks exactly this property on the host).  The implicit-GEMM kernels therefore never test bounds on the input side;
 // producers only ever write valid positions, halos stay zero from allocation time.
 // `guard` zero positions precede position 0 and follow the last one so shifted tile reads and the
 // overhang of the last 128-row tile stay inside the allocation.

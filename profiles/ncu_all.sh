@@ -10,7 +10,7 @@ if [ "$1" = "sampler" ]; then
   ncu -i $O/ncu_sampler_eval.ncu-rep --page raw --csv > $O/ncu_sampler_eval_raw.csv 2>/dev/null; rm -f $O/ncu_sampler_eval.ncu-rep
   echo "sampler eval done at $(( $(date +%s) - T0 )) s"
   python profiles/sample_once.py 1300 3 > $O/plain_sample.log 2>&1 &&
-  timeout 200 ncu --set full --clock-control none -f -k regex:'conv_tc_kernel<9, 1, 64, 34, 6, 2|randn_dev' -s 2 -c 2 -o $O/ncu_sampler_final python profiles/sample_once.py 1300 3 > $O/ncu_sample.log 2>&1
+  timeout 200 ncu --set full --clock-control none -f -k regex:'conv_tc_kernel<9, 1, 64, 33, 6, 2|randn_dev' -s 2 -c 2 -o $O/ncu_sampler_final python profiles/sample_once.py 1300 3 > $O/ncu_sample.log 2>&1
   ncu -i $O/ncu_sampler_final.ncu-rep --page raw --csv > $O/ncu_sampler_final_raw.csv 2>/dev/null; rm -f $O/ncu_sampler_final.ncu-rep
   echo "sampler final done at $(( $(date +%s) - T0 )) s"
   python profiles/run_kernel.py conv1 1300 3 > $O/plain_c1.log 2>&1 &&
