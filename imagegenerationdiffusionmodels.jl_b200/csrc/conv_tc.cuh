@@ -317,6 +317,9 @@ struct TcParams {
     int relu;
     int num_m_tiles;
     int chunk1_src1;      // 1: K-chunk 1 comes from the second tensor map (channel concat), 0: channels 64.. of the first
+    int rev;              // 1: walk the tiles from the last to the first.  Consecutive layers of the sampler alternate the
+                          // direction, so a layer starts with the part of its input the previous kernel wrote LAST -- the part
+                          // that is still in the 126 MB L2 (an LRU-streamed 100-200 MB tensor read front to back misses all of it)
     long long* dbg;       // optional [gridDim.x*gridDim.y][8] cycle counters (role wait/busy breakdown), nullptr = off
     // EPI == 2: final Conv((1,1), 64=>1) + reverse-diffusion update fused into this conv's epilogue
     float* x;             // [N][H*W] current sample, updated in place
@@ -485,7 +488,7 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constant__
         int stage = 0;
         uint32_t phase = 0;
         for (int ut = unit; ut < num_units_tiles; ut += n_units) {
-            const int tile = ut * CG + (int)rank;
+            const int tile = (p.rev ? num_units_tiles - 1 - ut : ut) * CG + (int)rank;
             const int row0 = tile * TC_BM - HALO + p.g.guard;   // row coordinate in the tensor map (base = allocation start)
 #pragma unroll
             for (int c = 0; c < CHUNKS; ++c) {
@@ -695,7 +698,7 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constant__
         for (int seq = eset, ut = unit + eset * n_units; ut < num_units_tiles; seq += 2, ut += 2 * n_units) {
             const int buf = seq % ACC_BUFS;
             const uint32_t acc_phase = (uint32_t)(seq / ACC_BUFS) & 1u;
-            const int tile = ut * CG + (int)rank;
+            const int tile = (p.rev ? num_units_tiles - 1 - ut : ut) * CG + (int)rank;
             // position -> (image, row, column) with compile-time divisors (square images: Hs = H + 1 = W + 1 = WP)
             const int pos = tile * TC_BM + row;
             const int pr = pos / WP, pc = pos - pr * WP;
@@ -923,6 +926,8 @@ struct State {
     // 8 = 64=>128 @16x16, 16 = the two data-gradient-only shapes (128=>64 @16x16, 64=>128 @32x32)
     int pair_mask = 31;
     bool pdl = true;            // launch the tcgen05 conv kernels as programmatic dependents of their stream predecessor
+    bool reverse = true;        // option tc_reverse: alternate the tile direction between consecutive layers of the sampler
+    int rev_next = 0;           // direction of the NEXT conv launch (set by the engine's inference forward, consumed by the launch)
     // per-DEVICE launch bookkeeping (function attributes and occupancy are properties of a (kernel, device) pair)
     std::map<const void*, int> smem_attr;     // kernel -> dynamic shared memory size already granted on this device
     std::map<const void*, int> max_pairs;     // kernel -> resident CTA pairs on this device
@@ -1130,6 +1135,8 @@ bool conv3x3(cudaStream_t st, const TIn* s0, int C0, const TIn* s1, int C1, cons
     p.out = out; p.out_cs = Cout; p.g = g; p.g_out = g; p.shift = shift; p.relu = relu;
     p.num_m_tiles = cdiv(g.npos, TC_BM);
     p.chunk1_src1 = (s1 != nullptr) ? 1 : 0;
+    p.rev = state().reverse ? state().rev_next : 0;
+    state().rev_next = 0;
     p.dbg = state().dbg;
     const int bm = (bn && bn->mode && !p.dbg) ? bn->mode : 0;
     if (bm) {
@@ -1203,6 +1210,8 @@ bool conv3x3_final(cudaStream_t st, const TIn* s0, const TIn* Wt, const Geo& g, 
     p.out = nullptr; p.out_cs = 64; p.g = g; p.g_out = g; p.shift = shift; p.relu = 1;
     p.num_m_tiles = cdiv(g.npos, TC_BM);
     p.chunk1_src1 = 0;
+    p.rev = state().reverse ? state().rev_next : 0;
+    state().rev_next = 0;
     p.dbg = nullptr;
     p.x = x; p.z = z; p.wf = wf; p.bf = bf;
     p.sig = scal[0]; p.sqa = scal[1]; p.sqp = scal[2]; p.sqv = scal[3];
@@ -1228,6 +1237,8 @@ bool up2(cudaStream_t st, const TA* a6, const TA* Wt, TA* u, const Geo& gi, cons
     p.out = u; p.out_cs = 64; p.g = gi; p.g_out = go; p.shift = bias; p.relu = 0;
     p.num_m_tiles = cdiv(gi.npos, TC_BM);
     p.chunk1_src1 = 0;
+    p.rev = state().reverse ? state().rev_next : 0;
+    state().rev_next = 0;
     CUtensorMap a0 = make_map_2d<TA>(a6 - (size_t)gi.guard * 128, (uint64_t)gi.alloc_positions(), 128, TC_BM);
     CUtensorMap w = make_map_2d<TA>(Wt, 256, 128, 64);
     launch<1, 2, 64, WP_16, 1, 0, TA, TA>(st, a0, a0, w, a0, p, 4);

@@ -827,7 +827,11 @@ void Engine::forward_t(ActSet& s, const float* x_dev, const int* ts_dev, int t_f
             conv3<TA, TG>(in0, in1, l, s.y[l], false, arr(c.b), 0, lsum(l));
             bn(l, l == 2);
         } else {
+            // launch order of an evaluation: first conv, L2, pool, L3, L4, L5, L6, ConvTranspose, L7, L8, L9, L10; the tile
+            // direction alternates along it (the first conv and the pool run front to back), see TcParams::rev
+            tc::state().rev_next = (l == 2 || l == 3 || l == 5 || l == 8 || l == 10) ? 1 : 0;
             conv3<TA, TG>(in0, in1, l, s.a[l], true, inf_shift[l], 1, nullptr);
+            tc::state().rev_next = 0;
         }
     };
 
@@ -868,8 +872,11 @@ void Engine::forward_t(ActSet& s, const float* x_dev, const int* ts_dev, int t_f
         const Geo& gi = s.a[6].g;
         const Geo& go = s.u.g;
         bool done = false;
-        if (use_tc())
+        if (use_tc()) {
+            tc::state().rev_next = train ? 0 : 1;
             done = tc::up2<TA>(stream, s.a[6].pos0<TA>(), (const TA*)Wt, s.u.pos0<TA>(), gi, go, arr(kUpB));
+            tc::state().rev_next = 0;
+        }
         if (!done) {
             EpiUp2<TA> epi{s.u.view<TA>(), gi, go, arr(kUpB), 64, nullptr};
             launch_igemm_simt<TA, TA>(stream, s.a[6].cview<TA>(), 128, View<const TA>{nullptr, 0}, 0, (const TA*)Wt, 256, 1,
@@ -1278,8 +1285,10 @@ void Engine::sample_steps_t(ActSet& s, float* x_dev, const float* z_dev, int N, 
         const float* sc = &h_samp[(size_t)(t - 1) * 4];
         if (use_tc() && opt_fuse_final) {
             forward_t<TA, TG>(s, x_dev, nullptr, t, Mode::Infer, false, true);
+            tc::state().rev_next = 1;                   // layer 10 of the alternating tile direction (see forward_t)
             bool fused = tc::conv3x3_final<TA>(stream, s.a[9].pos0<TA>(), (const TA*)Wfi[10], s.a[9].g, inf_shift[10], x_dev, zstep,
                                               arr(kFinalW), arr(kFinalB), sc, t == 2 ? 1 : 0);
+            tc::state().rev_next = 0;
             if (fused) {
                 cnt_launches += 1;
                 continue;

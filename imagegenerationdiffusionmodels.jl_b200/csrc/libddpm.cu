@@ -479,6 +479,7 @@ int ddpm_set_option(ddpm_handle* h, const char* key, int64_t value) {
     else if (k == "loss_scale_log2") { DDPM_CHECK(value >= -30 && value <= 30, "loss_scale_log2 out of range"); e.opt_loss_scale_log2 = value; e.drop_train_graphs(); }
     else if (k == "tc_tma_store") { tc::state().tma_store = value != 0; for (auto& kv : e.infer_sets) kv.second->drop_graphs(); }
     else if (k == "tc_pair") { tc::state().pair_mask = value; for (auto& kv : e.infer_sets) kv.second->drop_graphs(); }
+    else if (k == "tc_reverse") { tc::state().reverse = value != 0; for (auto& kv : e.infer_sets) kv.second->drop_graphs(); }
     else if (k == "tc_pdl") { tc::state().pdl = value != 0; for (auto& kv : e.infer_sets) kv.second->drop_graphs(); }
     else if (k == "conv1_tc") { e.opt_conv1_tc = value; for (auto& kv : e.infer_sets) kv.second->drop_graphs(); }
     else if (k == "bnbwd_blocks") { DDPM_CHECK(value >= 1 && value <= 8, "bnbwd_blocks must be 1..8"); e.opt_bnbwd_blocks = value; e.drop_train_graphs(); }

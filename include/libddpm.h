@@ -143,7 +143,8 @@ int ddpm_comm_init(ddpm_handle*, const void* id, int rank, int world, int sync_b
  *   sample_streams (1), use_graph (1), conv_impl (0 auto | 1 CUDA-core | 2 tcgen05), sync_bn (1),
  *   fuse_final (1: last conv + final 1x1 conv + reverse update in one epilogue),
  *   tc_pair (bit mask of layer shapes run as CTA pairs / cta_group::2, 31 = all), tc_pdl (1: programmatic dependent
- *   launch of the tcgen05 kernels), conv1_tc (2: first conv of the sampler on tensor cores with the timestep constants folded into the contraction, 1: constants added in the epilogue, 0: CUDA cores), tc_tma_store (1),
+ *   launch of the tcgen05 kernels), tc_reverse (1: consecutive conv layers of the sampler walk their tiles in alternating
+ *   directions, so each starts with the part of its input that is still in L2), conv1_tc (2: first conv of the sampler on tensor cores with the timestep constants folded into the contraction, 1: constants added in the epilogue, 0: CUDA cores), tc_tma_store (1),
  *   tc_role_profile (0: in-kernel cycle counters), train_graph (1: replay the training iteration from a CUDA graph),
  *   bn_p2p (1: SyncBN statistics exchanged over peer-memory mailboxes inside the finalize kernels; 0: one NCCL all-reduce
  *   per layer), dp_skip (0; TIMING ONLY, results become wrong: bit 0 skips the gradient all-reduces, bit 1 the SyncBN ones),
