@@ -271,6 +271,7 @@ struct Engine {
 
     // options / counters
     long long opt_sample_streams = 1;
+    long long opt_train_reverse = 1; // BatchNorm apply / backward kernels walk their tensors from the end (L2-resident tail first)
     long long opt_bnbwd_blocks = 4; // resident blocks per SM of the second BatchNorm-backward pass
     long long opt_conv1_tc = 2;    // sampler: first conv on tensor cores (hi/lo split operands) when the batch shares one timestep;
                                    // 2 = (timestep, border class) constants folded into the contraction as well, 1 = added in the epilogue
@@ -811,11 +812,12 @@ void Engine::forward_t(ActSet& s, const float* x_dev, const int* ts_dev, int t_f
         if (pool) {
             work = (long long)N * 16 * 16 * (c.cout / 8);
             bn_apply_pool_kernel<TA><<<cdiv(work, 256), 256, 0, stream>>>(s.y[l].cview<TA>(), s.a[l].view<TA>(), s.p1.view<TA>(),
-                                                                          s.y[l].g, s.p1.g, c.cout, tr_scale[l], tr_shift[l]);
+                                                                          s.y[l].g, s.p1.g, c.cout, tr_scale[l], tr_shift[l],
+                                                                          (int)opt_train_reverse);
         } else {
             work = (long long)N * c.hw * c.hw * (c.cout / 8);
             bn_apply_kernel<TA><<<cdiv(work, 256), 256, 0, stream>>>(s.y[l].cview<TA>(), s.a[l].view<TA>(), s.y[l].g, c.cout,
-                                                                     tr_scale[l], tr_shift[l]);
+                                                                     tr_scale[l], tr_shift[l], (int)opt_train_reverse);
         }
         DDPM_LAUNCH_CHECK();
         cnt_launches += 2;
@@ -998,7 +1000,8 @@ void Engine::backward_t(ActSet& s, const float* xt_dev, const int* ts_dev, const
         bn_bwd_means_kernel<<<1, 256, 0, stream>>>(lsum(l), gs, m, c.cout, bw_mg[l], bw_mgx[l], garr(c.bn), garr(c.bn + 1),
                                                    alpha, xr, slot, gsum(l));
         bn_bwd_kernel<TA, TG, 2><<<blocks, 256, 0, stream>>>(s.y[l].cview<TA>(), da, dy.view<TG>(), g, c.cout, tr_scale[l],
-                                                             tr_shift[l], tr_mean[l], tr_istd[l], bw_mg[l], bw_mgx[l], lsum(l));
+                                                             tr_shift[l], tr_mean[l], tr_istd[l], bw_mg[l], bw_mgx[l], lsum(l),
+                                                             (int)opt_train_reverse);
         f64_to_f32_kernel<<<1, 128, 0, stream>>>(lsum(l) + 2 * c.cout, garr(c.b), c.cout, (double)alpha);
         DDPM_LAUNCH_CHECK();
         cnt_launches += 3;

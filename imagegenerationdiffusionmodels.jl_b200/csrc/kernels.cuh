@@ -407,9 +407,12 @@ __global__ void bn_inference_affine_kernel(const float* __restrict__ gamma, cons
 // a = relu(y*scale + shift) over valid pixels
 template <typename TA>
 __global__ void __launch_bounds__(256)
-bn_apply_kernel(View<const TA> y, View<TA> a, Geo g, int C, const float* __restrict__ scale, const float* __restrict__ shift) {
+bn_apply_kernel(View<const TA> y, View<TA> a, Geo g, int C, const float* __restrict__ scale, const float* __restrict__ shift,
+                int rev = 0) {
+    // rev: blocks walk the tensor from its end.  The conv that produced y wrote it front to back, so its tail is what the
+    // L2 still holds; this kernel then leaves the FRONT of a in L2, where the next (front-to-back) conv starts reading
     const int groups = C / 8;
-    long long idx = (long long)blockIdx.x * 256 + threadIdx.x;
+    long long idx = (long long)(rev ? gridDim.x - 1 - blockIdx.x : blockIdx.x) * 256 + threadIdx.x;
     long long pix = idx / groups;
     int c0 = (int)(idx - pix * groups) * 8;
     if (pix >= (long long)g.N * g.H * g.W) return;
@@ -429,9 +432,9 @@ bn_apply_kernel(View<const TA> y, View<TA> a, Geo g, int C, const float* __restr
 template <typename TA>
 __global__ void __launch_bounds__(256)
 bn_apply_pool_kernel(View<const TA> y, View<TA> a, View<TA> pooled, Geo gf, Geo gc, int C,
-                     const float* __restrict__ scale, const float* __restrict__ shift) {
+                     const float* __restrict__ scale, const float* __restrict__ shift, int rev = 0) {
     const int groups = C / 8;
-    long long idx = (long long)blockIdx.x * 256 + threadIdx.x;
+    long long idx = (long long)(rev ? gridDim.x - 1 - blockIdx.x : blockIdx.x) * 256 + threadIdx.x;
     long long pix = idx / groups;
     int c0 = (int)(idx - pix * groups) * 8;
     if (pix >= (long long)gc.N * gc.H * gc.W) return;
@@ -604,8 +607,8 @@ template <typename TA, typename TG, int PASS>
 __global__ void __launch_bounds__(256, PASS == 2 ? 4 : 2)
 bn_bwd_kernel(View<const TA> y, View<const TG> da, View<TG> dy, Geo g, int C, const float* __restrict__ scale,
               const float* __restrict__ shift, const float* __restrict__ mean, const float* __restrict__ istd,
-              const float* __restrict__ mg, const float* __restrict__ mgx, double* __restrict__ sums) {
-    // blocks stride over 512-pixel chunks; per-thread partial sums live in registers for the whole block and are reduced
+              const float* __restrict__ mg, const float* __restrict__ mgx, double* __restrict__ sums, int rev = 0) {
+    // blocks stride over 512-pixel chunks (rev: from the last chunk down -- da was just written front to back); per-thread partial sums live in registers for the whole block and are reduced
     // ONCE through a [lanes][C] shared-memory table (per-chunk shared float atomics were 32-way contended)
     __shared__ float red[2][256 * 8];
     const int t = threadIdx.x;
@@ -630,7 +633,8 @@ bn_bwd_kernel(View<const TA> y, View<const TG> da, View<TG> dy, Geo g, int C, co
     }
     const int HW = g.H * g.W;
     const long long nchunks = (total + BNB_PIX_PER_BLOCK - 1) / BNB_PIX_PER_BLOCK;
-    for (long long chunk = blockIdx.x; chunk < nchunks; chunk += gridDim.x) {
+    for (long long ck = blockIdx.x; ck < nchunks; ck += gridDim.x) {
+        const long long chunk = rev ? nchunks - 1 - ck : ck;
         const long long pbeg = chunk * BNB_PIX_PER_BLOCK;
         long long pend = pbeg + BNB_PIX_PER_BLOCK;
         if (pend > total) pend = total;

@@ -482,6 +482,7 @@ int ddpm_set_option(ddpm_handle* h, const char* key, int64_t value) {
     else if (k == "tc_reverse") { tc::state().reverse = value != 0; for (auto& kv : e.infer_sets) kv.second->drop_graphs(); }
     else if (k == "tc_pdl") { tc::state().pdl = value != 0; for (auto& kv : e.infer_sets) kv.second->drop_graphs(); }
     else if (k == "conv1_tc") { e.opt_conv1_tc = value; for (auto& kv : e.infer_sets) kv.second->drop_graphs(); }
+    else if (k == "train_reverse") { e.opt_train_reverse = value != 0; e.drop_train_graphs(); }
     else if (k == "bnbwd_blocks") { DDPM_CHECK(value >= 1 && value <= 8, "bnbwd_blocks must be 1..8"); e.opt_bnbwd_blocks = value; e.drop_train_graphs(); }
     else if (k == "fuse_final") { e.opt_fuse_final = value; for (auto& kv : e.infer_sets) kv.second->drop_graphs(); }
     else if (k == "tc_role_profile") {

@@ -149,7 +149,8 @@ int ddpm_comm_init(ddpm_handle*, const void* id, int rank, int world, int sync_b
  *   bn_p2p (1: SyncBN statistics exchanged over peer-memory mailboxes inside the finalize kernels; 0: one NCCL all-reduce
  *   per layer), dp_skip (0; TIMING ONLY, results become wrong: bit 0 skips the gradient all-reduces, bit 1 the SyncBN ones),
  *   fuse_bn (1: train-mode BatchNorm reductions inside the tcgen05 conv / data-gradient epilogues),
- *   bnbwd_blocks (4: resident blocks per SM of the second BatchNorm-backward pass),
+ *   bnbwd_blocks (4: resident blocks per SM of the second BatchNorm-backward pass), train_reverse (1: the BatchNorm apply
+ *   and backward kernels of a training step walk their tensors from the end, where the producing conv left them in L2),
  *   loss_scale_log2 (0: extra power-of-two factor on the static loss scale of the 16-bit gradient tensors).
  * None of them changes results beyond the documented rounding of the selected kernels.
  * Counter keys: launches, n_params, tc_available, uses_tc, bn_p2p_active, skipped_steps (updates skipped by the overflow guard: a
