@@ -927,7 +927,6 @@ struct State {
     int pair_mask = 31;
     bool pdl = true;            // launch the tcgen05 conv kernels as programmatic dependents of their stream predecessor
     bool reverse = true;        // option tc_reverse: alternate the tile direction between consecutive layers of the sampler
-    int rev_next = 0;           // direction of the NEXT conv launch (set by the engine's inference forward, consumed by the launch)
     // per-DEVICE launch bookkeeping (function attributes and occupancy are properties of a (kernel, device) pair)
     std::map<const void*, int> smem_attr;     // kernel -> dynamic shared memory size already granted on this device
     std::map<const void*, int> max_pairs;     // kernel -> resident CTA pairs on this device
@@ -1084,7 +1083,7 @@ struct BnFuse {
 // default CTA-pair variants carry the fused code; otherwise the caller runs the stand-alone reduction kernel).
 template <typename TIn, typename TOut>
 bool conv3x3(cudaStream_t st, const TIn* s0, int C0, const TIn* s1, int C1, const TIn* Wt, int Cout, TOut* out,
-             const Geo& g, const float* shift, int relu, const BnFuse* bn = nullptr, bool* bn_done = nullptr) {
+             const Geo& g, const float* shift, int relu, const BnFuse* bn = nullptr, bool* bn_done = nullptr, int rev = 0) {
     if (bn_done) *bn_done = false;
     if (!available()) return false;
     if constexpr (std::is_same<TIn, float>::value && std::is_same<TOut, float>::value) {
@@ -1135,8 +1134,7 @@ bool conv3x3(cudaStream_t st, const TIn* s0, int C0, const TIn* s1, int C1, cons
     p.out = out; p.out_cs = Cout; p.g = g; p.g_out = g; p.shift = shift; p.relu = relu;
     p.num_m_tiles = cdiv(g.npos, TC_BM);
     p.chunk1_src1 = (s1 != nullptr) ? 1 : 0;
-    p.rev = state().reverse ? state().rev_next : 0;
-    state().rev_next = 0;
+    p.rev = (state().reverse && rev) ? 1 : 0;
     p.dbg = state().dbg;
     const int bm = (bn && bn->mode && !p.dbg) ? bn->mode : 0;
     if (bm) {
@@ -1200,7 +1198,7 @@ bool conv3x3(cudaStream_t st, const TIn* s0, int C0, const TIn* s1, int C1, cons
 // Last 3x3 conv (64=>64 @32x32) of the sampler with the final 1x1 conv and the reverse update fused in its epilogue
 template <typename TIn>
 bool conv3x3_final(cudaStream_t st, const TIn* s0, const TIn* Wt, const Geo& g, const float* shift, float* x, const float* z,
-                   const float* wf, const float* bf, const float scal[4], int final_clamp) {
+                   const float* wf, const float* bf, const float scal[4], int final_clamp, int rev = 0) {
     if (!available()) return false;
     if constexpr (sizeof(TIn) != 2) {
         return false;
@@ -1210,8 +1208,7 @@ bool conv3x3_final(cudaStream_t st, const TIn* s0, const TIn* Wt, const Geo& g, 
     p.out = nullptr; p.out_cs = 64; p.g = g; p.g_out = g; p.shift = shift; p.relu = 1;
     p.num_m_tiles = cdiv(g.npos, TC_BM);
     p.chunk1_src1 = 0;
-    p.rev = state().reverse ? state().rev_next : 0;
-    state().rev_next = 0;
+    p.rev = (state().reverse && rev) ? 1 : 0;
     p.dbg = nullptr;
     p.x = x; p.z = z; p.wf = wf; p.bf = bf;
     p.sig = scal[0]; p.sqa = scal[1]; p.sqp = scal[2]; p.sqv = scal[3];
@@ -1228,7 +1225,7 @@ bool conv3x3_final(cudaStream_t st, const TIn* s0, const TIn* Wt, const Geo& g, 
 
 // ConvTranspose((2,2), 128 => 64, stride=2): [pos16][128] x Wt[q*64+co][128]^T, pixel-shuffle epilogue + bias
 template <typename TA>
-bool up2(cudaStream_t st, const TA* a6, const TA* Wt, TA* u, const Geo& gi, const Geo& go, const float* bias) {
+bool up2(cudaStream_t st, const TA* a6, const TA* Wt, TA* u, const Geo& gi, const Geo& go, const float* bias, int rev = 0) {
     if (!available()) return false;
     if constexpr (sizeof(TA) != 2) {
         return false;
@@ -1237,8 +1234,7 @@ bool up2(cudaStream_t st, const TA* a6, const TA* Wt, TA* u, const Geo& gi, cons
     p.out = u; p.out_cs = 64; p.g = gi; p.g_out = go; p.shift = bias; p.relu = 0;
     p.num_m_tiles = cdiv(gi.npos, TC_BM);
     p.chunk1_src1 = 0;
-    p.rev = state().reverse ? state().rev_next : 0;
-    state().rev_next = 0;
+    p.rev = (state().reverse && rev) ? 1 : 0;
     CUtensorMap a0 = make_map_2d<TA>(a6 - (size_t)gi.guard * 128, (uint64_t)gi.alloc_positions(), 128, TC_BM);
     CUtensorMap w = make_map_2d<TA>(Wt, 256, 128, 64);
     launch<1, 2, 64, WP_16, 1, 0, TA, TA>(st, a0, a0, w, a0, p, 4);

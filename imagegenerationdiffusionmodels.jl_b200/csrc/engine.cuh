@@ -314,7 +314,7 @@ struct Engine {
 
     template <typename TA, typename TG>
     void conv3(const Tensor& s0, const Tensor* s1, int l, Tensor& out, bool infer_weights, const float* shift, int relu,
-               double* stats);
+               double* stats, int rev = 0);
     template <typename TA, typename TG>
     void dgrad3(ActSet& s, const Tensor& dy, int l, Tensor& out, int out_c_total, int bn_layer = 0, bool* bn_done = nullptr);
     tc::BnFuse bn_bwd_fuse(ActSet& s, int bn_layer);
@@ -706,7 +706,7 @@ inline void Engine::prepare_infer_affine() {
 // Conv((3,3), cin=>cout, pad=1) of layer l on s0 (and s1 concatenated along channels)
 template <typename TA, typename TG>
 void Engine::conv3(const Tensor& s0, const Tensor* s1, int l, Tensor& out, bool infer_weights, const float* shift,
-                   int relu, double* stats) {
+                   int relu, double* stats, int rev) {
     const void* weights = infer_weights ? Wfi[l] : Wf[l];
     const ConvSpec& c = kConv[l];
     const Geo& g = out.g;
@@ -719,7 +719,7 @@ void Engine::conv3(const Tensor& s0, const Tensor* s1, int l, Tensor& out, bool 
         bf.mode = (stats && opt_fuse_bn) ? 1 : 0; bf.sums = stats; bf.C = c.cout;
         bool fused = false;
         bool ok = tc::conv3x3<TA, TA>(stream, s0.pos0<TA>(), C0, s1 ? s1->pos0<TA>() : nullptr, C1, (const TA*)weights, c.cout,
-                                      out.pos0<TA>(), g, shift, relu, &bf, &fused);
+                                      out.pos0<TA>(), g, shift, relu, &bf, &fused, rev);
         if (ok) {
             cnt_launches += 1;
             if (stats && !fused) {
@@ -831,9 +831,7 @@ void Engine::forward_t(ActSet& s, const float* x_dev, const int* ts_dev, int t_f
         } else {
             // launch order of an evaluation: first conv, L2, pool, L3, L4, L5, L6, ConvTranspose, L7, L8, L9, L10; the tile
             // direction alternates along it (the first conv and the pool run front to back), see TcParams::rev
-            tc::state().rev_next = (l == 2 || l == 3 || l == 5 || l == 8 || l == 10) ? 1 : 0;
-            conv3<TA, TG>(in0, in1, l, s.a[l], true, inf_shift[l], 1, nullptr);
-            tc::state().rev_next = 0;
+            conv3<TA, TG>(in0, in1, l, s.a[l], true, inf_shift[l], 1, nullptr, (l == 2 || l == 3 || l == 5 || l == 8 || l == 10) ? 1 : 0);
         }
     };
 
@@ -874,11 +872,8 @@ void Engine::forward_t(ActSet& s, const float* x_dev, const int* ts_dev, int t_f
         const Geo& gi = s.a[6].g;
         const Geo& go = s.u.g;
         bool done = false;
-        if (use_tc()) {
-            tc::state().rev_next = train ? 0 : 1;
-            done = tc::up2<TA>(stream, s.a[6].pos0<TA>(), (const TA*)Wt, s.u.pos0<TA>(), gi, go, arr(kUpB));
-            tc::state().rev_next = 0;
-        }
+        if (use_tc())
+            done = tc::up2<TA>(stream, s.a[6].pos0<TA>(), (const TA*)Wt, s.u.pos0<TA>(), gi, go, arr(kUpB), train ? 0 : 1);
         if (!done) {
             EpiUp2<TA> epi{s.u.view<TA>(), gi, go, arr(kUpB), 64, nullptr};
             launch_igemm_simt<TA, TA>(stream, s.a[6].cview<TA>(), 128, View<const TA>{nullptr, 0}, 0, (const TA*)Wt, 256, 1,
@@ -1288,10 +1283,9 @@ void Engine::sample_steps_t(ActSet& s, float* x_dev, const float* z_dev, int N, 
         const float* sc = &h_samp[(size_t)(t - 1) * 4];
         if (use_tc() && opt_fuse_final) {
             forward_t<TA, TG>(s, x_dev, nullptr, t, Mode::Infer, false, true);
-            tc::state().rev_next = 1;                   // layer 10 of the alternating tile direction (see forward_t)
             bool fused = tc::conv3x3_final<TA>(stream, s.a[9].pos0<TA>(), (const TA*)Wfi[10], s.a[9].g, inf_shift[10], x_dev, zstep,
-                                              arr(kFinalW), arr(kFinalB), sc, t == 2 ? 1 : 0);
-            tc::state().rev_next = 0;
+                                              arr(kFinalW), arr(kFinalB), sc, t == 2 ? 1 : 0,
+                                              1 /* layer 10 of the alternating tile direction, see forward_t */);
             if (fused) {
                 cnt_launches += 1;
                 continue;
