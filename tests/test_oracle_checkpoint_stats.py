@@ -91,3 +91,22 @@ def test_the_statistics_pin_sees_wrong_semantics(oracle, mutate, T):
     T = 1000 instead of 500: 0.42; the true semantics: 0.07)."""
     r = _layer_stats(oracle, os.path.join(FIX, "trained_model.bson"), T, NB_MUT, mutate=mutate)
     assert max(r) > 0.18, (mutate, T, r)
+
+
+def test_recorded_sweep_over_all_shipped_checkpoints():
+    """tests/golden/checkpoint_stats_all.json (made by tests/golden/make_checkpoint_stats.py in the build container, where
+    /root/reference is mounted): the same comparison for ALL 20 checkpoints the reference ships, plus the oracle's train-mode
+    eps-MSE at each of them, which must fall along the epochs and end at the ~0.23 of the published training_loss.png."""
+    import json
+    from conftest import GOLDEN
+    d = json.load(open(os.path.join(GOLDEN, "checkpoint_stats_all.json")))
+    assert len(d) == 20
+    ep = {int(k.split("_")[2].split(".")[0]): v for k, v in d.items() if k.startswith("ddpm_epoch_")}
+    assert sorted(ep) == list(range(5, 100, 5))
+    for e, v in ep.items():
+        if e >= 15:                                  # earlier checkpoints: the moving average lags the fast-moving weights
+            assert v["max_rel_l2"] < 0.10 and v["median_rel_l2"] < 0.03, (e, v)
+    assert d["trained_model.bson"]["max_rel_l2"] < 0.10 and d["trained_model.bson"]["median_rel_l2"] < 0.03
+    loss = [ep[e]["train_mode_eps_mse"] for e in sorted(ep)]
+    assert loss[0] > 0.7 and all(loss[i + 2] < loss[i] for i in range(len(loss) - 2)), loss     # falls (one 5-epoch blip allowed)
+    assert abs(loss[-1] - 0.23) < 0.02, loss[-1]
