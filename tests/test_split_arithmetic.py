@@ -33,3 +33,36 @@ def test_two_part_bf16_split_is_16_bit_accurate():
     big = np.maximum(np.abs(a), np.abs(b)).astype(np.float16)
     ulp = np.maximum(np.spacing(big).astype(np.float32), (2.0 ** -15 * scale).astype(np.float32))
     assert (np.abs(a.astype(np.float32) - b.astype(np.float32)) <= 1.01 * ulp).all()
+
+
+def test_folded_constant_rides_on_the_contraction_exactly():
+    """conv1f_tc_kernel (csrc/conv1_tc.cuh, second version): the K = 64 rows the kernel builds, restated in NumPy.
+       A row = [(x_hi, x_lo) x 9 taps | x_hi x 9 | onehot(cls) x 3 | 0 x 10]
+       B row = [(w_hi, w_hi) x 9      | w_lo x 9 | E_hi(9 cls), E_mid(9), E_lo(9) | 0 x 10]
+    Claims: (1) every entry is BF16-representable; (2) the three BF16 parts of E[cls] reproduce the FP32 value exactly, so the
+    contraction equals  split-conv + E[cls]  with no extra error; (3) a halo row (all-zero A row) contracts to exactly 0;
+    (4) rounding then ReLU on the packed 16-bit value equals ReLU then rounding (the epilogue does the former)."""
+    rng = np.random.default_rng(1)
+    n = 20000
+    x = (3.0 * rng.standard_normal((n, 9))).astype(np.float32)
+    w = (0.15 * rng.standard_normal(9)).astype(np.float32)
+    E = (2.0 * rng.standard_normal(9)).astype(np.float32)               # E[cls][co]*scale + shift for one output channel
+    cls = rng.integers(0, 9, n)
+    xh = _bf16(x); xl = _bf16(x - xh)
+    wh = _bf16(w); wl = _bf16(w - wh)
+    e0 = _bf16(E); r1 = (E - e0).astype(np.float32); e1 = _bf16(r1); e2 = _bf16((r1 - e1).astype(np.float32))
+    assert np.array_equal((e0.astype(np.float64) + e1 + e2).astype(np.float32), E)          # (2): 24 significand bits
+    A = np.zeros((n, 64), np.float32)
+    A[:, 0:18:2] = xh; A[:, 1:18:2] = xl; A[:, 18:27] = xh
+    onehot = np.eye(9, dtype=np.float32)[cls]
+    A[:, 27:36] = onehot; A[:, 36:45] = onehot; A[:, 45:54] = onehot
+    B = np.zeros(64, np.float32)
+    B[0:18:2] = wh; B[1:18:2] = wh; B[18:27] = wl; B[27:36] = e0; B[36:45] = e1; B[45:54] = e2
+    assert np.array_equal(_bf16(A), A) and np.array_equal(_bf16(B), B)                        # (1)
+    got = (A.astype(np.float64) * B).sum(1)
+    want = ((xh.astype(np.float64) * wh).sum(1) + (xl.astype(np.float64) * wh).sum(1) + (xh.astype(np.float64) * wl).sum(1)
+            + E[cls].astype(np.float64))
+    assert np.allclose(got, want, rtol=0, atol=1e-12)                                         # (2) in exact arithmetic
+    assert (np.zeros(64, np.float32) * B).sum() == 0.0                                        # (3)
+    v = got.astype(np.float32)
+    assert np.array_equal(np.maximum(v.astype(np.float16), np.float16(0)), np.maximum(v, 0).astype(np.float16))   # (4)
